@@ -1,0 +1,173 @@
+/*
+ * lgp_b200.h -- C ABI of liblgpb200.so, the B200-native (sm_100a) GP-fitting hot path:
+ * Gram-matrix build -> equilibrated, jittered dense Cholesky -> triangular solves, log-determinant,
+ * inverse-from-factor and the hyperparameter-gradient contraction.
+ *
+ * The reference (Gattocrucco/lsqfitgp 0.22.dev0) is pure Python/JAX and has no FFI for this path; each
+ * entry point below names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is caller-owned DEVICE memory unless stated otherwise (torch tensors on the Python side)
+ *   - matrices are row-major float64 with an explicit leading dimension in elements
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it and never synchronise
+ *   - return value: 0 = launched ok; <0 = argument/launch error (LGP_ERR_*).  Numerical failure of the
+ *     factorisation is reported in the device-side `info` word (LAPACK convention, 1-based pivot index)
+ *   - no allocation happens inside the library
+ */
+#ifndef LGP_B200_H
+#define LGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGP_ABI_VERSION 1
+
+#define LGP_OK 0
+#define LGP_ERR_BADARG (-1)
+#define LGP_ERR_ALIGN (-2) /* pointer not 16-byte aligned or odd leading dimension */
+#define LGP_ERR_CUDA (-3)
+#define LGP_ERR_UNSUPPORTED (-4)
+
+typedef void *lgp_stream_t;
+
+int lgp_abi_version(void);
+/* static string: compiler, arch, build flags */
+const char *lgp_build_info(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gram matrix of a sum of products of isotropic kernel factors.
+ * Replaces GPElements._makecovblock_points -> CrossKernel.__call__ -> IsotropicKernel core
+ * (src/lsqfitgp/_GP/_elements.py:554-579, _Kernel/_crosskernel.py:192-200, _Kernel/_ops.py:292-326,
+ *  _Kernel/_isotropic.py:61-81, _Kernel/_util.py:74-99, _kernels/_basic.py:34-75,315-343,
+ *  _kernels/_matern.py:29-76, _special/_bessel.py:101-110, _Kernel/_alg.py:48-82).
+ *
+ *   K[i][j] = sum_terms prod_{factors f in term} amp_f * core_f( r2_f(i,j) )
+ *   r2_f(i,j) = sum_{fields d in dimmask_f, ascending} ( (x[d][i]-loc_x)/scale_x - (y[d][j]-loc_y)/scale_y )^2
+ * with every operation individually rounded (no FMA contraction), as the reference does.
+ * ---------------------------------------------------------------------------------------------- */
+#define LGP_K_EXPQUAD 0  /* exp(-r2/2)                                   _basic.py:75 */
+#define LGP_K_MATERNP 1  /* half-integer Matern, nu = ipar + 1/2; par0 = offset added to (2p+1)*r2
+                            (1e-30 for Maternp, 0 for Matern(nu=p+1/2))   _matern.py:48-49,74-76 */
+#define LGP_K_CAUCHY 2   /* (1 + r2^(par0/2)/par1)^(-par1/par0)           _basic.py:339-343 */
+#define LGP_K_WHITE 3    /* prod_d (x_d == y_d)                           _basic.py:59 */
+#define LGP_K_CONSTANT 4 /* 1                                             _basic.py:46 */
+
+#define LGP_MAX_FACTORS 8
+#define LGP_MAX_DIMS 32
+
+typedef struct lgp_factor {
+    int32_t kind;     /* LGP_K_* */
+    int32_t term;     /* additive term index; factors with equal term multiply */
+    uint32_t dimmask; /* bit d set: field d enters r2 */
+    int32_t ipar;     /* MATERNP: p */
+    double scale_x, scale_y, loc_x, loc_y;
+    double par0, par1;
+    double amp;
+} lgp_factor_t;
+
+/* x: ndim fields of n points, x[d*ldx + i]; y likewise (m points).  K_out[i*ldk + j], i<n, j<m.
+ * `factors` is HOST memory (copied into kernel parameters).
+ * flags: LGP_GRAM_SYMMETRIC asserts x==y (same pointer): lower tiles are evaluated once and mirrored. */
+#define LGP_GRAM_SYMMETRIC 1
+int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
+                 int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, double *K_out, int64_t ldk,
+                 int flags);
+
+/* Reverse-mode contraction of the Gram build: for the symmetric case x==y,
+ *   out[f*(3)+0] = sum_ij G_ij * dK_ij/d amp_f
+ *   out[f*(3)+1] = sum_ij G_ij * dK_ij/d log(scale_f)        (scale_x == scale_y == scale_f)
+ *   out[f*(3)+2] = sum_ij G_ij * dK_ij/d par1_f              (Cauchy beta; 0 otherwise)
+ * with G_ij = w_ij * (Ginv[i][j] - b_i b_j) read from the LOWER triangle of Ginv (w = 2 off-diagonal, 1 on it).
+ * This is dK_vjp(invK) - dK_vjp(outer(invKr, invKr)) of Chol.minus_log_normal_density collapsed into one pass
+ * (src/lsqfitgp/_linalg/_decomp.py:505-509; src/lsqfitgp/_fit.py:687-702).  out is device memory, 3*nfactors doubles. */
+int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
+                     int64_t ldx, int64_t n, const double *Ginv, int64_t ldg, const double *b, double *out);
+
+/* ------------------------------------------------------------------------------------------------
+ * BART Gram (fast path of BART._correlation: src/lsqfitgp/_kernels/_bart.py:628-757, with the
+ * bracket folding of BART.correlation :415-455 done by the caller).
+ * ix[d*ldx + i], iy[d*ldy + j]: int32 bin indices in [0, nsplits[d]]; w[p] weights; rows: `nrows` rows of width
+ * `width` (1..3) of non-termination probabilities, deepest bracket first (row-major, host memory); gamma scalar.
+ * ---------------------------------------------------------------------------------------------- */
+int lgp_gram_bart(lgp_stream_t stream, int p, const int32_t *nsplits /*host*/, const double *w /*host*/,
+                  const double *rows /*host*/, int nrows, int width, double gamma, double amp,
+                  const double *psi /*device: psi[k] = digamma(k), k <= max(nsplits)+1; needed for width 3*/,
+                  const int32_t *ix, int64_t ldx, int64_t n, const int32_t *iy, int64_t ldy, int64_t m,
+                  double *K_out, int64_t ldk, int flags);
+/* fills HOST buffer psi_out[k] = digamma(k), k = 1..len-1 (psi_out[0] = -inf): jspecial.digamma of integers
+ * (_bart.py:735-743) by an extended-precision recurrence */
+int lgp_bart_digamma_table(double *psi_out, int64_t len);
+
+/* ------------------------------------------------------------------------------------------------
+ * FP64 GEMM on the DMMA tensor pipe:  C[i][j] (+)= alpha * sum_k Aop[i][k]*Bop[j][k]
+ *   a_kmajor: Aop[i][k] = A[i*lda+k], else A[k*lda+i];  b_kmajor: Bop[j][k] = B[j*ldb+k], else B[k*ldb+j]
+ * flags: LGP_GEMM_*.  Replaces the dgemm/dsyrk custom calls under `@`/einsum in _decomp.py:409,420,472.
+ * ---------------------------------------------------------------------------------------------- */
+#define LGP_GEMM_LOWER 1
+#define LGP_GEMM_BETA0 2
+#define LGP_GEMM_A_LOWER_K 4
+#define LGP_GEMM_B_LOWER_K 8
+#define LGP_GEMM_A_UPPER_K 16
+#define LGP_GEMM_B_UPPER_K 32
+int lgp_dgemm(lgp_stream_t stream, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
+              const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int flags);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cholesky with lsqfitgp's equilibration + Gershgorin jitter (Chol.__init__,
+ * src/lsqfitgp/_linalg/_decomp.py:245-255,349-361,380-393):
+ *   s_i = 2^rint(log2(K_ii)/2) (1 if K_ii == 0);  Kt = K/s/s^T;  eps = epsrel*max_i sum_j |Kt_ij| + epsabs;
+ *   Kt_ii += eps;  Lt = chol(Kt);  L = diag(s) Lt.
+ * The factor is kept as (Lt, s): W holds Lt in the lower triangle of an npad x npad matrix
+ * (npad = n rounded up to 128, identity padding), aux holds s, 1/s, diag(Lt), the scalars and the
+ * inverted 128x128 diagonal blocks.
+ *   K      : n x n input (ldk); only read.  addmat (optional, may be NULL): n x n matrix added to K
+ *            (GPCompute._solver `Kxx + ycov`, src/lsqfitgp/_GP/_compute.py:84-85);
+ *            adddiag (optional): n-vector added to the diagonal.
+ *   epsrel < 0 means 'auto' = n * 2^-52.
+ *   aux scalars (doubles at aux + 3*npad): [0] max row abs-sum of Kt, [1] eps, [2] reserved,
+ *            [3] min_i s_i^2  (so Chol.eps = [1]*[3]); [4] = sum_i log(L_ii) again (written by the final reduction),
+ *            [5] = 0
+ *   info   : device int32; 0 on success, else 1-based index of the first non-positive/NaN pivot.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t lgp_chol_npad(int64_t n);
+int64_t lgp_chol_aux_doubles(int64_t n);
+#define LGP_AUX_S(npad) (0)
+#define LGP_AUX_SINV(npad) (npad)
+#define LGP_AUX_DIAG(npad) (2 * (npad))
+#define LGP_AUX_SCALARS(npad) (3 * (npad))
+#define LGP_AUX_INVDIAG(npad) (3 * (npad) + 16)
+int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const double *addmat, int64_t ldadd,
+                    const double *adddiag, int64_t n, double epsrel, double epsabs, double *W, int64_t ldw,
+                    double *aux, int32_t *info);
+
+/* B (n x m, ldb even, 16-byte aligned) <- L^-1 B (trans=0) or L^-T B (trans=1), L = diag(s) Lt.
+ * Replaces jax.scipy.linalg.solve_triangular in _decomp.py:402-403,407-408,419,426,439,467-469. */
+int lgp_chol_solve(lgp_stream_t stream, const double *W, int64_t ldw, const double *aux, int64_t n, double *B,
+                   int64_t ldb, int64_t m, int trans);
+
+/* Y (n x m) = L X (trans=0) or L^T X (trans=1).  Chol.correlate / back_correlate (_decomp.py:429-435). */
+/* tmp (n x m, ldt even, 16-byte aligned) is scratch, required for trans=1 only. X, tmp: ld even, aligned. */
+int lgp_chol_mult(lgp_stream_t stream, const double *W, int64_t ldw, const double *aux, int64_t n, const double *X,
+                  int64_t ldx, int64_t m, double *Y, int64_t ldy, double *tmp, int64_t ldt, int trans);
+
+/* Lout (n x n) = L = diag(s) Lt with zeros above the diagonal. */
+int lgp_chol_get_factor(lgp_stream_t stream, const double *W, int64_t ldw, const double *aux, int64_t n,
+                        double *Lout, int64_t ldl);
+
+/* Kinv (npad x npad, ld = ldk) lower triangle <- (L L^T)^-1 via TRTRI + LAUUM on the DMMA pipe
+ * (2n^3/3 flop instead of the reference's L^-1 I and invL^T invL = 3n^3, _decomp.py:471-472).
+ * scratch: npad x npad doubles (ld = npad). */
+int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const double *aux, int64_t n,
+                     double *scratch, double *Kinv, int64_t ldk);
+
+/* out[0] = sum_i log L_ii ; out[1] = sum_i a_i^2 for a (n-vector, may be NULL -> 0).
+ * The reductions of Chol.minus_log_normal_density (value), _decomp.py:484-488. */
+int lgp_chol_logdet_quad(lgp_stream_t stream, const double *aux, int64_t n, const double *a, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGP_B200_H */

@@ -1,0 +1,118 @@
+"""ctypes binding of liblgpb200.so (the C ABI declared in include/lgp_b200.h).
+
+The library is the product path: there is no CPU or PyTorch fallback. Importing this module never
+needs a GPU (so the CPU test tier can check that every declared symbol is exported); calling a
+compute entry point without the library or without a CUDA device raises.
+"""
+
+import ctypes
+import os
+import pathlib
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / 'csrc' / 'liblgpb200.so'
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int32_p = ctypes.POINTER(ctypes.c_int32)
+
+LGP_OK = 0
+ERRORS = {-1: 'bad argument', -2: 'misaligned pointer or odd leading dimension', -3: 'CUDA launch error',
+          -4: 'unsupported configuration'}
+
+# kernel kinds (lgp_b200.h)
+K_EXPQUAD, K_MATERNP, K_CAUCHY, K_WHITE, K_CONSTANT = range(5)
+MAX_FACTORS = 8
+MAX_DIMS = 32
+
+GEMM_LOWER, GEMM_BETA0, GEMM_A_LOWER_K, GEMM_B_LOWER_K, GEMM_A_UPPER_K, GEMM_B_UPPER_K = 1, 2, 4, 8, 16, 32
+
+
+class Factor(ctypes.Structure):
+    """ struct lgp_factor (include/lgp_b200.h) """
+    _fields_ = [
+        ('kind', ctypes.c_int32),
+        ('term', ctypes.c_int32),
+        ('dimmask', ctypes.c_uint32),
+        ('ipar', ctypes.c_int32),
+        ('scale_x', ctypes.c_double),
+        ('scale_y', ctypes.c_double),
+        ('loc_x', ctypes.c_double),
+        ('loc_y', ctypes.c_double),
+        ('par0', ctypes.c_double),
+        ('par1', ctypes.c_double),
+        ('amp', ctypes.c_double),
+    ]
+
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_dbl = ctypes.c_double
+
+# name -> (restype, argtypes); must list every function declared in include/lgp_b200.h
+SIGNATURES = {
+    'lgp_abi_version': (_int, []),
+    'lgp_build_info': (ctypes.c_char_p, []),
+    'lgp_gram_iso': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int]),
+    'lgp_gram_iso_vjp': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    'lgp_gram_bart': (_int, [_vp, _int, c_int32_p, c_double_p, c_double_p, _int, _int, _dbl, _dbl, _vp,
+                             _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int]),
+    'lgp_bart_digamma_table': (_int, [c_double_p, _i64]),
+    'lgp_dgemm': (_int, [_vp, _int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _vp, _i64, _int]),
+    'lgp_chol_npad': (_i64, [_i64]),
+    'lgp_chol_aux_doubles': (_i64, [_i64]),
+    'lgp_chol_factor': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, _i64, _vp, _vp]),
+    'lgp_chol_solve': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _int]),
+    'lgp_chol_mult': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _int]),
+    'lgp_chol_get_factor': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64]),
+    'lgp_chol_inverse': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64]),
+    'lgp_chol_logdet_quad': (_int, [_vp, _vp, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load liblgpb200.so (built in-tree by `__graft_entry__.build()` / `make -C lsqfitgp_b200/csrc`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise LibraryMissing(
+            f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            f'or `make -C {LIB_PATH.parent}`. There is no CPU fallback.')
+    lib = ctypes.CDLL(os.fspath(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != LGP_OK:
+        raise RuntimeError(f'{what} failed: {ERRORS.get(rc, rc)}')
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """ device pointer of a torch tensor (or None) """
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('lsqfitgp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    load()

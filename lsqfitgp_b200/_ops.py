@@ -1,0 +1,221 @@
+"""Thin torch-tensor wrappers over the C ABI (one function per entry point of include/lgp_b200.h).
+
+torch is used for device memory and streams only; all arithmetic happens in liblgpb200.so.
+"""
+
+import ctypes
+
+import numpy
+import torch
+
+from . import _lib
+from ._lib import ptr, stream_ptr, check
+
+f64 = torch.float64
+
+
+def _even(m):
+    return m + (m & 1)
+
+
+def aligned_empty(rows, cols, device, zero=False):
+    """ (rows, cols) float64 view with an even leading dimension and 16-byte aligned base """
+    ld = _even(max(cols, 1))
+    buf = (torch.zeros if zero else torch.empty)((max(rows, 1), ld), dtype=f64, device=device)
+    return buf[:rows, :cols]
+
+
+def as_aligned(t):
+    """ return a 2-d float64 tensor on the device with unit column stride, even row stride, aligned base """
+    assert t.ndim == 2 and t.dtype == f64
+    if (t.stride(1) == 1 and t.stride(0) % 2 == 0 and t.stride(0) >= t.shape[1] and t.data_ptr() % 16 == 0):
+        return t
+    out = aligned_empty(t.shape[0], t.shape[1], t.device)
+    out.copy_(t)
+    return out
+
+
+def dgemm(A, B, C, *, a_kmajor, b_kmajor, M, N, K, alpha=1.0, flags=0):
+    lib = _lib.load()
+    check(lib.lgp_dgemm(stream_ptr(), int(a_kmajor), int(b_kmajor), M, N, K, float(alpha), ptr(A), A.stride(0),
+                        ptr(B), B.stride(0), ptr(C), C.stride(0), flags), 'lgp_dgemm')
+    return C
+
+
+# ---------------------------------------------------------------------------------------------
+# Gram
+# ---------------------------------------------------------------------------------------------
+
+def make_factors(descs):
+    """ descs: list of dicts with the fields of struct lgp_factor -> ctypes array """
+    arr = (_lib.Factor * len(descs))()
+    for a, d in zip(arr, descs):
+        a.kind = d['kind']
+        a.term = d['term']
+        a.dimmask = d['dimmask']
+        a.ipar = d.get('ipar', 0)
+        a.scale_x = d.get('scale_x', 1.0)
+        a.scale_y = d.get('scale_y', 1.0)
+        a.loc_x = d.get('loc_x', 0.0)
+        a.loc_y = d.get('loc_y', 0.0)
+        a.par0 = d.get('par0', 0.0)
+        a.par1 = d.get('par1', 0.0)
+        a.amp = d.get('amp', 1.0)
+    return arr
+
+
+def gram_iso(descs, x, y, out=None, symmetric=False):
+    """ x: (ndim, n) float64 device tensor (one row per field), y: (ndim, m). Returns (n, m). """
+    lib = _lib.load()
+    ndim, n = x.shape
+    m = y.shape[1]
+    assert y.shape[0] == ndim
+    x = x.contiguous() if x.stride(1) != 1 else x
+    y = y.contiguous() if y.stride(1) != 1 else y
+    if out is None:
+        out = aligned_empty(n, m, x.device)
+    facs = make_factors(descs)
+    check(lib.lgp_gram_iso(stream_ptr(), facs, len(descs), ndim, ptr(x), x.stride(0) if ndim else 0, n, ptr(y),
+                           y.stride(0) if ndim else 0, m, ptr(out), out.stride(0), 1 if symmetric else 0),
+          'lgp_gram_iso')
+    return out
+
+
+def gram_iso_vjp(descs, x, Ginv, b):
+    """ returns a (nfactors, 3) device tensor: d/d amp, d/d log(scale), d/d par1 (see lgp_b200.h) """
+    lib = _lib.load()
+    ndim, n = x.shape
+    x = x.contiguous() if x.stride(1) != 1 else x
+    out = torch.empty((len(descs), 3), dtype=f64, device=x.device)
+    facs = make_factors(descs)
+    check(lib.lgp_gram_iso_vjp(stream_ptr(), facs, len(descs), ndim, ptr(x), x.stride(0) if ndim else 0, n,
+                               ptr(Ginv), Ginv.stride(0), ptr(b), ptr(out)), 'lgp_gram_iso_vjp')
+    return out
+
+
+_psi_cache = {}
+
+
+def digamma_table(length, device):
+    key = (str(device), length)
+    t = _psi_cache.get(key)
+    if t is None:
+        lib = _lib.load()
+        host = numpy.empty(length, dtype=numpy.float64)
+        check(lib.lgp_bart_digamma_table(host.ctypes.data_as(_lib.c_double_p), length), 'lgp_bart_digamma_table')
+        t = torch.from_numpy(host).to(device)
+        _psi_cache.clear()
+        _psi_cache[key] = t
+    return t
+
+
+def gram_bart(nsplits, w, rows, gamma, amp, ix, iy, out=None):
+    """ ix: (p, n) int32 device, iy: (p, m) int32 device; rows: (nrows, width) host array """
+    lib = _lib.load()
+    p, n = ix.shape
+    m = iy.shape[1]
+    nsplits = numpy.ascontiguousarray(nsplits, dtype=numpy.int32)
+    w = numpy.ascontiguousarray(w, dtype=numpy.float64)
+    rows = numpy.ascontiguousarray(rows, dtype=numpy.float64)
+    nrows, width = rows.shape
+    if out is None:
+        out = aligned_empty(n, m, ix.device)
+    psi = digamma_table(int(nsplits.max(initial=0)) + 2, ix.device) if p else None
+    ix = ix.contiguous()
+    iy = iy.contiguous()
+    check(lib.lgp_gram_bart(stream_ptr(), p, nsplits.ctypes.data_as(_lib.c_int32_p),
+                            w.ctypes.data_as(_lib.c_double_p), rows.ctypes.data_as(_lib.c_double_p), nrows, width,
+                            float(gamma), float(amp), ptr(psi), ptr(ix), ix.stride(0) if p else 0, n, ptr(iy),
+                            iy.stride(0) if p else 0, m, ptr(out), out.stride(0), 0), 'lgp_gram_bart')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Cholesky
+# ---------------------------------------------------------------------------------------------
+
+class FactorState:
+    """ device-resident factor: W (npad x npad, lower = Lt), aux (s, 1/s, diag, scalars, inverted blocks) """
+
+    __slots__ = ('n', 'npad', 'W', 'aux', 'info', 'device')
+
+    def scalars(self):
+        """ device view: [maxrowsum, eps, -, min s^2, sum log L_ii, -] """
+        return self.aux[3 * self.npad: 3 * self.npad + 16]
+
+
+def chol_factor(K, addmat=None, adddiag=None, epsrel='auto', epsabs=0.0):
+    lib = _lib.load()
+    assert K.ndim == 2 and K.shape[0] == K.shape[1] and K.dtype == f64
+    n = K.shape[0]
+    if K.stride(1) != 1:
+        K = K.contiguous()
+    if addmat is not None and addmat.stride(1) != 1:
+        addmat = addmat.contiguous()
+    if adddiag is not None:
+        adddiag = adddiag.contiguous()
+    st = FactorState()
+    st.n = n
+    st.npad = int(lib.lgp_chol_npad(n))
+    st.device = K.device
+    st.W = torch.empty((st.npad, st.npad), dtype=f64, device=K.device)
+    st.aux = torch.empty(int(lib.lgp_chol_aux_doubles(n)), dtype=f64, device=K.device)
+    st.info = torch.empty(1, dtype=torch.int32, device=K.device)
+    er = -1.0 if (isinstance(epsrel, str) and epsrel == 'auto') else float(epsrel)
+    ea = 2.220446049250313e-16 if (isinstance(epsabs, str) and epsabs == 'auto') else float(epsabs)
+    check(lib.lgp_chol_factor(stream_ptr(), ptr(K), K.stride(0), ptr(addmat),
+                              addmat.stride(0) if addmat is not None else 0, ptr(adddiag), n, er, ea, ptr(st.W),
+                              st.W.stride(0), ptr(st.aux), ptr(st.info)), 'lgp_chol_factor')
+    return st
+
+
+def chol_solve(st, B, trans, inplace=False):
+    """ B: (n, m) device tensor -> L^-1 B (trans=False) or L^-T B (trans=True) """
+    lib = _lib.load()
+    Bw = as_aligned(B)
+    if Bw is B and not inplace:
+        Bw = aligned_empty(B.shape[0], B.shape[1], B.device)
+        Bw.copy_(B)
+    check(lib.lgp_chol_solve(stream_ptr(), ptr(st.W), st.W.stride(0), ptr(st.aux), st.n, ptr(Bw), Bw.stride(0),
+                             Bw.shape[1], int(bool(trans))), 'lgp_chol_solve')
+    return Bw
+
+
+def chol_mult(st, X, trans):
+    lib = _lib.load()
+    Xa = as_aligned(X)
+    Y = aligned_empty(X.shape[0], X.shape[1], X.device)
+    tmp = aligned_empty(X.shape[0], X.shape[1], X.device) if trans else None
+    check(lib.lgp_chol_mult(stream_ptr(), ptr(st.W), st.W.stride(0), ptr(st.aux), st.n, ptr(Xa), Xa.stride(0),
+                            Xa.shape[1], ptr(Y), Y.stride(0), ptr(tmp), tmp.stride(0) if trans else 0,
+                            int(bool(trans))), 'lgp_chol_mult')
+    return Y
+
+
+def chol_get_factor(st):
+    lib = _lib.load()
+    L = torch.empty((st.n, st.n), dtype=f64, device=st.device)
+    check(lib.lgp_chol_get_factor(stream_ptr(), ptr(st.W), st.W.stride(0), ptr(st.aux), st.n, ptr(L), L.stride(0)),
+          'lgp_chol_get_factor')
+    return L
+
+
+def chol_inverse(st):
+    """ lower triangle of (L L^T)^-1 in an (npad, npad) buffer; returns the (n, n) view (upper part undefined) """
+    lib = _lib.load()
+    scratch = torch.empty((st.npad, st.npad), dtype=f64, device=st.device)
+    Kinv = torch.empty((st.npad, st.npad), dtype=f64, device=st.device)
+    check(lib.lgp_chol_inverse(stream_ptr(), ptr(st.W), st.W.stride(0), ptr(st.aux), st.n, ptr(scratch), ptr(Kinv),
+                               Kinv.stride(0)), 'lgp_chol_inverse')
+    del scratch
+    return Kinv[:st.n, :st.n]
+
+
+def chol_logdet_quad(st, a=None):
+    """ device tensor [sum_i log L_ii, sum_i a_i^2] """
+    lib = _lib.load()
+    out = torch.empty(2, dtype=f64, device=st.device)
+    if a is not None:
+        a = a.contiguous()
+    check(lib.lgp_chol_logdet_quad(stream_ptr(), ptr(st.aux), st.n, ptr(a), ptr(out)), 'lgp_chol_logdet_quad')
+    return out

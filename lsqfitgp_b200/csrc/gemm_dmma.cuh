@@ -1,0 +1,232 @@
+// FP64 GEMM on the Blackwell FP64 tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).
+//
+//   C[i][j] = (beta0 ? 0 : C[i][j]) + alpha * sum_k Aop[i][k] * Bop[j][k]
+//
+// Operand storage (all row-major with a leading dimension in doubles):
+//   a_kmajor : Aop[i][k] = A[i*lda + k]      (k contiguous)
+//   !a_kmajor: Aop[i][k] = A[k*lda + i]      (i contiguous, "transposed")
+//   b_kmajor : Bop[j][k] = B[j*ldb + k]
+//   !b_kmajor: Bop[j][k] = B[k*ldb + j]
+//
+// This single kernel family is the trailing-update (SYRK), the TRSM (as multiplication by
+// the inverted 128x128 diagonal block) and the TRTRI/LAUUM building block of the blocked
+// Cholesky that replaces jax.scipy.linalg.cholesky / solve_triangular in the reference
+// (reference: src/lsqfitgp/_linalg/_decomp.py:388,402-403,467-472).
+//
+// CTA tile 128x128x16, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA tiles, 4-stage cp.async
+// pipeline.  tcgen05/TMEM have no f64 kind, so the legacy warp-level MMA is the FP64 tensor
+// path on sm_100a.
+#pragma once
+#include "common.cuh"
+
+namespace lgp {
+
+enum GemmFlags : int {
+    GEMM_LOWER = 1,       // C is square; compute/store only j <= i
+    GEMM_BETA0 = 2,       // overwrite C instead of accumulating
+    GEMM_A_LOWER_K = 4,   // Aop[i][k] == 0 for k > i  (skip k-tiles beyond the row tile)
+    GEMM_B_LOWER_K = 8,   // Bop[j][k] == 0 for k > j
+    GEMM_A_UPPER_K = 16,  // Aop[i][k] == 0 for k < i
+    GEMM_B_UPPER_K = 32,  // Bop[j][k] == 0 for k < j
+};
+
+struct GemmParams {
+    const double *A;
+    const double *B;
+    double *C;
+    int M, N, K;
+    int64_t lda, ldb, ldc;
+    double alpha;
+    int flags;
+    int tiles_m, tiles_n;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 128;
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 256;
+// k-major tile: 128 rows x 128 B, 16-B chunks XOR-swizzled by ((row&1)<<2): conflict-free LDS.128
+constexpr int GEMM_TILE_KMAJ_BYTES = GEMM_BM * GEMM_BK * 8;  // 16384
+// m-major tile: 16 k-rows x 130 doubles (stride 1040 B): conflict-free LDS.64
+constexpr int GEMM_MMAJ_STRIDE = 130;
+constexpr int GEMM_TILE_MMAJ_BYTES = GEMM_BK * GEMM_MMAJ_STRIDE * 8;  // 16640
+constexpr int GEMM_TILE_BYTES = GEMM_TILE_MMAJ_BYTES;                  // per operand per stage
+constexpr int GEMM_SMEM_BYTES = 2 * GEMM_STAGES * GEMM_TILE_BYTES;     // 133120
+
+template <bool KMAJ>
+__device__ __forceinline__ void gemm_load_tile(uint32_t smem_tile, const double *__restrict__ G, int64_t ld,
+                                               int r0, int rows_total, int k0, int k_total, int tid) {
+    if (KMAJ) {
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            int id = tid + it * GEMM_THREADS;
+            int row = id >> 3, c = id & 7;
+            int gr = r0 + row, gk = k0 + 2 * c;
+            int bytes = 0;
+            if (gr < rows_total) {
+                int rem = (k_total - gk) * 8;
+                bytes = rem >= 16 ? 16 : (rem > 0 ? rem : 0);
+            }
+            const double *src = bytes ? (G + (int64_t)gr * ld + gk) : G;
+            uint32_t dst = smem_tile + row * 128 + ((c ^ ((row & 1) << 2)) << 4);
+            cp_async16(dst, src, bytes);
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            int id = tid + it * GEMM_THREADS;
+            int krow = id >> 6, c = id & 63;
+            int gk = k0 + krow, gr = r0 + 2 * c;
+            int bytes = 0;
+            if (gk < k_total) {
+                int rem = (rows_total - gr) * 8;
+                bytes = rem >= 16 ? 16 : (rem > 0 ? rem : 0);
+            }
+            const double *src = bytes ? (G + (int64_t)gk * ld + gr) : G;
+            uint32_t dst = smem_tile + krow * (GEMM_MMAJ_STRIDE * 8) + c * 16;
+            cp_async16(dst, src, bytes);
+        }
+    }
+}
+
+// Fragment for MMA slot q (= lane%4) within 8-k group g: k = 8g + 2q + t, t in {0,1}.
+template <bool KMAJ>
+__device__ __forceinline__ void gemm_load_frag(const unsigned char *tile, int row, int g, int q, double &v0,
+                                               double &v1) {
+    if (KMAJ) {
+        int c = (4 * g + q) ^ ((row & 1) << 2);
+        double2 v = *reinterpret_cast<const double2 *>(tile + row * 128 + (c << 4));
+        v0 = v.x;
+        v1 = v.y;
+    } else {
+        int k = 8 * g + 2 * q;
+        const double *p = reinterpret_cast<const double *>(tile) + k * GEMM_MMAJ_STRIDE + row;
+        v0 = p[0];
+        v1 = p[GEMM_MMAJ_STRIDE];
+    }
+}
+
+template <bool A_KMAJ, bool B_KMAJ>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+    const int lr = lane >> 2, q = lane & 3;
+
+    int tm, tn;
+    if (p.flags & GEMM_LOWER) {
+        // blockIdx.x enumerates lower-triangular tiles (tm >= tn), row by row
+        int b = blockIdx.x;
+        tm = (int)((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
+        while ((tm + 1) * (tm + 2) / 2 <= b) tm++;
+        while (tm * (tm + 1) / 2 > b) tm--;
+        tn = b - tm * (tm + 1) / 2;
+    } else {
+        // column-of-tiles fastest so that consecutive CTAs share the B tile stream in L2
+        tm = blockIdx.x % p.tiles_m;
+        tn = blockIdx.x / p.tiles_m;
+    }
+    const int m0 = tm * GEMM_BM, n0 = tn * GEMM_BN;
+
+    int k_begin = 0, k_end = p.K;
+    if (p.flags & GEMM_A_LOWER_K) k_end = min(k_end, m0 + GEMM_BM);
+    if (p.flags & GEMM_B_LOWER_K) k_end = min(k_end, n0 + GEMM_BN);
+    if (p.flags & GEMM_A_UPPER_K) k_begin = max(k_begin, m0);
+    if (p.flags & GEMM_B_UPPER_K) k_begin = max(k_begin, n0);
+    k_begin &= ~(GEMM_BK - 1);
+    const int KT = k_end > k_begin ? (k_end - k_begin + GEMM_BK - 1) / GEMM_BK : 0;
+
+    const uint32_t smem_base = smem_u32(smem);
+    auto a_tile = [&](int s) { return smem_base + s * GEMM_TILE_BYTES; };
+    auto b_tile = [&](int s) { return smem_base + (GEMM_STAGES + s) * GEMM_TILE_BYTES; };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // prologue
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; s++) {
+        if (s < KT) {
+            int k0 = k_begin + s * GEMM_BK;
+            gemm_load_tile<A_KMAJ>(a_tile(s), p.A, p.lda, m0, p.M, k0, k_end, tid);
+            gemm_load_tile<B_KMAJ>(b_tile(s), p.B, p.ldb, n0, p.N, k0, k_end, tid);
+        }
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < KT; kt++) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + GEMM_STAGES - 1;
+            if (nk < KT) {
+                int s = nk % GEMM_STAGES;
+                int k0 = k_begin + nk * GEMM_BK;
+                gemm_load_tile<A_KMAJ>(a_tile(s), p.A, p.lda, m0, p.M, k0, k_end, tid);
+                gemm_load_tile<B_KMAJ>(b_tile(s), p.B, p.ldb, n0, p.N, k0, k_end, tid);
+            }
+            cp_async_commit();
+        }
+        const int s = kt % GEMM_STAGES;
+        const unsigned char *at = smem + s * GEMM_TILE_BYTES;
+        const unsigned char *bt = smem + (GEMM_STAGES + s) * GEMM_TILE_BYTES;
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            double af[8][2], bf[4][2];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                gemm_load_frag<A_KMAJ>(at, wm * 64 + i * 8 + lr, g, q, af[i][0], af[i][1]);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                gemm_load_frag<B_KMAJ>(bt, wn * 32 + j * 8 + lr, g, q, bf[j][0], bf[j][1]);
+#pragma unroll
+            for (int t = 0; t < 2; t++)
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i][t], bf[j][t]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: each lane owns C[row][col..col+1]
+    const bool lower = p.flags & GEMM_LOWER;
+    const bool beta0 = p.flags & GEMM_BETA0;
+    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int row = m0 + wm * 64 + i * 8 + lr;
+        if (row >= p.M) continue;
+        double *crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int col = n0 + wn * 32 + j * 8 + 2 * q;
+            int cmax = lower ? min(p.N, row + 1) : p.N;  // exclusive bound on valid columns
+            if (col >= cmax) continue;
+            double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+            if (vec_ok && col + 1 < cmax) {
+                double2 *cp = reinterpret_cast<double2 *>(crow + col);
+                if (!beta0) {
+                    double2 o = *cp;
+                    v0 += o.x;
+                    v1 += o.y;
+                }
+                *cp = make_double2(v0, v1);
+            } else {
+                if (!beta0) v0 += crow[col];
+                crow[col] = v0;
+                if (col + 1 < cmax) {
+                    if (!beta0) v1 += crow[col + 1];
+                    crow[col + 1] = v1;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace lgp

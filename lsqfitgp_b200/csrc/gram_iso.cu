@@ -1,0 +1,396 @@
+// Gram-matrix build for sums of products of isotropic kernels, and its reverse-mode contraction.
+//
+// Reference arithmetic (one rounding per operation, field order, divide-before-difference):
+//   src/lsqfitgp/_Kernel/_ops.py:292-326 (loc, scale applied per argument),
+//   src/lsqfitgp/_Kernel/_isotropic.py:61-81 + _Kernel/_util.py:74-99 (r2 = sum_f (x_f-y_f)^2),
+//   src/lsqfitgp/_kernels/_basic.py:46,59,75,339-343, _kernels/_matern.py:48-49,74-76,
+//   src/lsqfitgp/_special/_bessel.py:101-122 (kvmodx2_hi and its derivative),
+//   src/lsqfitgp/_Kernel/_alg.py:48-82 (sum / product / scalar multiple).
+#include <math.h>
+#include <string.h>
+
+#include "../../include/lgp_b200.h"
+#include "common.cuh"
+
+namespace lgp {
+
+constexpr int GT = 64;          // CTA tile (rows = cols)
+constexpr int G_THREADS = 256;  // 16 x 16 threads, 4 x 4 entries each
+constexpr int G_MAX_SLOTS = 96; // sum over factors of participating fields
+constexpr int G_MAX_P = 8;
+
+struct GramDesc {
+    int nfactors;
+    int nslots;
+    int kind[LGP_MAX_FACTORS];
+    int term[LGP_MAX_FACTORS];
+    int ipar[LGP_MAX_FACTORS];
+    int slot0[LGP_MAX_FACTORS];   // first slot of the factor
+    int nslot[LGP_MAX_FACTORS];   // number of participating fields
+    double scale_x[LGP_MAX_FACTORS], scale_y[LGP_MAX_FACTORS], loc_x[LGP_MAX_FACTORS], loc_y[LGP_MAX_FACTORS];
+    double par0[LGP_MAX_FACTORS], par1[LGP_MAX_FACTORS], amp[LGP_MAX_FACTORS];
+    double coef[LGP_MAX_FACTORS][G_MAX_P];  // Maternp Horner ratios c_{k+1}/c_k, k = 0..p-1
+    unsigned char slot_dim[G_MAX_SLOTS];
+    unsigned char slot_factor[G_MAX_SLOTS];
+};
+
+static int build_desc(const lgp_factor_t *f, int nf, int ndim, GramDesc &d) {
+    if (nf < 1 || nf > LGP_MAX_FACTORS || ndim < 0 || ndim > LGP_MAX_DIMS) return LGP_ERR_BADARG;
+    memset(&d, 0, sizeof(d));
+    d.nfactors = nf;
+    int slots = 0;
+    for (int i = 0; i < nf; i++) {
+        if (i > 0 && f[i].term < f[i - 1].term) return LGP_ERR_BADARG;  // factors must be grouped by term
+        d.kind[i] = f[i].kind;
+        d.term[i] = f[i].term;
+        d.ipar[i] = f[i].ipar;
+        d.scale_x[i] = f[i].scale_x; d.scale_y[i] = f[i].scale_y;
+        d.loc_x[i] = f[i].loc_x; d.loc_y[i] = f[i].loc_y;
+        d.par0[i] = f[i].par0; d.par1[i] = f[i].par1; d.amp[i] = f[i].amp;
+        d.slot0[i] = slots;
+        if (f[i].kind < 0 || f[i].kind > LGP_K_CONSTANT) return LGP_ERR_UNSUPPORTED;
+        if (f[i].kind == LGP_K_MATERNP) {
+            int p = f[i].ipar;
+            if (p < 0 || p > G_MAX_P) return LGP_ERR_UNSUPPORTED;
+            for (int k = 0; k < p; k++) d.coef[i][k] = (double)(p - k) / (double)((2 * p - k) * (k + 1));
+        }
+        if (f[i].kind != LGP_K_CONSTANT) {
+            for (int dd = 0; dd < ndim; dd++)
+                if (f[i].dimmask & (1u << dd)) {
+                    if (slots >= G_MAX_SLOTS) return LGP_ERR_UNSUPPORTED;
+                    d.slot_dim[slots] = (unsigned char)dd;
+                    d.slot_factor[slots] = (unsigned char)i;
+                    slots++;
+                }
+        }
+        d.nslot[i] = slots - d.slot0[i];
+    }
+    d.nslots = slots;
+    return LGP_OK;
+}
+
+// value of factor f (without amp) at squared distance r2
+__device__ __forceinline__ double core_value(const GramDesc &d, int f, double r2) {
+    switch (d.kind[f]) {
+        case LGP_K_EXPQUAD:
+            return exp(__dmul_rn(-0.5, r2));
+        case LGP_K_MATERNP: {
+            const int p = d.ipar[f];
+            double z = __dadd_rn(__dmul_rn((double)(2 * p + 1), r2), d.par0[f]);
+            double x = sqrt(z);
+            double poly = 1.0;
+            for (int k = p - 1; k >= 0; k--)
+                poly = __dadd_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(poly, d.coef[f][k]), 2.0), x));
+            return __dmul_rn(exp(-x), poly);
+        }
+        case LGP_K_CAUCHY: {
+            const double alpha = d.par0[f], beta = d.par1[f];
+            double pw = (alpha == 2.0) ? r2 : pow(r2, alpha / 2.0);
+            return pow(__dadd_rn(1.0, pw / beta), -beta / alpha);
+        }
+        case LGP_K_WHITE:
+            return r2 == 0.0 ? 1.0 : 0.0;
+        default:
+            return 1.0;
+    }
+}
+
+// d core / d r2 and d core / d par1 (Cauchy beta)
+__device__ __forceinline__ void core_derivs(const GramDesc &d, int f, double r2, double &val, double &dr2,
+                                            double &dpar1) {
+    dpar1 = 0.0;
+    switch (d.kind[f]) {
+        case LGP_K_EXPQUAD:
+            val = exp(-0.5 * r2);
+            dr2 = -0.5 * val;
+            return;
+        case LGP_K_MATERNP: {
+            const int p = d.ipar[f];
+            const double nu2 = (double)(2 * p + 1);
+            double z = nu2 * r2 + d.par0[f];
+            double x = sqrt(z);
+            double ex = exp(-x);
+            double poly = 1.0;
+            for (int k = p - 1; k >= 0; k--) poly = 1.0 + poly * d.coef[f][k] * 2.0 * x;
+            val = ex * poly;
+            if (p == 0) {
+                dr2 = x > 0.0 ? -nu2 * ex / (2.0 * x) : 0.0;
+            } else {
+                // d/dz kvmodx2_hi(z, p) = -kvmodx2_hi(z, p-1) / (4 (p - 1/2))   (_bessel.py:112-122)
+                const int pm = p - 1;
+                double polym = 1.0;
+                for (int k = pm - 1; k >= 0; k--)
+                    polym = 1.0 + polym * ((double)(pm - k) / (double)((2 * pm - k) * (k + 1))) * 2.0 * x;
+                dr2 = -nu2 * ex * polym / (4.0 * ((double)p - 0.5));
+            }
+            return;
+        }
+        case LGP_K_CAUCHY: {
+            const double alpha = d.par0[f], beta = d.par1[f];
+            double t = (alpha == 2.0) ? r2 : pow(r2, alpha / 2.0);
+            double base = 1.0 + t / beta;
+            val = pow(base, -beta / alpha);
+            // d val / d t = -(1/alpha) base^(-beta/alpha - 1)
+            double dvdt = -(1.0 / alpha) * val / base;
+            double dtdr2 = (alpha == 2.0) ? 1.0 : (r2 > 0.0 ? (alpha / 2.0) * t / r2 : 0.0);
+            dr2 = dvdt * dtdr2;
+            dpar1 = val * (-(1.0 / alpha) * log(base) + (t / (alpha * beta)) / base);
+            return;
+        }
+        case LGP_K_WHITE:
+            val = r2 == 0.0 ? 1.0 : 0.0;
+            dr2 = 0.0;
+            return;
+        default:
+            val = 1.0;
+            dr2 = 0.0;
+            return;
+    }
+}
+
+// stage transformed coordinates of a 64-point tile: su[slot][64]
+__device__ __forceinline__ void stage_points(const GramDesc &d, double *s, const double *__restrict__ x, int64_t ldx,
+                                             int64_t n, int64_t i0, bool is_y, int tid) {
+    for (int idx = tid; idx < d.nslots * GT; idx += G_THREADS) {
+        int slot = idx / GT, r = idx % GT;
+        int f = d.slot_factor[slot];
+        int64_t i = i0 + r;
+        double v = 0.0;
+        if (i < n) {
+            double raw = x[(int64_t)d.slot_dim[slot] * ldx + i];
+            double loc = is_y ? d.loc_y[f] : d.loc_x[f];
+            double sc = is_y ? d.scale_y[f] : d.scale_x[f];
+            v = __ddiv_rn(__dsub_rn(raw, loc), sc);
+        }
+        s[slot * GT + r] = v;
+    }
+}
+
+__global__ void __launch_bounds__(G_THREADS) gram_iso_kernel(const __grid_constant__ GramDesc d,
+                                                             const double *__restrict__ x, int64_t ldx, int64_t n,
+                                                             const double *__restrict__ y, int64_t ldy, int64_t m,
+                                                             double *__restrict__ K, int64_t ldk, int vec_ok) {
+    extern __shared__ __align__(16) double gsm[];
+    double *su = gsm;
+    double *sv = gsm + (size_t)d.nslots * GT;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t i0 = (int64_t)blockIdx.y * GT, j0 = (int64_t)blockIdx.x * GT;
+    stage_points(d, su, x, ldx, n, i0, false, tid);
+    stage_points(d, sv, y, ldy, m, j0, true, tid);
+    __syncthreads();
+
+    double sum[4][4];
+    double prod[4][4];
+    int cur_term = -1;
+    bool first_term = true;
+    for (int f = 0; f < d.nfactors; f++) {
+        double r2[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) r2[a][c] = 0.0;
+        for (int s = d.slot0[f]; s < d.slot0[f] + d.nslot[f]; s++) {
+            double uu[4], vv[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) uu[a] = su[s * GT + ty + 16 * a];
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                double2 t = *reinterpret_cast<const double2 *>(&sv[s * GT + 2 * tx + 32 * b]);
+                vv[2 * b] = t.x;
+                vv[2 * b + 1] = t.y;
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    double df = __dsub_rn(uu[a], vv[c]);
+                    double sq = __dmul_rn(df, df);
+                    r2[a][c] = (s == d.slot0[f]) ? sq : __dadd_rn(r2[a][c], sq);
+                }
+        }
+        const bool new_term = d.term[f] != cur_term;
+        if (new_term && cur_term != -1) {
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) sum[a][c] = first_term ? prod[a][c] : __dadd_rn(sum[a][c], prod[a][c]);
+            first_term = false;
+        }
+        cur_term = d.term[f];
+        const double amp = d.amp[f];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double v = __dmul_rn(amp, core_value(d, f, r2[a][c]));
+                prod[a][c] = new_term ? v : __dmul_rn(prod[a][c], v);
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) sum[a][c] = first_term ? prod[a][c] : __dadd_rn(sum[a][c], prod[a][c]);
+
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        int64_t i = i0 + ty + 16 * a;
+        if (i >= n) continue;
+        double *krow = K + i * ldk;
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            int64_t j = j0 + 2 * tx + 32 * b;
+            if (j >= m) continue;
+            if (vec_ok && j + 1 < m) {
+                *reinterpret_cast<double2 *>(krow + j) = make_double2(sum[a][2 * b], sum[a][2 * b + 1]);
+            } else {
+                krow[j] = sum[a][2 * b];
+                if (j + 1 < m) krow[j + 1] = sum[a][2 * b + 1];
+            }
+        }
+    }
+}
+
+// Reverse-mode contraction over the lower triangle of the symmetric Gram (x == y).
+// acc layout per factor: [0] d/d amp, [1] d/d log(scale), [2] d/d par1
+__global__ void __launch_bounds__(G_THREADS) gram_iso_vjp_kernel(const __grid_constant__ GramDesc d,
+                                                                 const double *__restrict__ x, int64_t ldx,
+                                                                 int64_t n, const double *__restrict__ G, int64_t ldg,
+                                                                 const double *__restrict__ bvec,
+                                                                 double *__restrict__ out) {
+    extern __shared__ __align__(16) double gsm[];
+    double *su = gsm;
+    double *sv = gsm + (size_t)d.nslots * GT;
+    __shared__ double red[G_THREADS / 32][3 * LGP_MAX_FACTORS];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    // lower-triangular tile enumeration
+    int b = blockIdx.x;
+    int tm = (int)((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
+    while ((tm + 1) * (tm + 2) / 2 <= b) tm++;
+    while (tm * (tm + 1) / 2 > b) tm--;
+    int tn = b - tm * (tm + 1) / 2;
+    const int64_t i0 = (int64_t)tm * GT, j0 = (int64_t)tn * GT;
+    stage_points(d, su, x, ldx, n, i0, false, tid);
+    stage_points(d, sv, x, ldx, n, j0, true, tid);
+    __syncthreads();
+
+    double acc[3 * LGP_MAX_FACTORS];
+#pragma unroll
+    for (int k = 0; k < 3 * LGP_MAX_FACTORS; k++) acc[k] = 0.0;
+
+#pragma unroll 1
+    for (int a = 0; a < 4; a++) {
+        const int64_t i = i0 + ty + 16 * a;
+        if (i >= n) continue;
+        const double bi = bvec ? bvec[i] : 0.0;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            const int cc = 2 * tx + 32 * (c >> 1) + (c & 1);
+            const int64_t j = j0 + cc;
+            if (j > i || j >= n) continue;
+            double g = G[i * ldg + j];
+            if (bvec) g -= bi * bvec[j];
+            if (j != i) g *= 2.0;
+            // evaluate all factors
+            double val[LGP_MAX_FACTORS], dr2[LGP_MAX_FACTORS], dp1[LGP_MAX_FACTORS], r2s[LGP_MAX_FACTORS];
+#pragma unroll
+            for (int f = 0; f < LGP_MAX_FACTORS; f++) {
+                if (f < d.nfactors) {
+                    double r2 = 0.0;
+                    for (int s = d.slot0[f]; s < d.slot0[f] + d.nslot[f]; s++) {
+                        double df = su[s * GT + ty + 16 * a] - sv[s * GT + cc];
+                        r2 += df * df;
+                    }
+                    r2s[f] = r2;
+                    core_derivs(d, f, r2, val[f], dr2[f], dp1[f]);
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < LGP_MAX_FACTORS; f++) {
+                if (f < d.nfactors) {
+                    // product of the other factors of the same term (with their amps)
+                    double others = 1.0;
+#pragma unroll
+                    for (int h = 0; h < LGP_MAX_FACTORS; h++)
+                        if (h < d.nfactors && h != f && d.term[h] == d.term[f]) others *= d.amp[h] * val[h];
+                    const double go = g * others;
+                    acc[3 * f + 0] += go * val[f];
+                    acc[3 * f + 1] += go * d.amp[f] * dr2[f] * (-2.0 * r2s[f]);
+                    acc[3 * f + 2] += go * d.amp[f] * dp1[f];
+                }
+            }
+        }
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int k = 0; k < 3 * LGP_MAX_FACTORS; k++) {
+        double v = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < 3 * d.nfactors) {
+        double v = 0.0;
+        for (int w = 0; w < G_THREADS / 32; w++) v += red[w][tid];
+        atomicAdd(out + tid, v);
+    }
+}
+
+__global__ void zero_kernel(double *p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
+}
+
+}  // namespace lgp
+
+using namespace lgp;
+
+extern "C" {
+
+int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
+                 int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, double *K_out, int64_t ldk,
+                 int flags) {
+    (void)flags;
+    if (!factors || !K_out || n < 0 || m < 0) return LGP_ERR_BADARG;
+    if (n == 0 || m == 0) return LGP_OK;
+    if (ndim > 0 && (!x || !y)) return LGP_ERR_BADARG;
+    if (ldk < m) return LGP_ERR_BADARG;
+    GramDesc d;
+    int rc = build_desc(factors, nfactors, ndim, d);
+    if (rc) return rc;
+    size_t smem = (size_t)2 * d.nslots * GT * sizeof(double);
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(gram_iso_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return LGP_ERR_CUDA;
+    }
+    dim3 grid((unsigned)((m + GT - 1) / GT), (unsigned)((n + GT - 1) / GT));
+    if (grid.y > 65535) return LGP_ERR_UNSUPPORTED;
+    int vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K_out) & 15) == 0);
+    gram_iso_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(d, x, ldx, n, y, ldy, m, K_out, ldk, vec_ok);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
+                     int64_t ldx, int64_t n, const double *Ginv, int64_t ldg, const double *b, double *out) {
+    if (!factors || !Ginv || !out || n < 1) return LGP_ERR_BADARG;
+    GramDesc d;
+    int rc = build_desc(factors, nfactors, ndim, d);
+    if (rc) return rc;
+    size_t smem = (size_t)2 * d.nslots * GT * sizeof(double);
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(gram_iso_vjp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return LGP_ERR_CUDA;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    zero_kernel<<<1, 32, 0, st>>>(out, 3 * nfactors);
+    LGP_CUDA_CHECK_LAUNCH();
+    int64_t t = (n + GT - 1) / GT;
+    int64_t nblk = t * (t + 1) / 2;
+    if (nblk > 2147483647LL) return LGP_ERR_UNSUPPORTED;
+    gram_iso_vjp_kernel<<<(unsigned)nblk, G_THREADS, smem, st>>>(d, x, ldx, n, Ginv, ldg, b, out);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+}  // extern "C"
