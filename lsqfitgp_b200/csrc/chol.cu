@@ -5,6 +5,8 @@
 // (eigval_bound, diag_scale_pow2), :380-393 (Chol.__init__), :398-439 (solves), :466-472.
 #include <limits.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/lgp_b200.h"
 #include "common.cuh"
@@ -110,8 +112,124 @@ __global__ void __launch_bounds__(1024) chol_jitter_kernel(int n, int npad, doub
 // Combined storage M[r][c]: r >= c holds A/L[r][c]; r < c holds row c of X = L^-1 (X[c][r]).
 // Thread (lane, w) owns rows lane+32a (a<4) and columns w+16b (b<8).  At step k the 32 lanes of warp
 // k%16 own column k, so the pivot is broadcast with one shuffle and there is a single barrier per step.
-constexpr int LEAF_THREADS = 512;
+constexpr int LEAF_THREADS = 256;
 constexpr int LEAF_SMEM_BYTES = (NB * (NB + 1) + 2 * NB) * 8;
+
+__device__ __forceinline__ void leaf_bar_sync(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(LEAF_THREADS) : "memory");
+}
+__device__ __forceinline__ void leaf_bar_arrive(int id) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(LEAF_THREADS) : "memory");
+}
+
+// Thread (lane, w), w < 8: rows r = lane + 32a (a < 4), columns c = w + 8b (b < 16): M[a][b].
+// Combined storage: r >= c holds A/L[r][c]; r < c holds X[c][r], X = L^-1 (rows of X stored as columns).
+// Rank-1 update of step k on column block B (all indices static so that M stays in registers):
+//   M[r][c] -= col[r]*col[c]  for r >= c (Cholesky part) or r <= k (inverse part).
+template <int B>
+__device__ __forceinline__ void leaf_update_column(double (&M)[4][16], const double (&cr)[4], const bool (&rle)[4],
+                                                   const bool (&lowd)[4], double cc) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        if (B < 4 * a) {  // block entirely below the diagonal
+            M[a][B] -= cr[a] * cc;
+        } else if (B >= 4 * a + 4) {  // entirely above: inverse part only
+            if (rle[a]) M[a][B] -= cr[a] * cc;
+        } else {  // block crossing the diagonal
+            if (lowd[B - 4 * a] || rle[a]) M[a][B] -= cr[a] * cc;
+        }
+    }
+}
+
+// Factor column k1 (held in M[.][B1] by the 32 lanes of this warp) after applying step k to it, and publish
+// col[r] = L[r][k1] (r > k1), X[k1][r] (r < k1), 1/L[k1][k1] (r == k1).
+template <int B1>
+__device__ __forceinline__ void leaf_next_column(double (&M)[4][16], const double (&cr)[4], const bool (&rle)[4],
+                                                 const bool (&lowd)[4], const double *col, double *colnext, int k1,
+                                                 int lane, int w, double *dvec, int32_t *info, int j0) {
+    constexpr int A1 = B1 >> 2;
+    leaf_update_column<B1>(M, cr, rle, lowd, col[w + 8 * B1]);
+    double pv = __shfl_sync(0xffffffffu, M[A1][B1], k1 & 31);
+    const double rl = rsqrt(pv);  // NaN for pv < 0, inf for pv == 0: propagates like a failed LAPACK/JAX factorisation
+    const double l = pv * rl;
+    if (lane == 0) {
+        if (!(pv > 0.0) || !(l < INFINITY)) atomicMin(info, j0 + k1 + 1);
+        dvec[j0 + k1] = l;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int r = lane + 32 * a;
+        const double v = M[a][B1] * rl;
+        colnext[r] = (r == k1) ? rl : v;
+        M[a][B1] = (r == k1) ? l : v;
+    }
+}
+
+template <int B, int BEND>
+struct LeafCols {
+    static __device__ __forceinline__ void run(double (&M)[4][16], const double (&cr)[4], const bool (&rle)[4],
+                                               const bool (&lowd)[4], const double *col, int w) {
+        if constexpr (B < BEND) {
+            leaf_update_column<B>(M, cr, rle, lowd, col[w + 8 * B]);
+            LeafCols<B + 1, BEND>::run(M, cr, rle, lowd, col, w);
+        }
+    }
+};
+
+// Steps k = 8*KB .. 8*KB+7 (columns of block KB; their owners are warps 0..7 in turn).
+template <int KB>
+__device__ __forceinline__ void leaf_block_steps(double (&M)[4][16], double *colbuf, int lane, int w,
+                                                 const bool (&lowd)[4], double *dvec, int32_t *info, int j0) {
+#pragma unroll 1
+    for (int kw = 0; kw < 8; kw++) {
+        const int k = 8 * KB + kw;
+        const double *col = colbuf + (k & 1) * NB;
+        double cr[4];
+        bool rle[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            cr[a] = col[lane + 32 * a];
+            rle[a] = (lane + 32 * a) <= k;
+        }
+        const int k1 = k + 1;
+        const bool next_owner = (k1 < NB) && (w == (k1 & 7));
+        // the warp owning column k+1 updates it first, factors it and releases the others (bar.arrive)
+        if (next_owner) {
+            double *colnext = colbuf + (k1 & 1) * NB;
+            if (kw < 7) {
+                leaf_next_column<KB>(M, cr, rle, lowd, col, colnext, k1, lane, w, dvec, info, j0);
+            } else {
+                if constexpr (KB + 1 < 16)
+                    leaf_next_column<KB + 1>(M, cr, rle, lowd, col, colnext, k1, lane, w, dvec, info, j0);
+            }
+            __threadfence_block();
+            leaf_bar_arrive(1 + (k1 & 1));
+        }
+        // column block KB: only columns c = w + 8*KB > k are still active
+        if ((w > kw) && !(next_owner && kw < 7)) leaf_update_column<KB>(M, cr, rle, lowd, col[w + 8 * KB]);
+        if constexpr (KB + 1 < 16) {
+            if (!(next_owner && kw == 7)) leaf_update_column<KB + 1>(M, cr, rle, lowd, col[w + 8 * (KB + 1)]);
+        }
+        LeafCols<KB + 2, 16>::run(M, cr, rle, lowd, col, w);
+        if (k1 < NB) {
+            if (next_owner)
+                __syncwarp();
+            else
+                leaf_bar_sync(1 + (k1 & 1));
+        }
+    }
+}
+
+template <int KB>
+struct LeafBlocks {
+    static __device__ __forceinline__ void run(double (&M)[4][16], double *colbuf, int lane, int w,
+                                               const bool (&lowd)[4], double *dvec, int32_t *info, int j0) {
+        if constexpr (KB < 16) {
+            leaf_block_steps<KB>(M, colbuf, lane, w, lowd, dvec, info, j0);
+            LeafBlocks<KB + 1>::run(M, colbuf, lane, w, lowd, dvec, info, j0);
+        }
+    }
+};
 
 __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double *__restrict__ Wblk, int64_t ld,
                                                                      double *__restrict__ invd,
@@ -127,74 +245,41 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double *__r
         stage[r * (NB + 1) + c] = Wblk[(int64_t)r * ld + c];
     }
     __syncthreads();
-    double M[4][8];
+    double M[4][16];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
-            int r = lane + 32 * a, c = w + 16 * b;
+        for (int b = 0; b < 16; b++) {
+            int r = lane + 32 * a, c = w + 8 * b;
             M[a][b] = (r >= c) ? stage[r * (NB + 1) + c] : 0.0;
         }
-    __syncthreads();
-
-    for (int k = 0; k < NB; k++) {
-        double *col = colbuf + (k & 1) * NB;
-        const int kb = k >> 4, kw = k & 15, ka = k >> 5, kl = k & 31;
-        if (w == kw) {
-            double cv[4];
+    bool lowd[4];
 #pragma unroll
-            for (int b = 0; b < 8; b++)
-                if (b == kb) {
-#pragma unroll
-                    for (int a = 0; a < 4; a++) cv[a] = M[a][b];
-                }
-            double pv = 0.0;
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-                if (a == ka) pv = cv[a];
-            pv = __shfl_sync(0xffffffffu, pv, kl);
-            const double l = sqrt(pv);
-            const double rl = 1.0 / l;
-            if (lane == 0) {
-                if (!(pv > 0.0) || !(l < INFINITY)) atomicMin(info, j0 + k + 1);
-                dvec[j0 + k] = l;
-            }
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                int r = lane + 32 * a;
-                double v = cv[a] * rl;
-                col[r] = (r == k) ? rl : v;
-                cv[a] = (r == k) ? l : v;
-            }
-#pragma unroll
-            for (int b = 0; b < 8; b++)
-                if (b == kb) {
-#pragma unroll
-                    for (int a = 0; a < 4; a++) M[a][b] = cv[a];
-                }
+    for (int j = 0; j < 4; j++) lowd[j] = lane >= w + 8 * j;
+    // column 0 is factored by its owner (warp 0) before the loop
+    if (w == 0) {
+        double pv = __shfl_sync(0xffffffffu, M[0][0], 0);
+        const double rl = rsqrt(pv);
+        const double l = pv * rl;
+        if (lane == 0) {
+            if (!(pv > 0.0) || !(l < INFINITY)) atomicMin(info, j0 + 1);
+            dvec[j0] = l;
         }
-        __syncthreads();
-        double cr[4];
 #pragma unroll
-        for (int a = 0; a < 4; a++) cr[a] = col[lane + 32 * a];
-#pragma unroll
-        for (int b = 0; b < 8; b++) {
-            const int c = w + 16 * b;
-            if (c > k) {
-                const double cc = col[c];
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    const int r = lane + 32 * a;
-                    if (r >= c || r <= k) M[a][b] -= cr[a] * cc;
-                }
-            }
+        for (int a = 0; a < 4; a++) {
+            const int r = lane + 32 * a;
+            const double v = M[a][0] * rl;
+            colbuf[r] = (r == 0) ? rl : v;
+            M[a][0] = (r == 0) ? l : v;
         }
     }
     __syncthreads();
+    LeafBlocks<0>::run(M, colbuf, lane, w, lowd, dvec, info, j0);
+    __syncthreads();
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 8; b++) stage[(lane + 32 * a) * (NB + 1) + (w + 16 * b)] = M[a][b];
+        for (int b = 0; b < 16; b++) stage[(lane + 32 * a) * (NB + 1) + (w + 8 * b)] = M[a][b];
     __syncthreads();
     for (int idx = tid; idx < NB * NB; idx += LEAF_THREADS) {
         int r = idx >> 7, c = idx & 127;
@@ -312,7 +397,7 @@ static void trsm_right_rec(CholCtx &c, int rb, int rows, int jb, int nb) {
     if (nb == 1) {
         double *B = Wp(c, rb, jb);
         RC(gemm_launch(c.st, true, true, rows, NB, NB, 1.0, B, c.ldw, c.invd + (int64_t)jb * NB * NB, NB, B, c.ldw,
-                       GEMM_BETA0 | GEMM_B_LOWER_K));
+                       GEMM_BETA0 | GEMM_B_LOWER_K | GEMM_INPLACE_A));
         return;
     }
     int n1 = nb / 2, n2 = nb - n1;
@@ -340,6 +425,105 @@ static void potrf_rec(CholCtx &c, int jb, int nb) {
     RC(gemm_launch(c.st, true, true, n2 * NB, n2 * NB, n1 * NB, -1.0, Wp(c, jb + n1, jb), c.ldw, Wp(c, jb + n1, jb),
                    c.ldw, Wp(c, jb + n1, jb + n1), c.ldw, GEMM_LOWER));
     potrf_rec(c, jb + n1, n2);
+}
+
+// Right-looking blocked factorisation with one-panel look-ahead on two streams:
+//   panel stream (high priority): diagonal-block potrf + TRSM of the block column below it;
+//   main stream: trailing SYRK, split into "next block column" (releases the next panel) and "rest".
+// The panel chain of small launches overlaps the big trailing update of the previous panel.
+static cudaStream_t panel_stream() {
+    static cudaStream_t s = nullptr;
+    static bool init = false;
+    if (!init) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) s = nullptr;
+        init = true;
+    }
+    return s;
+}
+
+static int potrf_lookahead(CholCtx &cm, int nblk, int pb) {
+    cudaStream_t ps = panel_stream();
+    if (!ps || nblk <= pb) {
+        potrf_rec(cm, 0, nblk);
+        return cm.rc;
+    }
+    const bool trace = getenv("LGP_TRACE") != nullptr;  // debug only: synchronises and prints a per-panel timeline
+    CholCtx cp = cm;
+    cp.st = ps;
+    const int np = (nblk + pb - 1) / pb;
+    const int nev = 2 * np + 1;
+    cudaEvent_t *ev = new cudaEvent_t[nev];
+    for (int i = 0; i < nev; i++) cudaEventCreateWithFlags(&ev[i], trace ? cudaEventDefault : cudaEventDisableTiming);
+    cudaEvent_t *e_panel = ev, *e_col = ev + np, e_fork = ev[2 * np];
+    cudaEvent_t *t_pstart = nullptr, *t_restend = nullptr;
+    if (trace) {
+        t_pstart = new cudaEvent_t[np];
+        t_restend = new cudaEvent_t[np];
+        for (int i = 0; i < np; i++) {
+            cudaEventCreate(&t_pstart[i]);
+            cudaEventCreate(&t_restend[i]);
+        }
+    }
+    cudaEventRecord(e_fork, cm.st);
+    cudaStreamWaitEvent(ps, e_fork, 0);
+    int rc = LGP_OK;
+    int last = 0;
+    for (int j = 0; j < np && rc == LGP_OK; j++) {
+        const int jb = j * pb;
+        const int w = (nblk - jb < pb) ? nblk - jb : pb;
+        const int rest = nblk - jb - w;
+        // ---- panel stream
+        if (j > 0) cudaStreamWaitEvent(ps, e_col[j], 0);
+        if (trace) cudaEventRecord(t_pstart[j], ps);
+        potrf_rec(cp, jb, w);
+        if (rest > 0) trsm_right_rec(cp, jb + w, rest * NB, jb, w);
+        cudaEventRecord(e_panel[j], ps);
+        last = j;
+        if ((rc = cp.rc) != LGP_OK || rest == 0) break;
+        // ---- main stream
+        cudaStreamWaitEvent(cm.st, e_panel[j], 0);
+        const int w2 = rest < pb ? rest : pb;
+        const int rest2 = rest - w2;
+        const int K = w * NB;
+        // next block column (rows jb+w.., cols jb+w..jb+w+w2): one full GEMM; the part above the block
+        // diagonal is scratch (never read: leaves and LOWER kernels only touch r >= c)
+        rc = gemm_launch(cm.st, true, true, rest * NB, w2 * NB, K, -1.0, Wp(cm, jb + w, jb), cm.ldw, Wp(cm, jb + w, jb),
+                         cm.ldw, Wp(cm, jb + w, jb + w), cm.ldw, 0);
+        cudaEventRecord(e_col[j + 1], cm.st);
+        // rest of the trailing matrix
+        if (rc == LGP_OK && rest2 > 0)
+            rc = gemm_launch(cm.st, true, true, rest2 * NB, rest2 * NB, K, -1.0, Wp(cm, jb + w + w2, jb), cm.ldw,
+                             Wp(cm, jb + w + w2, jb), cm.ldw, Wp(cm, jb + w + w2, jb + w + w2), cm.ldw, GEMM_LOWER);
+        if (trace) cudaEventRecord(t_restend[j], cm.st);
+    }
+    cudaStreamWaitEvent(cm.st, e_panel[last], 0);  // join
+    if (trace) {
+        cudaStreamSynchronize(cm.st);
+        cudaStreamSynchronize(ps);
+        for (int j = 0; j <= last; j++) {
+            float a = 0, b = 0, c2 = 0, d = 0;
+            cudaEventElapsedTime(&a, e_fork, t_pstart[j]);
+            cudaEventElapsedTime(&b, e_fork, e_panel[j]);
+            if (j < last) {
+                cudaEventElapsedTime(&c2, e_fork, e_col[j + 1]);
+                cudaEventElapsedTime(&d, e_fork, t_restend[j]);
+            }
+            fprintf(stderr, "[lgp trace] panel %3d: start %8.3f done %8.3f (%.3f ms) | colupd done %8.3f rest done %8.3f\n", j,
+                    a, b, b - a, c2, d);
+        }
+        for (int i = 0; i < np; i++) {
+            cudaEventDestroy(t_pstart[i]);
+            cudaEventDestroy(t_restend[i]);
+        }
+        delete[] t_pstart;
+        delete[] t_restend;
+    }
+    for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
+    delete[] ev;
+    if (rc == LGP_OK && cudaGetLastError() != cudaSuccess) rc = LGP_ERR_CUDA;
+    return rc;
 }
 
 struct SolveCtx {
@@ -370,7 +554,7 @@ static void solve_lower_rec(SolveCtx &c, int jb, int nb) {
     double *Bj = c.B + (int64_t)jb * NB * c.ldb;
     if (nb == 1) {
         RC(gemm_launch(c.st, true, false, rows, c.m, rows, 1.0, c.invd + (int64_t)jb * NB * NB, NB, Bj, c.ldb, Bj,
-                       c.ldb, GEMM_BETA0 | GEMM_A_LOWER_K));
+                       c.ldb, GEMM_BETA0 | GEMM_A_LOWER_K | GEMM_INPLACE_B));
         return;
     }
     int n1 = nb / 2, n2 = nb - n1;
@@ -392,7 +576,7 @@ static void solve_upper_rec(SolveCtx &c, int jb, int nb) {
     double *Bj = c.B + (int64_t)jb * NB * c.ldb;
     if (nb == 1) {
         RC(gemm_launch(c.st, false, false, rows, c.m, rows, 1.0, c.invd + (int64_t)jb * NB * NB, NB, Bj, c.ldb, Bj,
-                       c.ldb, GEMM_BETA0 | GEMM_A_UPPER_K));
+                       c.ldb, GEMM_BETA0 | GEMM_A_UPPER_K | GEMM_INPLACE_B));
         return;
     }
     int n1 = nb / 2, n2 = nb - n1;
@@ -479,12 +663,28 @@ int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const dou
     chol_jitter_kernel<<<1, 1024, 0, st>>>(n, npad, epsrel, epsabs, W, ldw, aux, info);
     LGP_CUDA_CHECK_LAUNCH();
     CholCtx c{st, W, ldw, aux + LGP_AUX_INVDIAG(npad), aux + LGP_AUX_DIAG(npad), info, LGP_OK};
-    potrf_rec(c, 0, npad / NB);
-    if (c.rc) return c.rc;
+    {
+        int pb = 4;
+        const char *e = getenv("LGP_PANEL_BLOCKS");
+        if (e && atoi(e) > 0) pb = atoi(e);
+        int rc = potrf_lookahead(c, npad / NB, pb);
+        if (rc) return rc;
+    }
     finalize_info_kernel<<<1, 1, 0, st>>>(info, n);
     LGP_CUDA_CHECK_LAUNCH();
     logdet_quad_kernel<<<1, 1024, 0, st>>>(aux + LGP_AUX_DIAG(npad), aux + LGP_AUX_S(npad), nullptr, n,
                                            aux + LGP_AUX_SCALARS(npad) + 4);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+// debug/benchmark hook (not in the public header): run the 128x128 leaf `reps` times back to back
+int lgp_debug_leaf(lgp_stream_t stream, double *Wblk, int64_t ld, double *invd, double *dvec, int32_t *info, int reps,
+                   int variant) {
+    (void)variant;
+    cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
+    for (int i = 0; i < reps; i++)
+        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, (cudaStream_t)stream>>>(Wblk, ld, invd, dvec, info, 0);
     LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
 }

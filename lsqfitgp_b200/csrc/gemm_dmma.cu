@@ -4,41 +4,58 @@
 
 namespace lgp {
 
+template <class Cfg, bool AK, bool BK_>
+static int launch_cfg(cudaStream_t stream, GemmParams &p) {
+    p.tiles_m = (p.M + Cfg::BM - 1) / Cfg::BM;
+    p.tiles_n = (p.N + Cfg::BN - 1) / Cfg::BN;
+    int64_t grid = (p.flags & GEMM_LOWER) ? (int64_t)p.tiles_m * (p.tiles_m + 1) / 2 : (int64_t)p.tiles_m * p.tiles_n;
+    if (grid > 2147483647LL) return LGP_ERR_UNSUPPORTED;
+    static bool attr_set = false;  // one flag per template instantiation
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_dmma_kernel<Cfg, AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES) != cudaSuccess)
+            return LGP_ERR_CUDA;
+        attr_set = true;
+    }
+    gemm_dmma_kernel<Cfg, AK, BK_><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+template <class Cfg>
+static int launch_layout(cudaStream_t stream, bool a_kmaj, bool b_kmaj, GemmParams &p) {
+    if (a_kmaj && b_kmaj) return launch_cfg<Cfg, true, true>(stream, p);
+    if (a_kmaj && !b_kmaj) return launch_cfg<Cfg, true, false>(stream, p);
+    if (!a_kmaj && b_kmaj) return launch_cfg<Cfg, false, true>(stream, p);
+    return launch_cfg<Cfg, false, false>(stream, p);
+}
+
 // Host-side launcher (internal; the C ABI wrapper is lgp_dgemm in capi.cu).
-int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int K, double alpha,
-                       const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
-                       int flags) {
+int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int K, double alpha, const double *A,
+                int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int flags) {
     if (M <= 0 || N <= 0) return LGP_OK;
     if ((lda & 1) || (ldb & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return LGP_ERR_ALIGN;
     if ((flags & GEMM_LOWER) && M != N) return LGP_ERR_BADARG;
+    if ((flags & GEMM_INPLACE_A) && N > 128) return LGP_ERR_BADARG;
+    if ((flags & GEMM_INPLACE_B) && M > 128) return LGP_ERR_BADARG;
     GemmParams p;
     p.A = A; p.B = B; p.C = C;
     p.M = M; p.N = N; p.K = K;
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.alpha = alpha;
     p.flags = flags;
-    p.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
-    p.tiles_n = (N + GEMM_BN - 1) / GEMM_BN;
-    int grid = (flags & GEMM_LOWER) ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-        attr_set = true;
+    // tile configuration: big tiles when they fill the machine, small ones for latency-bound products
+    const int64_t tm = (M + 127) / 128, tn = (N + 127) / 128;
+    const int64_t big_tiles = (flags & GEMM_LOWER) ? tm * (tm + 1) / 2 : tm * tn;
+    const bool small_ok = big_tiles < 112 && !(flags & GEMM_FORCE_BIG);
+    if (flags & GEMM_INPLACE_B) return launch_layout<GemmBig>(stream, a_kmaj, b_kmaj, p);
+    if (flags & GEMM_INPLACE_A) {
+        if (small_ok && a_kmaj && b_kmaj) return launch_cfg<GemmTall, true, true>(stream, p);
+        return launch_layout<GemmBig>(stream, a_kmaj, b_kmaj, p);
     }
-    if (a_kmaj && b_kmaj)
-        gemm_dmma_kernel<true, true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
-    else if (a_kmaj && !b_kmaj)
-        gemm_dmma_kernel<true, false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
-    else if (!a_kmaj && b_kmaj)
-        gemm_dmma_kernel<false, true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
-    else
-        gemm_dmma_kernel<false, false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
-    LGP_CUDA_CHECK_LAUNCH();
-    return LGP_OK;
+    if (small_ok) return launch_layout<GemmSmall>(stream, a_kmaj, b_kmaj, p);
+    return launch_layout<GemmBig>(stream, a_kmaj, b_kmaj, p);
 }
 
 }  // namespace lgp

@@ -13,9 +13,10 @@
 // Cholesky that replaces jax.scipy.linalg.cholesky / solve_triangular in the reference
 // (reference: src/lsqfitgp/_linalg/_decomp.py:388,402-403,467-472).
 //
-// CTA tile 128x128x16, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA tiles, 4-stage cp.async
-// pipeline.  tcgen05/TMEM have no f64 kind, so the legacy warp-level MMA is the FP64 tensor
-// path on sm_100a.
+// Two tile configurations: 128x128x16 with 16 warps (4x4, warp tile 32x32) for large problems, and
+// 64x64x16 with 4 warps (2x2) for the small, latency-bound products on the panel critical path.
+// Multi-stage cp.async pipeline.  tcgen05/TMEM have no f64 kind, so the warp-level DMMA is the FP64
+// tensor path on sm_100a.
 #pragma once
 #include "common.cuh"
 
@@ -28,6 +29,9 @@ enum GemmFlags : int {
     GEMM_B_LOWER_K = 8,   // Bop[j][k] == 0 for k > j
     GEMM_A_UPPER_K = 16,  // Aop[i][k] == 0 for k < i
     GEMM_B_UPPER_K = 32,  // Bop[j][k] == 0 for k < j
+    GEMM_INPLACE_A = 64,   // C aliases A (rows of C depend on the same rows of A only): needs N <= BN
+    GEMM_INPLACE_B = 128,  // C aliases B: needs M <= BM
+    GEMM_FORCE_BIG = 256,  // always use the 128x128 configuration
 };
 
 struct GemmParams {
@@ -41,26 +45,36 @@ struct GemmParams {
     int tiles_m, tiles_n;
 };
 
-constexpr int GEMM_BM = 128;
-constexpr int GEMM_BN = 128;
 constexpr int GEMM_BK = 16;
-constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 256;
-// k-major tile: 128 rows x 128 B, 16-B chunks XOR-swizzled by ((row&1)<<2): conflict-free LDS.128
-constexpr int GEMM_TILE_KMAJ_BYTES = GEMM_BM * GEMM_BK * 8;  // 16384
-// m-major tile: 16 k-rows x 130 doubles (stride 1040 B): conflict-free LDS.64
-constexpr int GEMM_MMAJ_STRIDE = 130;
-constexpr int GEMM_TILE_MMAJ_BYTES = GEMM_BK * GEMM_MMAJ_STRIDE * 8;  // 16640
-constexpr int GEMM_TILE_BYTES = GEMM_TILE_MMAJ_BYTES;                  // per operand per stage
-constexpr int GEMM_SMEM_BYTES = 2 * GEMM_STAGES * GEMM_TILE_BYTES;     // 133120
 
-template <bool KMAJ>
+template <int BM_, int BN_, int WARPS_M_, int WARPS_N_, int STAGES_>
+struct GemmCfg {
+    static constexpr int BM = BM_, BN = BN_, WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, STAGES = STAGES_;
+    static constexpr int THREADS = 32 * WARPS_M * WARPS_N;
+    static constexpr int MI = BM / (8 * WARPS_M);  // 8-row DMMA fragments per warp (rows)
+    static constexpr int NJ = BN / (8 * WARPS_N);  // 8-col DMMA fragments per warp (cols)
+    // k-major tile: rows x 128 B, 16-B chunks XOR-swizzled by ((row&1)<<2): conflict-free LDS.128
+    // m-major tile: 16 k-rows x (rows+2) doubles: conflict-free LDS.64 for the k = 8g+2q+t slot order
+    static constexpr int A_BYTES = (BM + 2) * GEMM_BK * 8;
+    static constexpr int B_BYTES = (BN + 2) * GEMM_BK * 8;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES;
+};
+
+using GemmBig = GemmCfg<128, 128, 4, 4, 4>;
+using GemmSmall = GemmCfg<64, 64, 2, 2, 4>;
+using GemmTall = GemmCfg<64, 128, 2, 4, 4>;  // in-place right-TRSM leaf: full N = 128 in one tile
+
+template <bool KMAJ, int ROWS, int THREADS>
 __device__ __forceinline__ void gemm_load_tile(uint32_t smem_tile, const double *__restrict__ G, int64_t ld,
                                                int r0, int rows_total, int k0, int k_total, int tid) {
+    constexpr int CHUNKS = ROWS * GEMM_BK / 2;
+    static_assert(CHUNKS % THREADS == 0, "tile chunks must divide evenly among threads");
+    constexpr int ITERS = CHUNKS / THREADS;
     if (KMAJ) {
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
-            int id = tid + it * GEMM_THREADS;
+        for (int it = 0; it < ITERS; it++) {
+            int id = tid + it * THREADS;
             int row = id >> 3, c = id & 7;
             int gr = r0 + row, gk = k0 + 2 * c;
             int bytes = 0;
@@ -73,10 +87,11 @@ __device__ __forceinline__ void gemm_load_tile(uint32_t smem_tile, const double 
             cp_async16(dst, src, bytes);
         }
     } else {
+        constexpr int CPR = ROWS / 2;  // 16-byte chunks per k-row
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
-            int id = tid + it * GEMM_THREADS;
-            int krow = id >> 6, c = id & 63;
+        for (int it = 0; it < ITERS; it++) {
+            int id = tid + it * THREADS;
+            int krow = id / CPR, c = id % CPR;
             int gk = k0 + krow, gr = r0 + 2 * c;
             int bytes = 0;
             if (gk < k_total) {
@@ -84,14 +99,14 @@ __device__ __forceinline__ void gemm_load_tile(uint32_t smem_tile, const double 
                 bytes = rem >= 16 ? 16 : (rem > 0 ? rem : 0);
             }
             const double *src = bytes ? (G + (int64_t)gk * ld + gr) : G;
-            uint32_t dst = smem_tile + krow * (GEMM_MMAJ_STRIDE * 8) + c * 16;
+            uint32_t dst = smem_tile + krow * ((ROWS + 2) * 8) + c * 16;
             cp_async16(dst, src, bytes);
         }
     }
 }
 
 // Fragment for MMA slot q (= lane%4) within 8-k group g: k = 8g + 2q + t, t in {0,1}.
-template <bool KMAJ>
+template <bool KMAJ, int ROWS>
 __device__ __forceinline__ void gemm_load_frag(const unsigned char *tile, int row, int g, int q, double &v0,
                                                double &v1) {
     if (KMAJ) {
@@ -101,18 +116,19 @@ __device__ __forceinline__ void gemm_load_frag(const unsigned char *tile, int ro
         v1 = v.y;
     } else {
         int k = 8 * g + 2 * q;
-        const double *p = reinterpret_cast<const double *>(tile) + k * GEMM_MMAJ_STRIDE + row;
+        const double *p = reinterpret_cast<const double *>(tile) + k * (ROWS + 2) + row;
         v0 = p[0];
-        v1 = p[GEMM_MMAJ_STRIDE];
+        v1 = p[ROWS + 2];
     }
 }
 
-template <bool A_KMAJ, bool B_KMAJ>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmParams p) {
+template <class Cfg, bool A_KMAJ, bool B_KMAJ>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_dmma_kernel(const GemmParams p) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, MI = Cfg::MI, NJ = Cfg::NJ, STAGES = Cfg::STAGES;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+    const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
     const int lr = lane >> 2, q = lane & 3;
 
     int tm, tn;
@@ -128,68 +144,70 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmPa
         tm = blockIdx.x % p.tiles_m;
         tn = blockIdx.x / p.tiles_m;
     }
-    const int m0 = tm * GEMM_BM, n0 = tn * GEMM_BN;
+    const int m0 = tm * BM, n0 = tn * BN;
 
     int k_begin = 0, k_end = p.K;
-    if (p.flags & GEMM_A_LOWER_K) k_end = min(k_end, m0 + GEMM_BM);
-    if (p.flags & GEMM_B_LOWER_K) k_end = min(k_end, n0 + GEMM_BN);
+    if (p.flags & GEMM_A_LOWER_K) k_end = min(k_end, m0 + BM);
+    if (p.flags & GEMM_B_LOWER_K) k_end = min(k_end, n0 + BN);
     if (p.flags & GEMM_A_UPPER_K) k_begin = max(k_begin, m0);
     if (p.flags & GEMM_B_UPPER_K) k_begin = max(k_begin, n0);
     k_begin &= ~(GEMM_BK - 1);
     const int KT = k_end > k_begin ? (k_end - k_begin + GEMM_BK - 1) / GEMM_BK : 0;
 
     const uint32_t smem_base = smem_u32(smem);
-    auto a_tile = [&](int s) { return smem_base + s * GEMM_TILE_BYTES; };
-    auto b_tile = [&](int s) { return smem_base + (GEMM_STAGES + s) * GEMM_TILE_BYTES; };
 
-    double acc[8][4][2];
+    double acc[MI][NJ][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // prologue
 #pragma unroll
-    for (int s = 0; s < GEMM_STAGES - 1; s++) {
+    for (int s = 0; s < STAGES - 1; s++) {
         if (s < KT) {
             int k0 = k_begin + s * GEMM_BK;
-            gemm_load_tile<A_KMAJ>(a_tile(s), p.A, p.lda, m0, p.M, k0, k_end, tid);
-            gemm_load_tile<B_KMAJ>(b_tile(s), p.B, p.ldb, n0, p.N, k0, k_end, tid);
+            gemm_load_tile<A_KMAJ, BM, Cfg::THREADS>(smem_base + s * Cfg::STAGE_BYTES, p.A, p.lda, m0, p.M, k0, k_end,
+                                                     tid);
+            gemm_load_tile<B_KMAJ, BN, Cfg::THREADS>(smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, p.B, p.ldb, n0,
+                                                     p.N, k0, k_end, tid);
         }
         cp_async_commit();
     }
 
     for (int kt = 0; kt < KT; kt++) {
-        cp_async_wait<GEMM_STAGES - 2>();
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
         {
-            int nk = kt + GEMM_STAGES - 1;
+            int nk = kt + STAGES - 1;
             if (nk < KT) {
-                int s = nk % GEMM_STAGES;
+                int s = nk % STAGES;
                 int k0 = k_begin + nk * GEMM_BK;
-                gemm_load_tile<A_KMAJ>(a_tile(s), p.A, p.lda, m0, p.M, k0, k_end, tid);
-                gemm_load_tile<B_KMAJ>(b_tile(s), p.B, p.ldb, n0, p.N, k0, k_end, tid);
+                gemm_load_tile<A_KMAJ, BM, Cfg::THREADS>(smem_base + s * Cfg::STAGE_BYTES, p.A, p.lda, m0, p.M, k0,
+                                                         k_end, tid);
+                gemm_load_tile<B_KMAJ, BN, Cfg::THREADS>(smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, p.B, p.ldb,
+                                                         n0, p.N, k0, k_end, tid);
             }
             cp_async_commit();
         }
-        const int s = kt % GEMM_STAGES;
-        const unsigned char *at = smem + s * GEMM_TILE_BYTES;
-        const unsigned char *bt = smem + (GEMM_STAGES + s) * GEMM_TILE_BYTES;
+        const int s = kt % STAGES;
+        const unsigned char *at = smem + s * Cfg::STAGE_BYTES;
+        const unsigned char *bt = at + Cfg::A_BYTES;
 #pragma unroll
         for (int g = 0; g < 2; g++) {
-            double af[8][2], bf[4][2];
+            double af[MI][2], bf[NJ][2];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                gemm_load_frag<A_KMAJ>(at, wm * 64 + i * 8 + lr, g, q, af[i][0], af[i][1]);
+            for (int i = 0; i < MI; i++)
+                gemm_load_frag<A_KMAJ, BM>(at, wm * (8 * MI) + i * 8 + lr, g, q, af[i][0], af[i][1]);
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                gemm_load_frag<B_KMAJ>(bt, wn * 32 + j * 8 + lr, g, q, bf[j][0], bf[j][1]);
+            for (int j = 0; j < NJ; j++)
+                gemm_load_frag<B_KMAJ, BN>(bt, wn * (8 * NJ) + j * 8 + lr, g, q, bf[j][0], bf[j][1]);
 #pragma unroll
             for (int t = 0; t < 2; t++)
 #pragma unroll
-                for (int i = 0; i < 8; i++)
+                for (int i = 0; i < MI; i++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i][t], bf[j][t]);
+                    for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i][t], bf[j][t]);
         }
     }
     cp_async_wait<0>();
@@ -199,13 +217,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmPa
     const bool beta0 = p.flags & GEMM_BETA0;
     const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        int row = m0 + wm * 64 + i * 8 + lr;
+    for (int i = 0; i < MI; i++) {
+        int row = m0 + wm * (8 * MI) + i * 8 + lr;
         if (row >= p.M) continue;
         double *crow = p.C + (int64_t)row * p.ldc;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int col = n0 + wn * 32 + j * 8 + 2 * q;
+        for (int j = 0; j < NJ; j++) {
+            int col = n0 + wn * (8 * NJ) + j * 8 + 2 * q;
             int cmax = lower ? min(p.N, row + 1) : p.N;  // exclusive bound on valid columns
             if (col >= cmax) continue;
             double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
