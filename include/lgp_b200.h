@@ -76,15 +76,19 @@ int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors,
                  int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, double *K_out, int64_t ldk,
                  int flags);
 
-/* Reverse-mode contraction of the Gram build: for the symmetric case x==y,
- *   out[f*(3)+0] = sum_ij G_ij * dK_ij/d amp_f
- *   out[f*(3)+1] = sum_ij G_ij * dK_ij/d log(scale_f)        (scale_x == scale_y == scale_f)
- *   out[f*(3)+2] = sum_ij G_ij * dK_ij/d par1_f              (Cauchy beta; 0 otherwise)
- * with G_ij = w_ij * (Ginv[i][j] - b_i b_j) read from the LOWER triangle of Ginv (w = 2 off-diagonal, 1 on it).
- * This is dK_vjp(invK) - dK_vjp(outer(invKr, invKr)) of Chol.minus_log_normal_density collapsed into one pass
- * (src/lsqfitgp/_linalg/_decomp.py:505-509; src/lsqfitgp/_fit.py:687-702).  out is device memory, 3*nfactors doubles. */
+/* Reverse-mode contraction of the Gram build (what jax.vjp of the Gram function gives the reference,
+ * src/lsqfitgp/_fit.py:687-702), without materialising dK:
+ *   out[3f+0] = sum_ij G_ij * dK_ij/d amp_f
+ *   out[3f+1] = sum_ij G_ij * dK_ij/d log(scale_f)        (scale_x == scale_y == scale_f)
+ *   out[3f+2] = sum_ij G_ij * dK_ij/d par1_f              (Cauchy beta; 0 otherwise)
+ * symlower = 0: G is a dense n x m matrix (ldg).  symlower = 1: x == y and G_ij = w_ij (G[i][j] - b_i b_j) read from
+ * the LOWER triangle only, w = 2 off the diagonal: with G = (K+eps)^-1 and b = K^-1 r this is
+ * dK_vjp(invK) - dK_vjp(outer(invKr, invKr)) of Chol.minus_log_normal_density collapsed into one pass
+ * (src/lsqfitgp/_linalg/_decomp.py:505-509).  b may be NULL.  out: device memory, 3*nfactors doubles
+ * (accumulated with atomicAdd: summation order, hence the last bits, may vary from run to run). */
 int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
-                     int64_t ldx, int64_t n, const double *Ginv, int64_t ldg, const double *b, double *out);
+                     int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, const double *G, int64_t ldg,
+                     const double *b, int symlower, double *out);
 
 /* ------------------------------------------------------------------------------------------------
  * BART Gram (fast path of BART._correlation: src/lsqfitgp/_kernels/_bart.py:628-757, with the
@@ -114,6 +118,12 @@ int lgp_bart_digamma_table(double *psi_out, int64_t len);
 #define LGP_GEMM_B_UPPER_K 32
 int lgp_dgemm(lgp_stream_t stream, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
               const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int flags);
+
+/* Y = alpha*X + beta*Y + gamma*I over an n x m block (X may be NULL).  The elementwise block sums of
+ * _assemblecovblocks / addtransf with scalar tensors (src/lsqfitgp/_GP/_elements.py:581-601,642-649) and
+ * `Kxx + ycov` (src/lsqfitgp/_GP/_compute.py:84-85). */
+int lgp_axpby(lgp_stream_t stream, int64_t n, int64_t m, double alpha, const double *X, int64_t ldx, double beta,
+              double *Y, int64_t ldy, double gamma);
 
 /* ------------------------------------------------------------------------------------------------
  * Cholesky with lsqfitgp's equilibration + Gershgorin jitter (Chol.__init__,

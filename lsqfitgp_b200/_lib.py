@@ -54,11 +54,13 @@ SIGNATURES = {
     'lgp_abi_version': (_int, []),
     'lgp_build_info': (ctypes.c_char_p, []),
     'lgp_gram_iso': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int]),
-    'lgp_gram_iso_vjp': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    'lgp_gram_iso_vjp': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64,
+                                _vp, _int, _vp]),
     'lgp_gram_bart': (_int, [_vp, _int, c_int32_p, c_double_p, c_double_p, _int, _int, _dbl, _dbl, _vp,
                              _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int]),
     'lgp_bart_digamma_table': (_int, [c_double_p, _i64]),
     'lgp_dgemm': (_int, [_vp, _int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _vp, _i64, _int]),
+    'lgp_axpby': (_int, [_vp, _i64, _i64, _dbl, _vp, _i64, _dbl, _vp, _i64, _dbl]),
     'lgp_chol_npad': (_i64, [_i64]),
     'lgp_chol_aux_doubles': (_i64, [_i64]),
     'lgp_chol_factor': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, _i64, _vp, _vp]),

@@ -42,6 +42,16 @@ def dgemm(A, B, C, *, a_kmajor, b_kmajor, M, N, K, alpha=1.0, flags=0):
     return C
 
 
+def axpby(alpha, X, beta, Y, gamma=0.0):
+    """ Y = alpha*X + beta*Y + gamma*I in place (X may be None) """
+    lib = _lib.load()
+    n, m = Y.shape
+    assert Y.stride(1) == 1 and (X is None or (X.shape == Y.shape and X.stride(1) == 1))
+    check(lib.lgp_axpby(stream_ptr(), n, m, float(alpha), ptr(X), X.stride(0) if X is not None else 0, float(beta),
+                        ptr(Y), Y.stride(0), float(gamma)), 'lgp_axpby')
+    return Y
+
+
 # ---------------------------------------------------------------------------------------------
 # Gram
 # ---------------------------------------------------------------------------------------------
@@ -82,14 +92,32 @@ def gram_iso(descs, x, y, out=None, symmetric=False):
 
 
 def gram_iso_vjp(descs, x, Ginv, b):
-    """ returns a (nfactors, 3) device tensor: d/d amp, d/d log(scale), d/d par1 (see lgp_b200.h) """
+    """ symmetric fused form: (nfactors, 3) device tensor of sum_ij w_ij (Ginv_ij - b_i b_j) dK_ij/d(amp, log scale,
+    par1), reading the lower triangle of Ginv (see lgp_b200.h) """
     lib = _lib.load()
     ndim, n = x.shape
     x = x.contiguous() if x.stride(1) != 1 else x
     out = torch.empty((len(descs), 3), dtype=f64, device=x.device)
     facs = make_factors(descs)
     check(lib.lgp_gram_iso_vjp(stream_ptr(), facs, len(descs), ndim, ptr(x), x.stride(0) if ndim else 0, n,
-                               ptr(Ginv), Ginv.stride(0), ptr(b), ptr(out)), 'lgp_gram_iso_vjp')
+                               ptr(x), x.stride(0) if ndim else 0, n, ptr(Ginv), Ginv.stride(0), ptr(b), 1, ptr(out)),
+          'lgp_gram_iso_vjp')
+    return out
+
+
+def gram_iso_vjp_general(descs, x, y, G):
+    """ general form: G dense (n, m); returns (nfactors, 3) """
+    lib = _lib.load()
+    ndim, n = x.shape
+    m = y.shape[1]
+    x = x.contiguous() if x.stride(1) != 1 else x
+    y = y.contiguous() if y.stride(1) != 1 else y
+    assert G.shape == (n, m) and G.stride(1) == 1
+    out = torch.empty((len(descs), 3), dtype=f64, device=x.device)
+    facs = make_factors(descs)
+    check(lib.lgp_gram_iso_vjp(stream_ptr(), facs, len(descs), ndim, ptr(x), x.stride(0) if ndim else 0, n,
+                               ptr(y), y.stride(0) if ndim else 0, m, ptr(G), G.stride(0), None, 0, ptr(out)),
+          'lgp_gram_iso_vjp')
     return out
 
 

@@ -250,27 +250,36 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_kernel(const __grid_consta
     }
 }
 
-// Reverse-mode contraction over the lower triangle of the symmetric Gram (x == y).
+// Reverse-mode contraction of the Gram build: out[f][.] += sum_ij G_ij dK_ij/d(param of factor f).
+// symlower = 0: G is a dense n x m matrix, all pairs (i, j) are visited.
+// symlower = 1: x == y, only j <= i is visited, G_ij = w_ij (Ginv[i][j] - b_i b_j) with w = 2 off the diagonal
+//               (the collapsed dK_vjp(invK) - dK_vjp(outer(invKr, invKr)) of _decomp.py:505-509).
 // acc layout per factor: [0] d/d amp, [1] d/d log(scale), [2] d/d par1
 __global__ void __launch_bounds__(G_THREADS) gram_iso_vjp_kernel(const __grid_constant__ GramDesc d,
                                                                  const double *__restrict__ x, int64_t ldx,
-                                                                 int64_t n, const double *__restrict__ G, int64_t ldg,
-                                                                 const double *__restrict__ bvec,
-                                                                 double *__restrict__ out) {
+                                                                 int64_t n, const double *__restrict__ y, int64_t ldy,
+                                                                 int64_t m, const double *__restrict__ G, int64_t ldg,
+                                                                 const double *__restrict__ bvec, int symlower,
+                                                                 int tiles_n, double *__restrict__ out) {
     extern __shared__ __align__(16) double gsm[];
     double *su = gsm;
     double *sv = gsm + (size_t)d.nslots * GT;
     __shared__ double red[G_THREADS / 32][3 * LGP_MAX_FACTORS];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    // lower-triangular tile enumeration
-    int b = blockIdx.x;
-    int tm = (int)((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
-    while ((tm + 1) * (tm + 2) / 2 <= b) tm++;
-    while (tm * (tm + 1) / 2 > b) tm--;
-    int tn = b - tm * (tm + 1) / 2;
+    int tm, tn;
+    if (symlower) {
+        int b = blockIdx.x;
+        tm = (int)((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
+        while ((tm + 1) * (tm + 2) / 2 <= b) tm++;
+        while (tm * (tm + 1) / 2 > b) tm--;
+        tn = b - tm * (tm + 1) / 2;
+    } else {
+        tm = blockIdx.x / tiles_n;
+        tn = blockIdx.x % tiles_n;
+    }
     const int64_t i0 = (int64_t)tm * GT, j0 = (int64_t)tn * GT;
     stage_points(d, su, x, ldx, n, i0, false, tid);
-    stage_points(d, sv, x, ldx, n, j0, true, tid);
+    stage_points(d, sv, y, ldy, m, j0, true, tid);
     __syncthreads();
 
     double acc[3 * LGP_MAX_FACTORS];
@@ -286,10 +295,10 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_vjp_kernel(const __grid_co
         for (int c = 0; c < 4; c++) {
             const int cc = 2 * tx + 32 * (c >> 1) + (c & 1);
             const int64_t j = j0 + cc;
-            if (j > i || j >= n) continue;
+            if (j >= m || (symlower && j > i)) continue;
             double g = G[i * ldg + j];
             if (bvec) g -= bi * bvec[j];
-            if (j != i) g *= 2.0;
+            if (symlower && j != i) g *= 2.0;
             // evaluate all factors
             double val[LGP_MAX_FACTORS], dr2[LGP_MAX_FACTORS], dp1[LGP_MAX_FACTORS], r2s[LGP_MAX_FACTORS];
 #pragma unroll
@@ -371,8 +380,10 @@ int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors,
 }
 
 int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
-                     int64_t ldx, int64_t n, const double *Ginv, int64_t ldg, const double *b, double *out) {
-    if (!factors || !Ginv || !out || n < 1) return LGP_ERR_BADARG;
+                     int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, const double *G, int64_t ldg,
+                     const double *b, int symlower, double *out) {
+    if (!factors || !G || !out || n < 1 || m < 1) return LGP_ERR_BADARG;
+    if (symlower && (n != m)) return LGP_ERR_BADARG;
     GramDesc d;
     int rc = build_desc(factors, nfactors, ndim, d);
     if (rc) return rc;
@@ -385,10 +396,11 @@ int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfact
     cudaStream_t st = (cudaStream_t)stream;
     zero_kernel<<<1, 32, 0, st>>>(out, 3 * nfactors);
     LGP_CUDA_CHECK_LAUNCH();
-    int64_t t = (n + GT - 1) / GT;
-    int64_t nblk = t * (t + 1) / 2;
+    int64_t tm = (n + GT - 1) / GT, tn = (m + GT - 1) / GT;
+    int64_t nblk = symlower ? tm * (tm + 1) / 2 : tm * tn;
     if (nblk > 2147483647LL) return LGP_ERR_UNSUPPORTED;
-    gram_iso_vjp_kernel<<<(unsigned)nblk, G_THREADS, smem, st>>>(d, x, ldx, n, Ginv, ldg, b, out);
+    gram_iso_vjp_kernel<<<(unsigned)nblk, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, G, ldg, b, symlower, (int)tn,
+                                                                 out);
     LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
 }
