@@ -138,7 +138,7 @@ class CrossKernel:
     def __add__(self, other):
         if _isscalar(other):
             const = _Term(other, (_Factor(_lib.K_CONSTANT),))
-            return self._clone(_common_class(type(self), Kernel), terms=self._terms + (const,))
+            return self._clone(_common_class(type(self), IsotropicKernel), terms=self._terms + (const,))
         if isinstance(other, CrossKernel):
             return self._clone(_common_class(type(self), type(other)), terms=self._terms + other._terms,
                                bart=self._bart + other._bart)

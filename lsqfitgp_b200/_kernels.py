@@ -300,6 +300,8 @@ class BART(Kernel):
         n, ix, iy = numpy.broadcast_arrays(n, ix, iy)
         shape = ix.shape[:-1]
         p = ix.shape[-1]
+        if p == 0:
+            return numpy.ones(shape)  # no covariates: correlation 1 (reference _bart.py:659-661)
         flatn = n.reshape(-1, p)
         out = numpy.empty(flatn.shape[0])
         _lib.require_cuda()

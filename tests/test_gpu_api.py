@@ -1,0 +1,326 @@
+"""GPU parity through the public API (GP / kernels / Chol / empbayes_fit) against the oracle and the golden
+fixtures.  Tolerances from BASELINE.json north_star: Gram 1e-13 relative; logML, gradient, posterior mean 1e-9."""
+import pathlib
+
+import numpy as np
+import pytest
+import torch
+from scipy import optimize, stats
+
+import lsqfitgp_b200 as lgp
+from oracle import gp as ogp, bart as obart, decomp as odecomp
+
+pytestmark = pytest.mark.gpu
+GOLD = pathlib.Path(__file__).resolve().parent / 'golden'
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def test_config1_full_size():
+    """ C1: lgp.GP(lgp.ExpQuad()) 1-D regression n=1000: marginal_likelihood + predfromdata """
+    rng = np.random.default_rng(1001)
+    x = np.sort(rng.uniform(0, 100, 1000))
+    y = np.sin(x / 3) + 0.1 * rng.standard_normal(1000)
+    xpred = np.linspace(-5, 105, 500)
+    gp = lgp.GP(lgp.ExpQuad(scale=3)).addx(x, 'data').addx(xpred, 'pred')
+    ycov = 0.01 * np.eye(1000)
+    ml = gp.marginal_likelihood({'data': y}, {('data', 'data'): ycov})
+    terms = [(1.0, [dict(kind='expquad', scale=3)])]
+    Kxx = ogp.gram(terms, x[None], x[None])
+    Kxs = ogp.gram(terms, x[None], xpred[None])
+    Kss = ogp.gram(terms, xpred[None], xpred[None])
+    ml_o = ogp.logml(Kxx, y, ycov)
+    assert abs(ml - ml_o) / abs(ml_o) < 1e-9
+    m, c = gp.predfromdata({'data': y}, 'pred', {('data', 'data'): ycov}, raw=True)
+    m_o, c_o = ogp.pred(Kxx, Kxs, Kss, y, ycov)
+    assert rel(m, m_o) < 1e-9
+    assert np.max(np.abs(c - c_o)) < 1e-9
+    prior = gp.prior('data', raw=True)
+    assert np.max(np.abs(prior - Kxx) / np.abs(Kxx).clip(1e-300)) < 1e-13
+    md, cd = gp.predfromdata({'data': y}, ['pred', 'data'], {('data', 'data'): ycov}, raw=True)
+    assert rel(md['pred'], m_o) < 1e-9 and cd['pred', 'data'].shape == (500, 1000)
+
+
+def test_predfromfit_vs_oracle():
+    """ fromdata=False: cov = Kss - Ksx K^-1 Kxs + A' ycov A, A = K^-1 Kxs (reference _compute.py:262-269) """
+    rng = np.random.default_rng(77)
+    x = np.sort(rng.uniform(0, 30, 120))
+    xp = np.linspace(0, 30, 31)
+    y = rng.standard_normal(120)
+    k = lgp.ExpQuad(scale=3) + 0.1 * lgp.White()
+    gp = lgp.GP(k).addx(x, 'data').addx(xp, 'pred')
+    ycov = np.diag(rng.uniform(0.01, 0.1, 120))
+    mf, cf = gp.predfromfit({'data': y}, 'pred', {('data', 'data'): ycov}, raw=True)
+    terms = [(1.0, [dict(kind='expquad', scale=3)]), (0.1, [dict(kind='white')])]
+    Kxx = ogp.gram(terms, x[None], x[None])
+    Kxs = ogp.gram(terms, x[None], xp[None])
+    Kss = ogp.gram(terms, xp[None], xp[None])
+    do = odecomp.Chol(Kxx)
+    A = do.ginv_linear(Kxs)
+    assert rel(mf, do.pinv_bilinear(Kxs, y)) < 1e-9
+    assert rel(cf, Kss - do.ginv_quad(Kxs) + A.T @ ycov @ A) < 1e-9
+
+
+def test_golden_c1():
+    g = np.load(GOLD / 'c1_expquad.npz')
+    n = len(g['x'])
+    gp = lgp.GP(lgp.ExpQuad(scale=3)).addx(g['x'], 'data').addx(g['xpred'], 'pred')
+    ycov = {('data', 'data'): 0.01 * np.eye(n)}
+    K = gp.prior('data', raw=True)
+    assert np.max(np.abs(K[0] - g['gram_row0']) / g['gram_row0'].clip(1e-300)) < 1e-13
+    assert abs(gp.marginal_likelihood({'data': g['y']}, ycov) - g['logml']) / abs(g['logml']) < 1e-9
+    m, c = gp.predfromdata({'data': g['y']}, 'pred', ycov, raw=True)
+    assert rel(m, g['mean']) < 1e-9
+    assert np.max(np.abs(np.diag(c) - g['cov_diag'])) < 1e-9
+
+
+def _c2_gp(X, theta):
+    xs = lgp.unstructured_to_structured(X, names=['f0', 'f1', 'f2'])
+    ell, sf, sn = torch.exp(theta[0]), torch.exp(theta[1]), torch.exp(theta[2])
+    kern = sf ** 2 * lgp.Matern(nu=2.5, scale=ell) + sn ** 2 * lgp.White()
+    return lgp.GP(kern, checkpos=False, checksym=False).addx(xs, 'data')
+
+
+def test_golden_c2_value_and_gradient():
+    g = np.load(GOLD / 'c2_matern.npz')
+    theta = torch.tensor(g['theta'], dtype=torch.float64, requires_grad=True)
+    gp = _c2_gp(g['X'], theta)
+    ml = gp.marginal_likelihood({'data': g['y']})
+    grad, = torch.autograd.grad(ml, theta)
+    assert abs(float(ml.detach()) + g['minus_logml']) / abs(g['minus_logml']) < 1e-9
+    assert rel(-grad.numpy(), g['grad_minus_logml']) < 1e-9
+    K = gp.prior('data', raw=True)
+    assert np.max(np.abs(K[0] - g['gram_row0']) / g['gram_row0']) < 1e-13
+    assert np.max(np.abs(K[:, 5] - g['gram_col5']) / g['gram_col5']) < 1e-13
+
+
+def test_config2_mid_size_vs_oracle():
+    """ C2 at n=1500 (oracle gradient is O(n^3) on the CPU): value, gradient, Gram """
+    rng = np.random.default_rng(2002)
+    n = 1500
+    X = rng.uniform(0, 10, (n, 3))
+    y = np.sin(X[:, 0]) + np.cos(X[:, 1]) * X[:, 2] / 10 + 0.1 * rng.standard_normal(n)
+    theta = torch.tensor([np.log(1.5), 0.0, np.log(0.1)], dtype=torch.float64, requires_grad=True)
+    gp = _c2_gp(X, theta)
+    ml = gp.marginal_likelihood({'data': y})
+    g, = torch.autograd.grad(ml, theta)
+    terms = [(1.0, [dict(kind='matern', nu=2.5, scale=1.5)]), (0.01, [dict(kind='white')])]
+    val_o, grad_o = ogp.logml_and_grad(terms, X.T.copy(), y, [('logscale', 0, 0), ('amp', 0), ('amp', 1)])
+    grad_o = np.array([grad_o[0], grad_o[1] * 2.0, grad_o[2] * 2 * 0.01])
+    assert abs(float(ml.detach()) + val_o) / abs(val_o) < 1e-9
+    assert rel(-g.numpy(), grad_o) < 1e-9
+    Kg = gp.prior('data', raw=True)
+    Ko = ogp.gram(terms, X.T.copy(), X.T.copy())
+    assert np.max(np.abs(Kg - Ko) / np.abs(Ko)) < 1e-13
+    # no-grad path gives the same value as a float
+    with torch.no_grad():
+        ml2 = _c2_gp(X, theta.detach()).marginal_likelihood({'data': y})
+    assert isinstance(ml2, float) and abs(ml2 - float(ml.detach())) <= 1e-12 * abs(ml2)
+
+
+def test_config3_empbayes_fit_vs_oracle():
+    rng = np.random.default_rng(3003)
+    n = 400
+    X3 = rng.uniform(0, 100, (n, 2))
+    K3 = ogp.gram([(1.3 ** 2, [dict(kind='expquad', scale=8.0)])], X3.T.copy(), X3.T.copy())
+    y3 = np.linalg.cholesky(K3 + 1e-10 * np.eye(n)) @ rng.standard_normal(n) + 0.2 * rng.standard_normal(n)
+    x3 = lgp.unstructured_to_structured(X3, names=['a', 'b'])
+    hyperprior = {'log(ell)': (np.log(3), 1.0), 'log(sf)': (0.0, 1.0), 'log(sn)': (np.log(0.1), 1.0)}
+
+    def gpfactory(hp):
+        k = hp['sf'] ** 2 * lgp.ExpQuad(scale=hp['ell']) + hp['sn'] ** 2 * lgp.White()
+        return lgp.GP(k, checkpos=False, checksym=False).addx(x3, 'data')
+    fit = lgp.empbayes_fit(hyperprior, gpfactory, {'data': y3}, raises=False)
+
+    def obj(p):
+        hp = np.array([np.log(3), 0.0, np.log(0.1)]) + p
+        terms = [(np.exp(hp[1]) ** 2, [dict(kind='expquad', scale=np.exp(hp[0]))]),
+                 (np.exp(hp[2]) ** 2, [dict(kind='white')])]
+        v, g = ogp.logml_and_grad(terms, X3.T.copy(), y3, [('logscale', 0, 0), ('amp', 0), ('amp', 1)])
+        g = np.array([g[0], g[1] * 2 * np.exp(hp[1]) ** 2, g[2] * 2 * np.exp(hp[2]) ** 2])
+        return v + 0.5 * (3 * np.log(2 * np.pi) + p @ p), g + p
+    res = optimize.minimize(obj, np.zeros(3), jac=True, method='bfgs')
+    assert np.max(np.abs(fit.minresult.x - res.x)) < 1e-5      # reference tests/test_fit.py:142-176 uses atol 1e-5
+    assert abs(fit.minresult.fun - res.fun) / abs(res.fun) < 1e-9
+    assert set(fit.pmean) == set(hyperprior) and fit.pcov['log(ell)', 'log(sf)'].shape == ()
+    # same optimum without gradients
+    fit2 = lgp.empbayes_fit(hyperprior, gpfactory, {'data': y3}, raises=False, method='nograd',
+                            minkw=dict(options=dict(xatol=1e-7, fatol=1e-10, maxiter=2000)))
+    assert np.max(np.abs(fit2.minresult.x - res.x)) < 1e-4
+    # fixed parameter and explicit starting point
+    fit3 = lgp.empbayes_fit(hyperprior, gpfactory, {'data': y3}, raises=False, fix={'sn': True},
+                            initial={'log(ell)': np.log(5.0), 'log(sf)': 0.1, 'log(sn)': np.log(0.2)})
+    assert fit3.pmean['log(sn)'] == pytest.approx(np.log(0.2), abs=1e-15)
+    # additional_loss offsets the objective exactly (reference tests/test_fit.py:281-310)
+    fit4 = lgp.empbayes_fit(hyperprior, gpfactory, {'data': y3}, raises=False, additional_loss=lambda hp: 3.5)
+    assert fit4.minresult.fun == pytest.approx(fit.minresult.fun + 3.5, rel=1e-12)
+
+
+def test_golden_c4_bart():
+    g = np.load(GOLD / 'c4_bart.npz')
+    splits = lgp.BART.splits_from_coord(g['X'])
+    assert np.array_equal(splits[0], g['length'])
+    idx = lgp.BART.indices_from_coord(g['X'], splits)
+    assert np.array_equal(idx, g['idx'])
+    names = [f'c{i}' for i in range(idx.shape[1])]
+    xi = lgp.unstructured_to_structured(idx.astype(np.int32), names=names)
+    kb = lgp.BART(splits=splits, indices=True, alpha=0.95, beta=2, maxd=10, reset=[2, 4, 6, 8], gamma=1)
+    n = len(idx)
+    gp = lgp.GP(kb + 0.1 * lgp.White(), checkpos=False, checksym=False, epsrel=0).addx(xi, 'train')
+    K = gp.prior('train', raw=True)
+    assert np.max(np.abs(K - (g['gram'] + 0.1 * np.eye(n))) / (g['gram'] + 0.1 * np.eye(n))) < 1e-13
+    ml = gp.marginal_likelihood({'train': g['y']})
+    assert abs(ml - g['logml']) / abs(g['logml']) < 1e-9
+
+
+def test_bart_variants_vs_oracle():
+    rng = np.random.default_rng(4004)
+    n = 300
+    X4 = np.concatenate([rng.standard_normal((n, 8)), rng.integers(0, 2, (n, 2)).astype(float)], axis=1)
+    splits = lgp.BART.splits_from_coord(X4)
+    idx = lgp.BART.indices_from_coord(X4, splits)
+    xi = lgp.unstructured_to_structured(idx.astype(np.int32), names=[f'c{i}' for i in range(10)])
+    for kw in [dict(maxd=2), dict(maxd=1), dict(maxd=0), dict(maxd=4, reset=2), dict(maxd=2, gamma=0.3, intercept=False),
+               dict(maxd=10, reset=[2, 4, 6, 8]), dict(maxd=5, reset=[1, 2, 3, 4], gamma=0.0),
+               dict(maxd=6, reset=[2, 4], weights=np.r_[np.ones(5), 0., 2., 3., 0.5, 1.]),
+               dict(pnt=[0.9, 0.5, 0.2])]:
+        kb = lgp.BART(splits=splits, indices=True, **kw)
+        Kg = lgp.GP(kb, checkpos=False, checksym=False).addx(xi, 'train').prior('train', raw=True)
+        Ko = obart.gram(splits[0], idx, idx, **kw)
+        assert np.max(np.abs(Kg - Ko) / np.abs(Ko)) < 1e-13, kw
+    # coordinates instead of indices: identical (reference tests/kernels/test_bart.py:355-367, 0 ulp)
+    dt = [(f'c{i}', float) for i in range(10)]
+    xa = X4[:, None, :].copy().view(dt).squeeze(-1)
+    ya = X4[None, :40, :].copy().view(dt).squeeze(-1)
+    Kc = lgp.BART(splits=splits, indices=False, maxd=4, reset=2)(xa, ya)
+    ia = idx[:, None, :].astype(np.int64).copy().view([(f'c{i}', np.int64) for i in range(10)]).squeeze(-1)
+    ib = idx[None, :40, :].astype(np.int64).copy().view([(f'c{i}', np.int64) for i in range(10)]).squeeze(-1)
+    Ki = lgp.BART(splits=splits, indices=True, maxd=4, reset=2)(ia, ib)
+    assert np.array_equal(Kc, Ki)
+    # correlation classmethod: pair form and count form (reference test_altinput)
+    nn = splits[0]
+    c_alt = lgp.BART.correlation(nn, idx[:50], idx[50:100], maxd=4, reset=2, altinput=True)
+    lo, hi = np.minimum(idx[:50], idx[50:100]), np.maximum(idx[:50], idx[50:100])
+    c_cnt = lgp.BART.correlation(lo, hi - lo, nn - hi, maxd=4, reset=2)
+    np.testing.assert_allclose(c_alt, c_cnt, rtol=1e-15, atol=2e-15)
+    np.testing.assert_allclose(c_alt, obart.correlation(nn, idx[:50], idx[50:100], maxd=4, reset=2), rtol=1e-13)
+    empty = np.array([], int)
+    assert lgp.BART.correlation(empty, empty, empty) == 1
+
+
+def test_bart_recipe_logml():
+    """ bayestree.bart recipe (reference bayestree/_bart.py:187-205): lambda^2 BART + diag noise + constant """
+    rng = np.random.default_rng(4005)
+    n = 200
+    X = rng.standard_normal((n, 4))
+    splits = lgp.BART.splits_from_coord(X)
+    idx = lgp.BART.indices_from_coord(X, splits)
+    xi = lgp.unstructured_to_structured(idx.astype(np.int32), names=list('abcd'))
+    lam, sig, kk = 1.3, 0.5, 0.7
+    gp = (lgp.GP(lam ** 2 * lgp.BART(splits=splits, indices=True, maxd=10, reset=[2, 4, 6, 8]), checkpos=False,
+                 checksym=False, epsrel=0)
+          .addx(xi, 'trainmean').addcov(sig ** 2 * np.eye(n), 'trainnoise').addcov(kk ** 2, 'mean')
+          .addtransf({'trainmean': 1, 'trainnoise': 1, 'mean': 1}, 'train'))
+    y = rng.standard_normal(n)
+    ml = gp.marginal_likelihood({'train': y})
+    Ko = lam ** 2 * obart.gram(splits[0], idx, idx, maxd=10, reset=[2, 4, 6, 8]) + sig ** 2 * np.eye(n) + kk ** 2
+    ml_o = ogp.logml(Ko, y, epsrel=0)
+    assert abs(ml - ml_o) / abs(ml_o) < 1e-9
+    m, c = gp.predfromdata({'train': y}, 'trainmean', raw=True)
+    Kf = lam ** 2 * obart.gram(splits[0], idx, idx, maxd=10, reset=[2, 4, 6, 8])
+    m_o, c_o = ogp.pred(Ko, Kf, Kf, y, epsrel=0)
+    assert rel(m, m_o) < 1e-9
+
+
+@pytest.mark.parametrize('n', [1, 2, 10, 300])
+def test_chol_class_battery(n):
+    """ every Decomposition method against the oracle (reference tests/linalg/test_decomp.py:145-261) """
+    rng = np.random.default_rng(n)
+    O = stats.ortho_group.rvs(n, random_state=rng) if n > 1 else np.atleast_2d(1.0)
+    K = (O * (1 + 1e-3 + np.cos(1 + np.arange(n)))) @ O.T
+    K = (K + K.T) / 2
+    dec = lgp._linalg.Chol(K)
+    do = odecomp.Chol(K)
+    B = rng.standard_normal((n, 3))
+    r = rng.standard_normal(n)
+    assert abs(dec.eps - do.eps) / do.eps < 1e-12 and dec.n == n and dec.m == n
+    assert rel(dec.ginv_linear(B), do.ginv_linear(B)) < 1e-9
+    assert rel(dec.ginv_linear(r), do.ginv_linear(r)) < 1e-9
+    assert rel(dec.pinv_bilinear(B, r), do.pinv_bilinear(B, r)) < 1e-9
+    assert rel(dec.pinv_bilinear_robj(B, r), do.pinv_bilinear(B, r)) < 1e-9
+    assert rel(dec.ginv_quad(B), do.ginv_quad(B)) < 1e-9
+    assert rel(dec.ginv_diagquad(B), do.ginv_diagquad(B)) < 1e-9
+    assert rel(dec.correlate(B), do.correlate(B)) < 1e-11
+    assert rel(dec.back_correlate(B), do.back_correlate(B)) < 1e-11
+    assert rel(dec.pinv_correlate(r), do.pinv_correlate(r)) < 1e-9
+    assert rel(dec.ginv(), do.ginv()) < 1e-9
+    assert dec.matrix() is K
+    v1 = dec.minus_log_normal_density(r, value=True)[0]
+    v2 = do.minus_log_normal_density(r, value=True)[0]
+    assert abs(v1 - v2) / abs(v2) < 1e-10
+    dK = rng.standard_normal((n, n, 2))
+    dK = dK + dK.transpose(1, 0, 2)
+    dr = rng.standard_normal((n, 2))
+    o1 = dec.minus_log_normal_density(r, dK=dK, dr=dr, gradfwd=True, fisher=True)
+    o2 = do.minus_log_normal_density(r, dK=dK, dr=dr, gradfwd=True, fisher=True)
+    assert o1[0] is None and o1[1] is None and o1[4] is None
+    assert rel(o1[2], o2[2]) < 1e-8 and rel(o1[3], o2[3]) < 1e-8
+    vj = lambda G: np.einsum('ij,ijk->k', G, dK)
+    rj = lambda g: g @ dr
+    vec = rng.standard_normal(2)
+    kw = dict(dK_vjp=vj, dr_vjp=rj, dK_jvp_vec=dK @ vec, dr_jvp_vec=dr @ vec, gradrev=True, fishvec=True)
+    o1 = dec.minus_log_normal_density(r, **kw)
+    o2 = do.minus_log_normal_density(r, **kw)
+    assert rel(o1[1], o2[1]) < 1e-8 and rel(o1[4], o2[4]) < 1e-8
+
+
+def test_error_semantics():
+    with pytest.raises(np.linalg.LinAlgError):
+        lgp._linalg.Chol(-np.eye(5))
+    gp = lgp.GP(lgp.ExpQuad()).addx(np.arange(5.), 'a')
+    with pytest.raises(KeyError):
+        gp.addx(np.arange(3.), 'a')
+    with pytest.raises(ValueError):
+        gp.addx(np.arange(3.))
+    with pytest.raises(KeyError):
+        gp.marginal_likelihood({'zzz': np.zeros(5)})
+    with pytest.raises(ValueError):
+        gp.marginal_likelihood({'a': np.zeros(4)})
+    with pytest.raises(ValueError, match='not finite'):
+        gp.marginal_likelihood({'a': np.array([0, 1, np.nan, 0, 0])})
+    with pytest.raises(ValueError, match='not symmetric'):
+        gp.marginal_likelihood({'a': np.zeros(5)}, {('a', 'a'): np.triu(np.ones((5, 5)))})
+    with pytest.raises(TypeError):
+        gp.marginal_likelihood([1, 2, 3])
+    with pytest.raises(ValueError):
+        gp.pred({'a': np.zeros(5)}, 'a', raw=True)
+    with pytest.raises(NotImplementedError):
+        gp.pred({'a': np.zeros(5)}, 'a', fromdata=True)
+    # immutability: addx returns a new object
+    gp2 = gp.addx(np.arange(2.), 'b')
+    assert 'b' not in gp._elements and 'b' in gp2._elements
+    # decomposition cache reused when no ycov (reference tests/GP/test_GP.py:587-596)
+    d1 = gp2._solver(['a'])
+    assert gp2._solver(['a']) is d1
+    dec = lgp.GP.decompose(np.eye(4).reshape(2, 2, 2, 2))
+    assert dec.n == 4
+
+
+def test_kernel_call_broadcasting():
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0, 5, 7)
+    y = rng.uniform(0, 5, 4)
+    k = lgp.ExpQuad(scale=2) * 1.5 + lgp.Cauchy(beta=3)
+    K = k(x[:, None], y[None, :])
+    ref = 1.5 * np.exp(-0.5 * ((x[:, None] / 2 - y[None, :] / 2) ** 2)) + (1 + (x[:, None] - y[None, :]) ** 2 / 3) ** (-3 / 2)
+    np.testing.assert_allclose(K, ref, rtol=1e-13)
+    np.testing.assert_allclose(k(x, x), np.full(7, 2.5), rtol=1e-14)          # elementwise on equal shapes
+    xs = lgp.StructuredArray({'a': x, 'b': x[::-1].copy()})
+    ka = lgp.ExpQuad(dim='a')
+    np.testing.assert_allclose(ka(xs.reshape(7, 1), xs.reshape(1, 7)), np.exp(-0.5 * (x[:, None] - x[None, :]) ** 2),
+                               rtol=1e-13)
+    with pytest.raises(ValueError):
+        ka(x, x)

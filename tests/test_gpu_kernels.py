@@ -1,0 +1,231 @@
+"""GPU parity: low-level C-ABI kernels (GEMM, Cholesky pipeline, Gram) against the oracle / NumPy.
+Tolerances: Gram entries 1e-13 relative (north_star), factor/solves 1e-10, logdet/eps 1e-12."""
+import numpy as np
+import pytest
+import scipy.linalg as sl
+import torch
+
+from lsqfitgp_b200 import _lib, _ops
+from oracle import gp as ogp, decomp as odecomp
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def relerr(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 128), (300, 200, 150), (257, 129, 77), (1, 1, 1), (64, 640, 33),
+                                   (1024, 512, 2048)])
+@pytest.mark.parametrize('akm', [True, False])
+@pytest.mark.parametrize('bkm', [True, False])
+def test_dgemm_layouts(M, N, K, akm, bkm):
+    g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + K)
+    Aop = torch.randn(M, K, generator=g, dtype=torch.float64).to(dev())
+    Bop = torch.randn(N, K, generator=g, dtype=torch.float64).to(dev())
+    C0 = torch.randn(M, N, generator=g, dtype=torch.float64).to(dev())
+    A = _ops.as_aligned(Aop if akm else Aop.T.contiguous())
+    B = _ops.as_aligned(Bop if bkm else Bop.T.contiguous())
+    C = _ops.as_aligned(C0.clone())
+    _ops.dgemm(A, B, C, a_kmajor=akm, b_kmajor=bkm, M=M, N=N, K=K, alpha=-1.0)
+    assert relerr(C, C0 - Aop @ Bop.T) < 1e-13
+    _ops.dgemm(A, B, C, a_kmajor=akm, b_kmajor=bkm, M=M, N=N, K=K, alpha=2.0, flags=_lib.GEMM_BETA0)
+    assert relerr(C, 2 * (Aop @ Bop.T)) < 1e-13
+
+
+def test_dgemm_flags():
+    M, K = 384, 200
+    g = torch.Generator(device='cpu').manual_seed(5)
+    Aop = torch.randn(M, K, generator=g, dtype=torch.float64).to(dev())
+    C0 = torch.randn(M, M, generator=g, dtype=torch.float64).to(dev())
+    A = _ops.as_aligned(Aop)
+    C = _ops.as_aligned(C0.clone())
+    _ops.dgemm(A, A, C, a_kmajor=True, b_kmajor=True, M=M, N=M, K=K, alpha=-1.0, flags=_lib.GEMM_LOWER)
+    ref = C0 - Aop @ Aop.T
+    assert relerr(torch.tril(C), torch.tril(ref)) < 1e-13
+    assert torch.equal(torch.triu(C, 1), torch.triu(C0, 1))  # strictly upper part untouched, bit for bit
+    L = torch.tril(torch.randn(M, M, generator=g, dtype=torch.float64)).to(dev())
+    X = torch.randn(M, 130, generator=g, dtype=torch.float64).to(dev())
+    Y = _ops.aligned_empty(M, 130, dev())
+    _ops.dgemm(_ops.as_aligned(L), _ops.as_aligned(X), Y, a_kmajor=True, b_kmajor=False, M=M, N=130, K=M,
+               flags=_lib.GEMM_BETA0 | _lib.GEMM_A_LOWER_K)
+    assert relerr(Y, L @ X) < 1e-13
+    _ops.dgemm(_ops.as_aligned(L), _ops.as_aligned(X), Y, a_kmajor=False, b_kmajor=False, M=M, N=130, K=M,
+               flags=_lib.GEMM_BETA0 | _lib.GEMM_A_UPPER_K)
+    assert relerr(Y, L.T @ X) < 1e-13
+
+
+def test_dgemm_rejects_misaligned():
+    A = torch.zeros(9, 9, dtype=torch.float64, device=dev())
+    with pytest.raises(RuntimeError, match='misaligned'):
+        _ops.dgemm(A, A, A.clone(), a_kmajor=True, b_kmajor=True, M=9, N=9, K=9)
+
+
+def spd(n, seed):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    x = torch.rand(n, 2, generator=g, dtype=torch.float64) * 10
+    d2 = ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+    return 1.7 * torch.exp(-0.5 * d2 / 1.5 ** 2) + 0.05 * torch.eye(n, dtype=torch.float64)
+
+
+@pytest.mark.parametrize('n', [1, 2, 10, 127, 128, 129, 300, 640, 1000, 2500])
+def test_chol_pipeline_vs_oracle(n):
+    Kc = spd(n, n)
+    st = _ops.chol_factor(Kc.to(dev()))
+    assert int(st.info.item()) == 0
+    do = odecomp.Chol(Kc.numpy())
+    Lr = do._L
+    Lg = _ops.chol_get_factor(st).cpu().numpy()
+    assert np.abs(Lg - Lr).max() / np.abs(Lr).max() < 1e-12
+    assert np.all(np.triu(Lg, 1) == 0)
+    sc = st.scalars().cpu().numpy()
+    assert abs(sc[1] * sc[3] - do.eps) / do.eps < 1e-14          # eps: same Gershgorin bound, bit-level
+    ld = np.sum(np.log(np.diag(Lr)))
+    assert abs(sc[4] - ld) / max(1, abs(ld)) < 1e-12
+    g = torch.Generator(device='cpu').manual_seed(n)
+    for m in (1, 3, 130):
+        B = torch.randn(n, m, generator=g, dtype=torch.float64)
+        x1 = _ops.chol_solve(st, B.to(dev()), False).cpu().numpy()
+        r1 = sl.solve_triangular(Lr, B.numpy(), lower=True)
+        assert np.abs(x1 - r1).max() / np.abs(r1).max() < 1e-10
+        x2 = _ops.chol_solve(st, B.to(dev()), True).cpu().numpy()
+        r2 = sl.solve_triangular(Lr.T, B.numpy(), lower=False)
+        assert np.abs(x2 - r2).max() / np.abs(r2).max() < 1e-10
+        y1 = _ops.chol_mult(st, B.to(dev()), False).cpu().numpy()
+        assert np.abs(y1 - Lr @ B.numpy()).max() / np.abs(Lr @ B.numpy()).max() < 1e-12
+        y2 = _ops.chol_mult(st, B.to(dev()), True).cpu().numpy()
+        assert np.abs(y2 - Lr.T @ B.numpy()).max() / np.abs(Lr.T @ B.numpy()).max() < 1e-12
+    Ki = _ops.chol_inverse(st).cpu().numpy()
+    Kir = np.linalg.inv(Lr @ Lr.T)
+    assert np.abs(np.tril(Ki) - np.tril(Kir)).max() / np.abs(Kir).max() < 1e-9
+
+
+def test_chol_unequal_scales_and_addmat():
+    # diagonal spanning many powers of two: s differs per row; Kxx + ycov fused in the equilibration pass
+    n = 200
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((n, n))
+    K = A @ A.T / n + np.eye(n)
+    d = 2.0 ** rng.integers(-20, 20, n)
+    K = K * d[:, None] * d[None, :]
+    ycov = np.diag(rng.uniform(0.1, 1, n)) * d[:, None] * d[None, :]
+    st = _ops.chol_factor(torch.tensor(K).to(dev()), addmat=torch.tensor(ycov).to(dev()))
+    do = odecomp.Chol(K + ycov)
+    Lg = _ops.chol_get_factor(st).cpu().numpy()
+    assert np.abs(Lg / do._L.clip(1e-300) - 1)[np.tril_indices(n)].max() < 1e-9 or \
+        np.abs(Lg - do._L).max() / np.abs(do._L).max() < 1e-12
+    sc = st.scalars().cpu().numpy()
+    assert abs(sc[1] * sc[3] - do.eps) / do.eps < 1e-14
+
+
+def test_chol_failure_reporting():
+    K = torch.eye(200, dtype=torch.float64, device=dev())
+    K[150, 150] = 1e-30
+    K[150, 10] = K[10, 150] = 1.0   # not positive definite; diagonal stays positive so equilibration is finite
+    st = _ops.chol_factor(K, epsrel=0.0)
+    assert int(st.info.item()) == 151
+    st = _ops.chol_factor(-torch.eye(5, dtype=torch.float64, device=dev()))
+    assert int(st.info.item()) != 0
+
+
+def np_r2(x, y, scale, loc=0.0):
+    u = (x - loc) / scale
+    v = (y - loc) / scale
+    r2 = None
+    for f in range(u.shape[0]):
+        t = (u[f][:, None] - v[f][None, :]) ** 2
+        r2 = t if r2 is None else r2 + t
+    return r2
+
+
+def test_gram_iso_vs_oracle():
+    rng = np.random.default_rng(11)
+    n, m, d = 333, 257, 3
+    x = rng.uniform(0, 10, (d, n))
+    y = rng.uniform(0, 10, (d, m))
+    xd, yd = torch.tensor(x).to(dev()), torch.tensor(y).to(dev())
+    full = (1 << d) - 1
+
+    def check(descs, terms, xx, yy, xxd, yyd):
+        Kg = _ops.gram_iso(descs, xxd, yyd).cpu().numpy()
+        Kr = ogp.gram(terms, xx, yy)
+        err = np.max(np.abs(Kg - Kr) / np.abs(Kr).clip(1e-300))
+        assert err < 1e-13, err
+
+    check([dict(kind=_lib.K_EXPQUAD, term=0, dimmask=full, scale_x=1.5, scale_y=1.5)],
+          [(1.0, [dict(kind='expquad', scale=1.5)])], x, y, xd, yd)
+    check([dict(kind=_lib.K_EXPQUAD, term=0, dimmask=full, scale_x=0.3, scale_y=0.3, loc_x=1.0, loc_y=1.0, amp=3.0)],
+          [(3.0, [dict(kind='expquad', scale=0.3, loc=1.0)])], x, y, xd, yd)
+    for p in range(5):
+        check([dict(kind=_lib.K_MATERNP, term=0, dimmask=full, ipar=p, par0=1e-30, scale_x=2.0, scale_y=2.0, amp=1.3),
+               dict(kind=_lib.K_WHITE, term=1, dimmask=full, amp=0.01)],
+              [(1.3, [dict(kind='maternp', p=p, scale=2.0)]), (0.01, [dict(kind='white')])], x, x, xd, xd)
+        # Matern(nu = p + 1/2) closed form against scipy.special.kv, as the reference evaluates it
+        check([dict(kind=_lib.K_MATERNP, term=0, dimmask=full, ipar=p, par0=0.0, scale_x=2.0, scale_y=2.0)],
+              [(1.0, [dict(kind='matern', nu=p + 0.5, scale=2.0)])], x, y, xd, yd)
+    check([dict(kind=_lib.K_CAUCHY, term=0, dimmask=0b101, par0=2.0, par1=3.0),
+           dict(kind=_lib.K_EXPQUAD, term=0, dimmask=0b010, scale_x=0.7, scale_y=0.7, amp=2.0)],
+          [(2.0, [dict(kind='cauchy', alpha=2, beta=3.0, dims=[0, 2]), dict(kind='expquad', scale=0.7, dims=[1])])],
+          x, y, xd, yd)
+    check([dict(kind=_lib.K_CAUCHY, term=0, dimmask=full, par0=1.3, par1=0.7, scale_x=4.0, scale_y=4.0),
+           dict(kind=_lib.K_CONSTANT, term=1, dimmask=0, amp=0.25)],
+          [(1.0, [dict(kind='cauchy', alpha=1.3, beta=0.7, scale=4.0)]), (0.25, [dict(kind='constant')])], x, y, xd, yd)
+
+
+def test_gram_second_factor_amp():
+    rng = np.random.default_rng(12)
+    x = rng.uniform(0, 10, (2, 100))
+    xd = torch.tensor(x).to(dev())
+    Kg = _ops.gram_iso([dict(kind=_lib.K_EXPQUAD, term=0, dimmask=1), dict(kind=_lib.K_EXPQUAD, term=0, dimmask=2, amp=2.0)],
+                       xd, xd).cpu().numpy()
+    Kr = ogp.gram([(1.0, [dict(kind='expquad', dims=[0])])], x, x) * (2.0 * ogp.gram([(1.0, [dict(kind='expquad', dims=[1])])], x, x))
+    assert np.max(np.abs(Kg - Kr) / Kr) < 1e-13
+
+
+def test_gram_edge_shapes():
+    xd = torch.rand(1, 1, dtype=torch.float64, device=dev())
+    d1 = [dict(kind=_lib.K_EXPQUAD, term=0, dimmask=1)]
+    assert _ops.gram_iso(d1, xd, xd).item() == 1.0
+    yd = torch.rand(1, 65, dtype=torch.float64, device=dev())
+    K = _ops.gram_iso(d1, xd, yd)
+    assert K.shape == (1, 65)
+    np.testing.assert_allclose(K.cpu().numpy(), np.exp(-0.5 * (xd.cpu().numpy().T - yd.cpu().numpy()) ** 2), rtol=1e-14)
+    # tiny entries: exp(-r2/2) down to the denormal range keeps 1e-13 relative on normal numbers
+    far = torch.tensor([[0.0, 30.0, 37.0]], dtype=torch.float64, device=dev())
+    K = _ops.gram_iso(d1, far, far).cpu().numpy()
+    ref = np.exp(-0.5 * (far.cpu().numpy().T - far.cpu().numpy()) ** 2)
+    assert np.max(np.abs(K - ref) / ref) < 1e-13
+
+
+def test_gram_vjp_matches_finite_differences():
+    rng = np.random.default_rng(13)
+    n, d = 150, 2
+    x = rng.uniform(0, 5, (d, n))
+    xd = torch.tensor(x).to(dev())
+    G = rng.standard_normal((n, n))
+    Gd = _ops.as_aligned(torch.tensor(G).to(dev()))
+
+    def descs(amp, scale, beta):
+        return [dict(kind=_lib.K_CAUCHY, term=0, dimmask=3, par0=2.0, par1=beta, scale_x=scale, scale_y=scale, amp=amp),
+                dict(kind=_lib.K_MATERNP, term=0, dimmask=1, ipar=2, par0=1e-30, scale_x=2 * scale, scale_y=2 * scale),
+                dict(kind=_lib.K_EXPQUAD, term=1, dimmask=2, scale_x=scale, scale_y=scale, amp=0.5 * amp)]
+    p0 = np.array([1.3, 0.8, 2.5])
+    f = lambda p: float((torch.tensor(G).to(dev()) * _ops.gram_iso(descs(*p), xd, xd)).sum())
+    out = _ops.gram_iso_vjp_general(descs(*p0), xd, xd, Gd).cpu().numpy()
+    h = 1e-6
+    fd = [(f(p0 + h * e) - f(p0 - h * e)) / (2 * h) for e in np.eye(3)]
+    # amp enters factor 0 (x1) and factor 2 (x0.5); scale enters all three factors
+    g_amp = out[0, 0] + 0.5 * out[2, 0]
+    g_scale = (out[0, 1] + out[1, 1] + out[2, 1]) / p0[1]
+    g_beta = out[0, 2]
+    np.testing.assert_allclose([g_amp, g_scale, g_beta], fd, rtol=1e-6)
+    # symmetric fused form == general form on the symmetrised input
+    Gs = G + G.T
+    b = rng.standard_normal(n)
+    full = _ops.gram_iso_vjp_general(descs(*p0), xd, xd, _ops.as_aligned(torch.tensor(Gs - np.outer(b, b)).to(dev())))
+    low = _ops.gram_iso_vjp(descs(*p0), xd, _ops.as_aligned(torch.tensor(Gs).to(dev())), torch.tensor(b).to(dev()))
+    np.testing.assert_allclose(low.cpu().numpy(), full.cpu().numpy(), rtol=1e-10, atol=1e-10)

@@ -1,0 +1,99 @@
+"""Host-side logic that needs no GPU: kernel algebra -> descriptors, StructuredArray, BART bracket folding,
+error semantics of the API shell."""
+import numpy as np
+import pytest
+
+import lsqfitgp_b200 as lgp
+from lsqfitgp_b200 import _lib, _array
+from lsqfitgp_b200._kernels import _BartSpec
+from oracle import bart as obart
+
+
+def test_kernel_algebra_descriptor():
+    k = 2.0 * lgp.ExpQuad(scale=3.0) + lgp.Matern(nu=2.5, scale=(1.5, 1.5)) * lgp.Cauchy(beta=3, dim='b') * 0.5 + 0.1
+    descs, index = k._descriptor(['a', 'b'])
+    assert [d['kind'] for d in descs] == [_lib.K_EXPQUAD, _lib.K_MATERNP, _lib.K_CAUCHY, _lib.K_CONSTANT]
+    assert [d['term'] for d in descs] == [0, 1, 1, 2]
+    assert [d['amp'] for d in descs] == [2.0, 0.5, 1.0, 0.1]
+    assert descs[0]['scale_x'] == 3.0 and descs[1]['ipar'] == 2 and descs[1]['par0'] == 0.0
+    assert descs[2]['dimmask'] == 0b10 and descs[0]['dimmask'] == 0b11
+    assert descs[2]['par0'] == 2 and descs[2]['par1'] == 3
+    assert isinstance(k, lgp.IsotropicKernel)
+    kp = lgp.Maternp(p=1)
+    assert kp._descriptor([None])[0][0]['par0'] == 1e-30
+    k2 = (lgp.ExpQuad() + lgp.White()) * (lgp.ExpQuad(scale=2) + 1)
+    assert len(k2._terms) == 4 and all(len(t.factors) == 2 for t in k2._terms)
+    k3 = lgp.ExpQuad() ** 3
+    assert len(k3._terms) == 1 and len(k3._terms[0].factors) == 3
+
+
+def test_kernel_errors():
+    with pytest.raises(NotImplementedError):
+        lgp.Matern(nu=1.3)
+    with pytest.raises(AssertionError):
+        lgp.ExpQuad(scale=-1)
+    with pytest.raises(AssertionError):
+        lgp.Cauchy(alpha=3)
+    with pytest.raises(NotImplementedError):
+        lgp.kernel(lambda x, y: x * y)
+    with pytest.raises(TypeError):
+        lgp.ExpQuad(dim=3)
+    with pytest.raises(TypeError):
+        lgp.GP(lambda x, y: 1)
+    big = lgp.ExpQuad()
+    for _ in range(9):
+        big = big * lgp.ExpQuad()
+    with pytest.raises(NotImplementedError):
+        big._descriptor([None])
+    with pytest.raises(ValueError):
+        lgp.ExpQuad(dim='a')._descriptor([None])
+
+
+def test_structured_array():
+    x = np.zeros(5, dtype=[('a', float), ('b', float, 2)])
+    x['a'] = np.arange(5)
+    x['b'] = np.arange(10).reshape(5, 2)
+    s = lgp.StructuredArray(x)
+    assert s.shape == (5,) and s.dtype.names == ('a', 'b')
+    labels, data, shape = _array.columns_of(s)
+    assert labels == ['a', ('b', 0), ('b', 1)] and data.shape == (3, 5) and shape == (5,)
+    np.testing.assert_array_equal(data[2], x['b'][:, 1])
+    t = s[1:3]
+    assert t.shape == (2,) and np.array_equal(t['a'], [1, 2])
+    r = s.reshape(5, 1)
+    assert r.shape == (5, 1) and r['b'].shape == (5, 1, 2)
+    u = lgp.unstructured_to_structured(np.arange(6.).reshape(3, 2), names=['p', 'q'])
+    assert u.dtype.names == ('p', 'q') and np.array_equal(u['q'], [1, 3, 5])
+    labels, data, shape = _array.columns_of(np.arange(4.).reshape(2, 2))
+    assert labels == [None] and data.shape == (1, 4) and shape == (2, 2)
+    with pytest.raises(TypeError):
+        _array.columns_of(np.array(['a', 'b']))
+
+
+@pytest.mark.parametrize('maxd,reset', [(2, None), (4, 2), (10, [2, 4, 6, 8]), (1, None), (0, None), (6, [2, 4])])
+def test_bart_bracket_folding_matches_oracle(maxd, reset):
+    spec = _BartSpec(1.0, (np.array([3]), None), True, 0.95, 2, maxd, 1, None, True, None, reset)
+    stages, gamma = spec.rows()
+    ref = obart.fold_brackets(obart.make_pnt(0.95, 2, maxd), reset)
+    assert len(stages) == len(ref)
+    for rows, (probs, repeat) in zip(stages, ref):
+        np.testing.assert_array_equal(rows.ravel(), probs)
+        assert rows.shape[0] == (repeat or 1)
+
+
+def test_bart_unsupported_depth():
+    spec = _BartSpec(1.0, (np.array([3]), None), True, 0.95, 2, 4, 1, None, True, None, None)
+    with pytest.raises(NotImplementedError):
+        spec.rows()
+
+
+def test_bart_preprocessing_matches_oracle(rng):
+    X = np.concatenate([rng.standard_normal((40, 3)), rng.integers(0, 2, (40, 1)).astype(float)], axis=1)
+    l1, s1 = lgp.BART.splits_from_coord(X)
+    l2, s2 = obart.splits_from_coord(X)
+    np.testing.assert_array_equal(l1, l2)
+    np.testing.assert_array_equal(s1, s2)
+    np.testing.assert_array_equal(lgp.BART.indices_from_coord(X, (l1, s1)), obart.indices_from_coord(X, (l2, s2)))
+    xs = lgp.unstructured_to_structured(X)
+    l3, s3 = lgp.BART.splits_from_coord(xs)
+    np.testing.assert_array_equal(l1, l3)
