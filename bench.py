@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GP-fitting hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n 20000]
+
+Workload (config.workload): BASELINE.json configs[1] -- Matern(nu=2.5), 3-D covariates, n = 20000, float64,
+one step = one evaluation of log marginal likelihood AND its gradient w.r.t. (log scale, log sigma_f, log sigma_n):
+Gram build -> equilibrated/jittered Cholesky -> triangular solves + log-determinant -> inverse from the factor ->
+Gram-VJP contraction.  Metric: logML(+gradient) evaluations per second, whole job.
+
+  value : device-timed (CUDA events), inputs (x, y) already resident in HBM, through the C ABI.
+  e2e   : the same metric through the public API (lgp.GP(...).marginal_likelihood + torch.autograd.grad) from HOST
+          arrays, host->device copies of x, y and the device->host read of (logML, gradient) inside the timed region.
+  N > 1 : one process per GPU (torchrun); every rank evaluates its own hyperparameter point of a batch on replicated
+          data (independent units, no data-path collective) -> weak scaling; time = max over ranks.
+  --impl reference : the CPU restatement of the reference path (oracle/, NumPy/SciPy/OpenBLAS on all host cores;
+          jax/gvar are not installable here so the reference itself cannot run) on a bounded sample of the same workload.
+"""
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'logML+gradient evaluations/s at n=20000 fp64 (Gram+Chol+solve+inverse+VJP)'
+UNIT = 'evals/s'
+FP64_DMMA_PEAK_TFLOPS = 37.0   # measured on this pool's B200 with tools/peaks_fp64.cu (profiles/peaks_fp64_r1.log);
+                               # MEASURED_PEAKS.json has no FP64 entry
+
+
+def make_data(n, seed=2002):
+    """ SURVEY.md section 8(d), config C2 """
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0, 10, (n, 3))
+    y = np.sin(X[:, 0]) + np.cos(X[:, 1]) * X[:, 2] / 10 + 0.1 * rng.standard_normal(n)
+    return X, y
+
+
+def theta_for(rank, step):
+    """ hyperparameter point of the batch evaluated by `rank` at `step`: (log ell, log sigma_f, log sigma_n) """
+    rng = np.random.default_rng(3004 + 1000 * rank + step)
+    return np.array([np.log(1.5), 0.0, np.log(0.1)]) + 0.05 * rng.standard_normal(3)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------------------
+
+def cpu_eval(X, y, theta):
+    from oracle import gp as ogp
+    ell, sf, sn = np.exp(theta)
+    terms = [(sf ** 2, [dict(kind='matern', nu=2.5, scale=ell)]), (sn ** 2, [dict(kind='white')])]
+    val, g = ogp.logml_and_grad(terms, X.T.copy(), y, [('logscale', 0, 0), ('amp', 0), ('amp', 1)])
+    return val, np.array([g[0], g[1] * 2 * sf ** 2, g[2] * 2 * sn ** 2])
+
+
+def cpu_threads():
+    try:
+        import threadpoolctl
+        infos = threadpoolctl.threadpool_info()
+        if infos:
+            return max(i.get('num_threads', 1) for i in infos)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_baseline(n_full, n_sample, reps=1):
+    """ time the oracle on a bounded sample (n_sample points) and scale by (n_full/n_sample)^3 (the path is O(n^3)) """
+    X, y = make_data(n_sample)
+    cpu_eval(X[:500], y[:500], theta_for(0, 0))  # warm up BLAS threads
+    ts = []
+    for r in range(reps):
+        t0 = time.perf_counter()
+        cpu_eval(X, y, theta_for(0, r))
+        ts.append(time.perf_counter() - t0)
+    t = min(ts)
+    scale = (n_full / n_sample) ** 3
+    return dict(value=1.0 / (t * scale), unit=UNIT, cores=cpu_threads(), kind='port',
+                sample=f'oracle (NumPy/SciPy OpenBLAS restatement of the reference path) logML+gradient at n={n_sample} '
+                       f'in {t:.2f} s, extrapolated to n={n_full} by (n/n_sample)^3 = {scale:.1f}x',
+                seconds_sample=t)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    n_sample = args.ref_n
+    X, y = make_data(n_sample)
+    cpu_eval(X[:500], y[:500], theta_for(0, 0))
+    for w in range(args.warmup):
+        cpu_eval(X, y, theta_for(0, w))
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_eval(X, y, theta_for(0, s))
+    t = (time.perf_counter() - t0) / args.steps
+    scale = (args.n / n_sample) ** 3
+    value = 1.0 / (t * scale)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=t * scale * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
+                data='synthetic', impl='reference',
+                config=dict(workload=f'Matern(nu=2.5) 3-D n={args.n} fp64 logML+gradient (BASELINE configs[1])',
+                            n=args.n, d=3, kernel='sf^2*Matern(nu=2.5, scale=ell) + sn^2*White'),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cpu_threads(), kind='port',
+                                  sample=f'each step = oracle logML+gradient at n={n_sample} ({t:.2f} s), scaled to '
+                                         f'n={args.n} by (n/n_sample)^3 = {scale:.1f}x; the reference itself needs '
+                                         'jax+gvar, not installable here'),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = threading.Event()
+        self.maxmhz = None
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(',')]
+                self.samples.append(float(parts[0]))
+                self.maxmhz = float(parts[1])
+                for nm, v in zip(names, parts[2:]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.maxmhz, reasons=sorted(self.reasons))
+        return dict(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.maxmhz, reasons=sorted(self.reasons),
+                    samples=len(self.samples))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import lsqfitgp_b200 as lgp
+    from lsqfitgp_b200 import _lib, _ops
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    n = args.n
+    X, y = make_data(n)
+    xd = torch.tensor(np.ascontiguousarray(X.T)).to(dev)          # (3, n) field-major, resident in HBM
+    yd = torch.tensor(y).to(dev)
+    names = ['f0', 'f1', 'f2']
+
+    def descs_for(theta):
+        ell, sf, sn = np.exp(theta)
+        return [dict(kind=_lib.K_MATERNP, term=0, dimmask=7, ipar=2, par0=0.0, scale_x=ell, scale_y=ell, amp=sf ** 2),
+                dict(kind=_lib.K_WHITE, term=1, dimmask=7, amp=sn ** 2)]
+
+    phases = ['gram', 'chol', 'solve', 'inverse', 'vjp']
+    K = _ops.aligned_empty(n, n, dev)
+
+    def step_device(theta, ev=None):
+        """ one logML+gradient evaluation with device-resident inputs, straight through the C ABI """
+        descs = descs_for(theta)
+
+        def mark(i):
+            if ev is not None:
+                ev[i].record()
+        mark(0)
+        _ops.gram_iso(descs, xd, xd, out=K, symmetric=True)
+        mark(1)
+        st = _ops.chol_factor(K)
+        mark(2)
+        a = _ops.chol_solve(st, yd[:, None], False)
+        ldq = _ops.chol_logdet_quad(st, a[:, 0].contiguous())
+        b = _ops.chol_solve(st, a, True, inplace=True)
+        mark(3)
+        Kinv = _ops.chol_inverse(st)
+        mark(4)
+        vjp = _ops.gram_iso_vjp(descs, xd, Kinv, b[:, 0].contiguous())
+        mark(5)
+        return ldq, vjp, st
+
+    def finish(theta, ldq, vjp):
+        ld, q = ldq.cpu().numpy()
+        v = vjp.cpu().numpy()
+        ell, sf, sn = np.exp(theta)
+        val = 0.5 * (n * math.log(2 * math.pi) + 2 * ld + q)
+        grad = 0.5 * np.array([v[0, 1], v[0, 0] * 2 * sf ** 2, v[1, 0] * 2 * sn ** 2])
+        return val, grad
+
+    # pinned host staging for the end-to-end arm
+    Xh = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    Xh.copy_(torch.tensor(X))
+    yh = torch.empty(n, dtype=torch.float64).pin_memory()
+    yh.copy_(torch.tensor(y))
+    Xnp, ynp = Xh.numpy(), yh.numpy()
+
+    def step_e2e(theta):
+        """ public API from host buffers: H2D of x and y, D2H of (logML, gradient) """
+        th = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+        ell, sf, sn = torch.exp(th[0]), torch.exp(th[1]), torch.exp(th[2])
+        kern = sf ** 2 * lgp.Matern(nu=2.5, scale=ell) + sn ** 2 * lgp.White()
+        xs = lgp.unstructured_to_structured(Xnp, names=names)
+        gp = lgp.GP(kern, checkpos=False, checksym=False, checkfinite=False).addx(xs, 'data')
+        ml = gp.marginal_likelihood({'data': ynp})
+        g, = torch.autograd.grad(ml, th)
+        return float(ml.detach()), g.numpy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness guard: the two arms agree (and, at rank 0, with the oracle on a subsample in tests/)
+    th0 = theta_for(rank, 0)
+    ldq, vjp, st = step_device(th0)
+    v_dev, g_dev = finish(th0, ldq, vjp)
+    assert int(st.info.item()) == 0
+    del st
+    v_api, g_api = step_e2e(th0)
+    assert abs(v_dev + v_api) <= 1e-9 * abs(v_dev), (v_dev, v_api)
+    assert np.max(np.abs(g_dev + g_api)) <= 1e-9 * np.max(np.abs(g_dev)), (g_dev, g_api)
+
+    # ---- device-resident arm
+    for w in range(args.warmup):
+        ldq, vjp, st = step_device(theta_for(rank, w))
+        del st
+    barrier()
+    launches0 = lib.lgp_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    results = []
+    e0.record()
+    for s in range(args.steps):
+        ldq, vjp, st = step_device(theta_for(rank, s), evs[s])
+        results.append((ldq, vjp))
+        del st
+    e1.record()
+    barrier()
+    sampler.stop_flag.set()
+    launches = lib.lgp_launch_count() - launches0
+    t_dev = e0.elapsed_time(e1) / 1e3
+    phase_ms = {p: float(np.mean([evs[s][i].elapsed_time(evs[s][i + 1]) for s in range(args.steps)]))
+                for i, p in enumerate(phases)}
+
+    # ---- end-to-end arm
+    for w in range(min(args.warmup, 2)):
+        step_e2e(theta_for(rank, w))
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_e2e(theta_for(rank, s))
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = (float(v) for v in tt.cpu())
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        value = args.steps * world / t_dev
+        e2e_value = args.steps * world / t_e2e
+        chol_tflops = n ** 3 / 3 / (phase_ms['chol'] * 1e-3) / 1e12
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+            dtype='f64', data='synthetic',
+            config=dict(workload=f'Matern(nu=2.5) 3-D n={n} fp64 logML+gradient (BASELINE configs[1])', n=n, d=3,
+                        kernel='sf^2*Matern(nu=2.5, scale=ell) + sn^2*White', parallelism=f'hyperparameter-batch x{world}',
+                        l2='working set (3.2 GB matrix) exceeds the 126 MB L2; no flush needed'),
+            clocks=sampler.summary(),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=n * 3 * 8 + n * 8, d2h_bytes_per_step=4 * 8,
+                     ms_per_step=t_e2e / args.steps * 1e3,
+                     api='lgp.GP(kernel).addx(x).marginal_likelihood({..}) + torch.autograd.grad'),
+            gpu_launches=int(launches),
+            roofline=dict(bound='tensor', kernel='gemm_dmma_kernel (Cholesky phase: lgp_chol_factor)',
+                          achieved=chol_tflops, peak=FP64_DMMA_PEAK_TFLOPS, unit='TFLOP/s',
+                          frac=chol_tflops / FP64_DMMA_PEAK_TFLOPS, traffic=None,
+                          peak_source='measured FP64 DMMA.8x8x4 register-resident loop, tools/peaks_fp64.cu '
+                                      '(MEASURED_PEAKS.json has no FP64 entry)',
+                          algorithmic_flops_per_launch=n ** 3 / 3),
+            phases_ms=phase_ms,
+            phase_rates=dict(gram_GBps=8 * n * n / (phase_ms['gram'] * 1e-3) / 1e9,
+                             chol_TFLOPs=chol_tflops,
+                             inverse_TFLOPs=2 * n ** 3 / 3 / (phase_ms['inverse'] * 1e-3) / 1e12,
+                             vjp_GBps=4 * n * n / (phase_ms['vjp'] * 1e-3) / 1e9,
+                             step_TFLOPs=n ** 3 / (t_dev / args.steps) / 1e12 / world * world),
+        )
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline(n, args.ref_n)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n', type=int, default=20000)
+    ap.add_argument('--ref-n', type=int, default=5000, help='sample size of the CPU baseline / reference arm')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

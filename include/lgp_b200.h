@@ -36,6 +36,8 @@ typedef void *lgp_stream_t;
 int lgp_abi_version(void);
 /* static string: compiler, arch, build flags */
 const char *lgp_build_info(void);
+/* number of CUDA kernel launches issued by the library since load (instrumentation for bench.py) */
+long long lgp_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Gram matrix of a sum of products of isotropic kernel factors.

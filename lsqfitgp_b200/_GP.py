@@ -146,6 +146,49 @@ class _NegLogDensityFn(torch.autograd.Function):
         return gK, gr, None
 
 
+class _FusedNegLogMLFn(torch.autograd.Function):
+    """ Gram -> Chol -> value in one node for the common case (one set of points, kernel-only covariance):
+    the backward pass feeds the lower triangle of K^-1 and b = K^-1 r straight into the symmetric Gram-VJP
+    kernel, so no dense n x n gradient matrix is ever formed (the two dK_vjp calls of the reference,
+    _decomp.py:505-509, collapse into one pass over the lower triangle). """
+
+    @staticmethod
+    def forward(ctx, kern, xd, labels, r, kw, *params):
+        K = kern._gram_device(xd, xd, labels, symmetric=True)
+        dec = _linalg.Chol(K, **kw)
+        del K
+        ldq, a = dec.logdet_quad(r)
+        ctx.kern, ctx.xd, ctx.labels, ctx.dec, ctx.a = kern, xd, labels, dec, a
+        half = torch.tensor(0.5, dtype=f64, device=xd.device)
+        return half * (dec.n * math.log(2 * math.pi) + 2 * ldq[0] + ldq[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        kern, xd, labels, dec, a = ctx.kern, ctx.xd, ctx.labels, ctx.dec, ctx.a
+        b = dec._solve(a[:, None], True)[:, 0].contiguous()
+        gr = g * b if ctx.needs_input_grad[3] else None
+        hyper = kern._hyperparams()
+        grads = []
+        if hyper:
+            low = dec.inverse_lower()
+            descs, index = kern._descriptor(labels)
+            vjp = (0.5 * _ops.gram_iso_vjp(descs, xd, low, b)).cpu()
+            del low
+            pos = {tf: i for i, tf in enumerate(index)}
+            gc = g.cpu()
+            for kind, ti, fi, tensor in hyper:
+                if kind == 'amp':
+                    v = vjp[pos[(ti, 0)], 0]
+                elif kind == 'scale':
+                    v = vjp[pos[(ti, fi)], 1] / tensor.detach().cpu()
+                elif kind == 'par1':
+                    v = vjp[pos[(ti, fi)], 2]
+                else:  # pragma: no cover
+                    raise NotImplementedError(kind)
+                grads.append((gc * v).to(tensor.device, tensor.dtype).reshape(tensor.shape))
+        return (None, None, None, gr, None, *grads)
+
+
 class GP:
     """Object that represents a Gaussian process over arbitrary input.
 
@@ -660,11 +703,16 @@ class GP:
                 decomp = self._solver(inkeys, ycov, **kw)
                 mll, _, _, _, _ = decomp.minus_log_normal_density(ymean, value=True)
             return -float(mll)
+        solverkw = dict(self._solverkw)
+        solverkw.update(kw)
+        if (len(inkeys) == 1 and ycov is None and isinstance(self._elements[inkeys[0]], _Points)
+                and self._covfun._terms and not self._covfun._bart):
+            elem = self._elements[inkeys[0]]
+            params = [h[3] for h in self._covfun._hyperparams()]
+            return -_FusedNegLogMLFn.apply(self._covfun, elem.xd, elem.labels, ymean, solverkw, *params)
         Kxx = self._assemblecovblocks(inkeys)
         if ycov is not None:
             Kxx = Kxx + ycov
-        solverkw = dict(self._solverkw)
-        solverkw.update(kw)
         return -_NegLogDensityFn.apply(Kxx, ymean, solverkw)
 
     @staticmethod

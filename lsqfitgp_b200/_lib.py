@@ -53,6 +53,7 @@ _dbl = ctypes.c_double
 SIGNATURES = {
     'lgp_abi_version': (_int, []),
     'lgp_build_info': (ctypes.c_char_p, []),
+    'lgp_launch_count': (ctypes.c_longlong, []),
     'lgp_gram_iso': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int]),
     'lgp_gram_iso_vjp': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64,
                                 _vp, _int, _vp]),

@@ -3,7 +3,10 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <atomic>
 namespace lgp {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // Y = alpha * X + beta * Y (+ gamma on the diagonal), elementwise over an n x m block
 __global__ void axpby_kernel(int64_t n, int64_t m, double alpha, const double *__restrict__ X, int64_t ldx, double beta,
                              double *__restrict__ Y, int64_t ldy, double gamma) {
@@ -20,6 +23,8 @@ __global__ void axpby_kernel(int64_t n, int64_t m, double alpha, const double *_
 extern "C" {
 
 int lgp_abi_version(void) { return LGP_ABI_VERSION; }
+
+long long lgp_launch_count(void) { return lgp::g_launches.load(); }
 
 const char *lgp_build_info(void) {
     return "liblgpb200 abi=1 arch=sm_100a nvcc=" LGP_STR(__CUDACC_VER_MAJOR__) "." LGP_STR(__CUDACC_VER_MINOR__)

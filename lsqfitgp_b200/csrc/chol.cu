@@ -415,6 +415,7 @@ static void potrf_rec(CholCtx &c, int jb, int nb) {
         potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, c.st>>>(Wp(c, jb, jb), c.ldw,
                                                                       c.invd + (int64_t)jb * NB * NB, c.dvec, c.info,
                                                                       jb * NB);
+        count_launch();
         if (cudaGetLastError() != cudaSuccess) c.rc = LGP_ERR_CUDA;
         return;
     }
@@ -607,6 +608,7 @@ static void trtri_rec(InvCtx &c, int jb, int nb) {
         dim3 g((NB + 127) / 128, NB);
         copy_block_kernel<<<g, 128, 0, c.st>>>(c.invd + (int64_t)jb * NB * NB, NB,
                                                c.X + (int64_t)jb * NB * c.ldx + (int64_t)jb * NB, c.ldx, NB, NB);
+        count_launch();
         if (cudaGetLastError() != cudaSuccess) c.rc = LGP_ERR_CUDA;
         return;
     }

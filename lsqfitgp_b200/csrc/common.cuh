@@ -12,8 +12,13 @@
 #define LGP_STR_(x) #x
 #define LGP_STR(x) LGP_STR_(x)
 
+// number of kernel launches issued by this library since it was loaded (bench.py reports it as gpu_launches)
+extern "C" long long lgp_launch_count(void);
+namespace lgp { void count_launch(); }
+
 #define LGP_CUDA_CHECK_LAUNCH()                          \
     do {                                                 \
+        lgp::count_launch();                             \
         cudaError_t e__ = cudaGetLastError();            \
         if (e__ != cudaSuccess) return LGP_ERR_CUDA;     \
     } while (0)
