@@ -74,6 +74,7 @@ typedef struct lgp_factor {
  * `factors` is HOST memory (copied into kernel parameters).
  * flags: LGP_GRAM_SYMMETRIC asserts x==y (same pointer): lower tiles are evaluated once and mirrored. */
 #define LGP_GRAM_SYMMETRIC 1
+#define LGP_GRAM_GENERAL 2 /* force the general (sum-of-products) kernel even when the fast path applies */
 int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
                  int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, double *K_out, int64_t ldk,
                  int flags);
@@ -86,7 +87,7 @@ int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors,
  * symlower = 0: G is a dense n x m matrix (ldg).  symlower = 1: x == y and G_ij = w_ij (G[i][j] - b_i b_j) read from
  * the LOWER triangle only, w = 2 off the diagonal: with G = (K+eps)^-1 and b = K^-1 r this is
  * dK_vjp(invK) - dK_vjp(outer(invKr, invKr)) of Chol.minus_log_normal_density collapsed into one pass
- * (src/lsqfitgp/_linalg/_decomp.py:505-509).  b may be NULL.  out: device memory, 3*nfactors doubles
+ * (src/lsqfitgp/_linalg/_decomp.py:505-509).  b may be NULL.  out: device memory, 3*nfactors + 8 doubles (the tail is scratch)
  * (accumulated with atomicAdd: summation order, hence the last bits, may vary from run to run). */
 int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
                      int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, const double *G, int64_t ldg,

@@ -84,11 +84,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = pathlib.Path(os.environ.get('LGP_LIB_PATH', LIB_PATH))  # override for kernel experiments only
+    if not path.exists():
         raise LibraryMissing(
             f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
             f'or `make -C {LIB_PATH.parent}`. There is no CPU fallback.')
-    lib = ctypes.CDLL(os.fspath(LIB_PATH))
+    lib = ctypes.CDLL(os.fspath(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res

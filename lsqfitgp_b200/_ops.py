@@ -97,12 +97,12 @@ def gram_iso_vjp(descs, x, Ginv, b):
     lib = _lib.load()
     ndim, n = x.shape
     x = x.contiguous() if x.stride(1) != 1 else x
-    out = torch.empty((len(descs), 3), dtype=f64, device=x.device)
+    buf = torch.empty(3 * len(descs) + 8, dtype=f64, device=x.device)
     facs = make_factors(descs)
     check(lib.lgp_gram_iso_vjp(stream_ptr(), facs, len(descs), ndim, ptr(x), x.stride(0) if ndim else 0, n,
-                               ptr(x), x.stride(0) if ndim else 0, n, ptr(Ginv), Ginv.stride(0), ptr(b), 1, ptr(out)),
+                               ptr(x), x.stride(0) if ndim else 0, n, ptr(Ginv), Ginv.stride(0), ptr(b), 1, ptr(buf)),
           'lgp_gram_iso_vjp')
-    return out
+    return buf[:3 * len(descs)].reshape(len(descs), 3)
 
 
 def gram_iso_vjp_general(descs, x, y, G):
@@ -113,12 +113,12 @@ def gram_iso_vjp_general(descs, x, y, G):
     x = x.contiguous() if x.stride(1) != 1 else x
     y = y.contiguous() if y.stride(1) != 1 else y
     assert G.shape == (n, m) and G.stride(1) == 1
-    out = torch.empty((len(descs), 3), dtype=f64, device=x.device)
+    buf = torch.empty(3 * len(descs) + 8, dtype=f64, device=x.device)
     facs = make_factors(descs)
     check(lib.lgp_gram_iso_vjp(stream_ptr(), facs, len(descs), ndim, ptr(x), x.stride(0) if ndim else 0, n,
-                               ptr(y), y.stride(0) if ndim else 0, m, ptr(G), G.stride(0), None, 0, ptr(out)),
+                               ptr(y), y.stride(0) if ndim else 0, m, ptr(G), G.stride(0), None, 0, ptr(buf)),
           'lgp_gram_iso_vjp')
-    return out
+    return buf[:3 * len(descs)].reshape(len(descs), 3)
 
 
 _psi_cache = {}

@@ -592,6 +592,177 @@ static void solve_upper_rec(SolveCtx &c, int jb, int nb) {
     solve_upper_rec(c, jb, n1);
 }
 
+// ------------------------------------------------------------------------------------------------
+// vector triangular solves (m == 1): one launch per 128-block, HBM-streaming GEMV updates
+// ------------------------------------------------------------------------------------------------
+__global__ void vec_scale_store_kernel(const double *src, double *dst, int64_t stride, int n,
+                                       const double *__restrict__ f);
+
+constexpr int TRSV_THREADS = 256;
+constexpr int TRSV_DIAG_THREADS = 1024;
+constexpr int TRSV_ROWS_PER_CTA = 64;  // forward update: 8 warps x 8 rows, all loads of a warp in flight at once
+
+// In-place blocked TRSV, two launches per 128-block:
+//   diag kernel  : b_j <- op(invd_j) b_j                        (one CTA of 32 warps, every load independent)
+//   update kernel: b[rest] -= op(L)[rest, j] b_j                (forward: rows below; backward: columns before)
+// `stride` is the element stride of the vector (a column of a row-major n x m matrix).
+template <bool TRANS>
+__global__ void __launch_bounds__(TRSV_DIAG_THREADS) trsv_diag_kernel(const double *__restrict__ invd,
+                                                                      double *__restrict__ b, int64_t stride, int j0,
+                                                                      int n) {
+    __shared__ double bj[NB], xs[NB];
+    __shared__ double part[8][NB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < NB) bj[tid] = (j0 + tid < n) ? b[(int64_t)(j0 + tid) * stride] : 0.0;
+    __syncthreads();
+    if (!TRANS) {
+        // x[r] = sum_{k <= r} invd[r][k] b[k]: warp w owns rows 4w..4w+3, lanes along k
+        double v[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[i][q] = invd[(4 * warp + i) * NB + lane + 32 * q];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc += v[i][q] * bj[lane + 32 * q];  // invd is zero above the diagonal
+            acc = warp_sum(acc);
+            if (lane == 0) xs[4 * warp + i] = acc;
+        }
+    } else {
+        // x[c] = sum_{k >= c} invd[k][c] b[k]: 8 threads per column, 16 k-values each
+        const int c = tid & 127, part_id = tid >> 7;
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = invd[(part_id * 16 + i) * NB + c];
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc += v[i] * bj[part_id * 16 + i];
+        part[part_id][c] = acc;
+        __syncthreads();
+        if (tid < NB) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) t += part[q][tid];
+            xs[tid] = t;
+        }
+    }
+    __syncthreads();
+    if (tid < NB && j0 + tid < n) b[(int64_t)(j0 + tid) * stride] = xs[tid];
+}
+
+// forward: rows r >= j0+128: b[r] -= L[r][j0..j0+127] . x_j   (x_j = b_j, already solved)
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_update_kernel(const double *__restrict__ W, int64_t ldw,
+                                                                       double *__restrict__ b, int64_t stride,
+                                                                       int j0, int n) {
+    __shared__ double xs[NB];
+    const int tid = threadIdx.x;
+    if (tid < NB) xs[tid] = b[(int64_t)(j0 + tid) * stride];
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int r0 = j0 + NB + TRSV_ROWS_PER_CTA * blockIdx.x + 8 * warp;
+    double xv[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) xv[q] = xs[4 * lane + q];
+    double4 l[8];
+    double old[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int r = r0 + i;
+        if (r < n) {
+            l[i] = *reinterpret_cast<const double4 *>(W + (int64_t)r * ldw + j0 + 4 * lane);
+            old[i] = (lane == 0) ? b[(int64_t)r * stride] : 0.0;
+        } else {
+            l[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+            old[i] = 0.0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        double acc = l[i].x * xv[0] + l[i].y * xv[1] + l[i].z * xv[2] + l[i].w * xv[3];
+        acc = warp_sum(acc);
+        if (lane == 0 && r0 + i < n) b[(int64_t)(r0 + i) * stride] = old[i] - acc;
+    }
+}
+
+// backward: columns c < j0: b[c] -= sum_{r < rows} L[j0+r][c] * x_j[r]; 2 threads per column (64 rows each)
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_update_kernel(const double *__restrict__ W, int64_t ldw,
+                                                                       double *__restrict__ b, int64_t stride,
+                                                                       int j0, int n) {
+    __shared__ double xs[NB];
+    __shared__ double part[TRSV_THREADS / 2];
+    const int tid = threadIdx.x;
+    const int rows = min(NB, n - j0);
+    if (tid < NB) xs[tid] = (tid < rows) ? b[(int64_t)(j0 + tid) * stride] : 0.0;
+    __syncthreads();
+    const int cl = tid & 127, half = tid >> 7;
+    const int col = blockIdx.x * (TRSV_THREADS / 2) + cl;
+    double acc = 0.0;
+    if (col < j0) {
+        const double *Lp = W + (int64_t)(j0 + half * 64) * ldw + col;
+#pragma unroll
+        for (int r8 = 0; r8 < 64; r8 += 16) {
+            double v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = Lp[(int64_t)(r8 + i) * ldw];  // rows beyond n are identity padding
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc += v[i] * xs[half * 64 + r8 + i];
+        }
+    }
+    if (half) part[cl] = acc;
+    __syncthreads();
+    if (!half && col < j0) b[(int64_t)col * stride] -= acc + part[cl];
+}
+
+static int trsv_inplace(cudaStream_t st, const double *W, int64_t ldw, const double *invd, const double *sinv, int n,
+                        double *b, int64_t stride, int trans) {
+    const int nblk = (n + NB - 1) / NB;
+    if (!trans) {
+        // L^-1 b = Lt^-1 (b / s): the scaling is applied when a block is first read.  Rows below the current
+        // block are updated before they are scaled, so scale the whole vector first (one tiny pass).
+        vec_scale_store_kernel<<<(n + 255) / 256, 256, 0, st>>>(b, b, stride, n, sinv);
+        LGP_CUDA_CHECK_LAUNCH();
+        for (int jb = 0; jb < nblk; jb++) {
+            const int j0 = jb * NB;
+            trsv_diag_kernel<false><<<1, TRSV_DIAG_THREADS, 0, st>>>(invd + (int64_t)jb * NB * NB, b, stride, j0, n);
+            LGP_CUDA_CHECK_LAUNCH();
+            const int rest = n - j0 - NB;
+            if (rest > 0) {
+                trsv_fwd_update_kernel<<<(rest + TRSV_ROWS_PER_CTA - 1) / TRSV_ROWS_PER_CTA, TRSV_THREADS, 0, st>>>(
+                    W, ldw, b, stride, j0, n);
+                LGP_CUDA_CHECK_LAUNCH();
+            }
+        }
+    } else {
+        // L^-T b = S^-1 Lt^-T b: scale each block by 1/s as it is finished
+        for (int jb = nblk - 1; jb >= 0; jb--) {
+            const int j0 = jb * NB;
+            trsv_diag_kernel<true><<<1, TRSV_DIAG_THREADS, 0, st>>>(invd + (int64_t)jb * NB * NB, b, stride, j0, n);
+            LGP_CUDA_CHECK_LAUNCH();
+            if (j0 > 0) {
+                trsv_bwd_update_kernel<<<(j0 + TRSV_THREADS / 2 - 1) / (TRSV_THREADS / 2), TRSV_THREADS, 0, st>>>(
+                    W, ldw, b, stride, j0, n);
+                LGP_CUDA_CHECK_LAUNCH();
+            }
+        }
+        vec_scale_store_kernel<<<(n + 255) / 256, 256, 0, st>>>(b, b, stride, n, sinv);
+        LGP_CUDA_CHECK_LAUNCH();
+    }
+    return LGP_OK;
+}
+
+__global__ void vec_scale_copy_kernel(const double *__restrict__ src, int64_t stride, double *__restrict__ dst, int n,
+                                      const double *__restrict__ f) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[(int64_t)i * stride] * (f ? f[i] : 1.0);
+}
+__global__ void vec_scale_store_kernel(const double *src, double *dst, int64_t stride, int n,
+                                       const double *__restrict__ f) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[(int64_t)i * stride] = src[(int64_t)i * stride] * (f ? f[i] : 1.0);
+}
+
 // X = Lt^-1 (lower) out of place into X (ld = ldx); the strict upper triangle of X is scratch.
 struct InvCtx {
     cudaStream_t st;
@@ -699,6 +870,7 @@ int lgp_chol_solve(lgp_stream_t stream, const double *W, int64_t ldw, const doub
     cudaStream_t st = (cudaStream_t)stream;
     const double *sinv = aux + LGP_AUX_SINV(npad);
     int64_t total = (int64_t)n * m;
+    if (m == 1) return trsv_inplace(st, W, ldw, aux + LGP_AUX_INVDIAG(npad), sinv, n, B, ldb, trans);
     SolveCtx c{st, W, ldw, aux + LGP_AUX_INVDIAG(npad), n, B, ldb, m, LGP_OK};
     if (!trans) {
         row_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, ldb, n, m, sinv);

@@ -8,7 +8,8 @@ template <class Cfg, bool AK, bool BK_>
 static int launch_cfg(cudaStream_t stream, GemmParams &p) {
     p.tiles_m = (p.M + Cfg::BM - 1) / Cfg::BM;
     p.tiles_n = (p.N + Cfg::BN - 1) / Cfg::BN;
-    int64_t grid = (p.flags & GEMM_LOWER) ? (int64_t)p.tiles_m * (p.tiles_m + 1) / 2 : (int64_t)p.tiles_m * p.tiles_n;
+    int64_t grid = (p.flags & GEMM_LOWER) ? (int64_t)(Cfg::BM >= Cfg::BN ? Cfg::BM / Cfg::BN : 1) * p.tiles_m * (p.tiles_m + 1) / 2
+                                          : (int64_t)p.tiles_m * p.tiles_n;
     if (grid > 2147483647LL) return LGP_ERR_UNSUPPORTED;
     static bool attr_set = false;  // one flag per template instantiation
     if (!attr_set) {
@@ -45,16 +46,16 @@ int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.alpha = alpha;
     p.flags = flags;
-    // tile configuration: big tiles when they fill the machine, small ones for latency-bound products
-    const int64_t tm = (M + 127) / 128, tn = (N + 127) / 128;
-    const int64_t big_tiles = (flags & GEMM_LOWER) ? tm * (tm + 1) / 2 : tm * tn;
-    const bool small_ok = big_tiles < 112 && !(flags & GEMM_FORCE_BIG);
-    if (flags & GEMM_INPLACE_B) return launch_layout<GemmBig>(stream, a_kmaj, b_kmaj, p);
-    if (flags & GEMM_INPLACE_A) {
-        if (small_ok && a_kmaj && b_kmaj) return launch_cfg<GemmTall, true, true>(stream, p);
-        return launch_layout<GemmBig>(stream, a_kmaj, b_kmaj, p);
+    // tile configuration: the in-place products need the aliased dimension inside one tile
+    if (flags & GEMM_INPLACE_B) {
+        if (a_kmaj && !b_kmaj) return launch_cfg<GemmWide, true, false>(stream, p);
+        if (!a_kmaj && !b_kmaj) return launch_cfg<GemmWide, false, false>(stream, p);
+        return LGP_ERR_UNSUPPORTED;
     }
-    if (small_ok) return launch_layout<GemmSmall>(stream, a_kmaj, b_kmaj, p);
+    if (flags & GEMM_INPLACE_A) {
+        if (a_kmaj && b_kmaj) return launch_cfg<GemmTall, true, true>(stream, p);
+        return LGP_ERR_UNSUPPORTED;
+    }
     return launch_layout<GemmBig>(stream, a_kmaj, b_kmaj, p);
 }
 

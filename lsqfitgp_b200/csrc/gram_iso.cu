@@ -343,6 +343,431 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_vjp_kernel(const __grid_co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path: K = amp * core(r2 / scale^2) [+ amp_w * White] [+ const], one isotropic factor over the same fields
+// for x and y.  Symmetric mode evaluates only tiles on or below the diagonal and mirrors them through shared
+// memory so that both the tile and its transpose are written with full 512-byte row segments.
+// The arithmetic (operation order, explicit roundings) is identical to the general kernel.
+// ------------------------------------------------------------------------------------------------
+struct FastDesc {
+    int kind, p, nd;        // main factor
+    int has_white, has_const, white_raw;
+    double scale, loc, par0, par1, amp, amp_white, amp_const;
+    double coef[G_MAX_P];
+    unsigned char dims[LGP_MAX_DIMS];
+};
+
+template <int KIND>
+__device__ __forceinline__ double fast_core(const FastDesc &d, double r2) {
+    if (KIND == LGP_K_EXPQUAD) return exp(__dmul_rn(-0.5, r2));
+    if (KIND == LGP_K_MATERNP) {
+        double z = __dadd_rn(__dmul_rn((double)(2 * d.p + 1), r2), d.par0);
+        double x = sqrt(z);
+        double poly = 1.0;
+        for (int k = d.p - 1; k >= 0; k--)
+            poly = __dadd_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(poly, d.coef[k]), 2.0), x));
+        return __dmul_rn(exp(-x), poly);
+    }
+    // Cauchy
+    double pw = (d.par0 == 2.0) ? r2 : pow(r2, d.par0 / 2.0);
+    return pow(__dadd_rn(1.0, pw / d.par1), -d.par1 / d.par0);
+}
+
+constexpr int FT = 64;
+
+template <int KIND, bool SYM>
+__global__ void __launch_bounds__(G_THREADS, 2) gram_fast_kernel(const __grid_constant__ FastDesc d,
+                                                                 const double *__restrict__ x, int64_t ldx, int64_t n,
+                                                                 const double *__restrict__ y, int64_t ldy, int64_t m,
+                                                                 double *__restrict__ K, int64_t ldk, int vec_ok,
+                                                                 int tiles_n) {
+    extern __shared__ __align__(16) double fsm[];
+    // layout: su[nd][64], sv[nd][64], (raw copies for White when the main factor rescales) ru[nd][64], rv[nd][64],
+    // then the transpose buffer T[64][65] in symmetric mode
+    const int nd = d.nd;
+    double *su = fsm, *sv = fsm + nd * FT;
+    double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
+    double *T = rv + (d.white_raw ? nd * FT : 0);
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    int tm, tn;
+    if (SYM) {
+        long long b = blockIdx.x;
+        tm = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+        while ((long long)(tm + 1) * (tm + 2) / 2 <= b) tm++;
+        while ((long long)tm * (tm + 1) / 2 > b) tm--;
+        tn = (int)(b - (long long)tm * (tm + 1) / 2);
+    } else {
+        tm = blockIdx.x / tiles_n;
+        tn = blockIdx.x % tiles_n;
+    }
+    const int64_t i0 = (int64_t)tm * FT, j0 = (int64_t)tn * FT;
+    for (int idx = tid; idx < nd * FT; idx += G_THREADS) {
+        const int s = idx / FT, r = idx % FT;
+        const int64_t i = i0 + r, j = j0 + r;
+        double xr = (i < n) ? x[(int64_t)d.dims[s] * ldx + i] : 0.0;
+        double yr = (j < m) ? y[(int64_t)d.dims[s] * ldy + j] : 0.0;
+        su[idx] = __ddiv_rn(__dsub_rn(xr, d.loc), d.scale);
+        sv[idx] = __ddiv_rn(__dsub_rn(yr, d.loc), d.scale);
+        if (d.white_raw) {
+            ru[idx] = xr;
+            rv[idx] = yr;
+        }
+    }
+    __syncthreads();
+
+    double r2[4][4];
+    bool eq[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            r2[a][c] = 0.0;
+            eq[a][c] = true;
+        }
+    for (int s = 0; s < nd; s++) {
+        double uu[4], vv[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) uu[a] = su[s * FT + ty + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            double2 t = *reinterpret_cast<const double2 *>(&sv[s * FT + 2 * tx + 32 * b]);
+            vv[2 * b] = t.x;
+            vv[2 * b + 1] = t.y;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double df = __dsub_rn(uu[a], vv[c]);
+                r2[a][c] = __dadd_rn(r2[a][c], __dmul_rn(df, df));
+            }
+        if (d.has_white) {
+            if (d.white_raw) {
+#pragma unroll
+                for (int a = 0; a < 4; a++) uu[a] = ru[s * FT + ty + 16 * a];
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    double2 t = *reinterpret_cast<const double2 *>(&rv[s * FT + 2 * tx + 32 * b]);
+                    vv[2 * b] = t.x;
+                    vv[2 * b + 1] = t.y;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) eq[a][c] = eq[a][c] && (uu[a] == vv[c]);
+        }
+    }
+    double val[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            double v = __dmul_rn(d.amp, fast_core<KIND>(d, r2[a][c]));
+            if (d.has_white) v = __dadd_rn(v, eq[a][c] ? d.amp_white : 0.0);
+            if (d.has_const) v = __dadd_rn(v, d.amp_const);
+            val[a][c] = v;
+        }
+    // direct tile
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        int64_t i = i0 + ty + 16 * a;
+        if (i >= n) continue;
+        double *krow = K + i * ldk;
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            int64_t j = j0 + 2 * tx + 32 * b;
+            if (j >= m) continue;
+            if (vec_ok && j + 1 < m) {
+                *reinterpret_cast<double2 *>(krow + j) = make_double2(val[a][2 * b], val[a][2 * b + 1]);
+            } else {
+                krow[j] = val[a][2 * b];
+                if (j + 1 < m) krow[j + 1] = val[a][2 * b + 1];
+            }
+        }
+    }
+    if (SYM && tm != tn) {
+        // mirrored tile: K[j][i] = K[i][j]
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) T[(2 * tx + 32 * (c >> 1) + (c & 1)) * (FT + 1) + ty + 16 * a] = val[a][c];
+        __syncthreads();
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int rr = warp; rr < FT; rr += G_THREADS / 32) {
+            int64_t j = j0 + rr;  // row of the mirrored tile
+            if (j >= m) break;
+            double *krow = K + j * ldk + i0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int cidx = lane + 32 * h;
+                if (i0 + cidx < n) krow[cidx] = T[rr * (FT + 1) + cidx];
+            }
+        }
+    }
+}
+
+// d core / d r2 for the fast path (value returned through `val`)
+template <int KIND>
+__device__ __forceinline__ void fast_core_derivs(const FastDesc &d, double r2, double &val, double &dr2,
+                                                 double &dpar1) {
+    dpar1 = 0.0;
+    if (KIND == LGP_K_EXPQUAD) {
+        val = exp(-0.5 * r2);
+        dr2 = -0.5 * val;
+    } else if (KIND == LGP_K_MATERNP) {
+        const double nu2 = (double)(2 * d.p + 1);
+        double z = nu2 * r2 + d.par0;
+        double x = sqrt(z);
+        double ex = exp(-x);
+        double poly = 1.0;
+        for (int k = d.p - 1; k >= 0; k--) poly = 1.0 + poly * d.coef[k] * 2.0 * x;
+        val = ex * poly;
+        if (d.p == 0) {
+            dr2 = x > 0.0 ? -nu2 * ex / (2.0 * x) : 0.0;
+        } else {
+            const int pm = d.p - 1;
+            double polym = 1.0;
+            for (int k = pm - 1; k >= 0; k--)
+                polym = 1.0 + polym * ((double)(pm - k) / (double)((2 * pm - k) * (k + 1))) * 2.0 * x;
+            dr2 = -nu2 * ex * polym / (4.0 * ((double)d.p - 0.5));
+        }
+    } else {
+        const double alpha = d.par0, beta = d.par1;
+        double t = (alpha == 2.0) ? r2 : pow(r2, alpha / 2.0);
+        double base = 1.0 + t / beta;
+        val = pow(base, -beta / alpha);
+        double dvdt = -(1.0 / alpha) * val / base;
+        double dtdr2 = (alpha == 2.0) ? 1.0 : (r2 > 0.0 ? (alpha / 2.0) * t / r2 : 0.0);
+        dr2 = dvdt * dtdr2;
+        dpar1 = val * (-(1.0 / alpha) * log(base) + (t / (alpha * beta)) / base);
+    }
+}
+
+// Fast symmetric VJP over the lower triangle: out[0..2] main factor (d amp, d log scale, d par1),
+// out[3] = d/d amp_white, out[4] = d/d amp_const.  G_ij = w_ij (Ginv_ij - b_i b_j).
+template <int KIND>
+__global__ void __launch_bounds__(G_THREADS, 2) gram_fast_vjp_kernel(const __grid_constant__ FastDesc d,
+                                                                     const double *__restrict__ x, int64_t ldx,
+                                                                     int64_t n, const double *__restrict__ G,
+                                                                     int64_t ldg, const double *__restrict__ bvec,
+                                                                     double *__restrict__ out) {
+    extern __shared__ __align__(16) double fsm[];
+    const int nd = d.nd;
+    double *su = fsm, *sv = fsm + nd * FT;
+    double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
+    __shared__ double sbi[FT], sbj[FT];
+    __shared__ double red[G_THREADS / 32][5];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    long long b = blockIdx.x;
+    int tm = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((long long)(tm + 1) * (tm + 2) / 2 <= b) tm++;
+    while ((long long)tm * (tm + 1) / 2 > b) tm--;
+    const int tn = (int)(b - (long long)tm * (tm + 1) / 2);
+    const int64_t i0 = (int64_t)tm * FT, j0 = (int64_t)tn * FT;
+    for (int idx = tid; idx < nd * FT; idx += G_THREADS) {
+        const int s = idx / FT, r = idx % FT;
+        const int64_t i = i0 + r, j = j0 + r;
+        double xr = (i < n) ? x[(int64_t)d.dims[s] * ldx + i] : 0.0;
+        double yr = (j < n) ? x[(int64_t)d.dims[s] * ldx + j] : 0.0;
+        su[idx] = (xr - d.loc) / d.scale;
+        sv[idx] = (yr - d.loc) / d.scale;
+        if (d.white_raw) {
+            ru[idx] = xr;
+            rv[idx] = yr;
+        }
+    }
+    if (tid < FT) {
+        sbi[tid] = (bvec && i0 + tid < n) ? bvec[i0 + tid] : 0.0;
+        sbj[tid] = (bvec && j0 + tid < n) ? bvec[j0 + tid] : 0.0;
+    }
+    __syncthreads();
+
+    double r2[4][4];
+    bool eq[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            r2[a][c] = 0.0;
+            eq[a][c] = true;
+        }
+    for (int s = 0; s < nd; s++) {
+        double uu[4], vv[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) uu[a] = su[s * FT + ty + 16 * a];
+#pragma unroll
+        for (int bb = 0; bb < 2; bb++) {
+            double2 t = *reinterpret_cast<const double2 *>(&sv[s * FT + 2 * tx + 32 * bb]);
+            vv[2 * bb] = t.x;
+            vv[2 * bb + 1] = t.y;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double df = uu[a] - vv[c];
+                r2[a][c] += df * df;
+            }
+        if (d.has_white) {
+            if (d.white_raw) {
+#pragma unroll
+                for (int a = 0; a < 4; a++) uu[a] = ru[s * FT + ty + 16 * a];
+#pragma unroll
+                for (int bb = 0; bb < 2; bb++) {
+                    double2 t = *reinterpret_cast<const double2 *>(&rv[s * FT + 2 * tx + 32 * bb]);
+                    vv[2 * bb] = t.x;
+                    vv[2 * bb + 1] = t.y;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) eq[a][c] = eq[a][c] && (uu[a] == vv[c]);
+        }
+    }
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const bool vec_ok = ((ldg & 1) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0);
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int64_t i = i0 + ty + 16 * a;
+        if (i >= n) continue;
+        const double bi = sbi[ty + 16 * a];
+#pragma unroll
+        for (int bb = 0; bb < 2; bb++) {
+            const int cc = 2 * tx + 32 * bb;
+            const int64_t j = j0 + cc;
+            if (j > i) continue;
+            double g0, g1 = 0.0;
+            const bool second = (j + 1 <= i);  // j + 1 <= i < n
+            if (vec_ok && second) {
+                double2 t = *reinterpret_cast<const double2 *>(G + i * ldg + j);
+                g0 = t.x;
+                g1 = t.y;
+            } else {
+                g0 = G[i * ldg + j];
+                if (second) g1 = G[i * ldg + j + 1];
+            }
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                if (e == 1 && !second) continue;
+                double g = (e ? g1 : g0) - bi * sbj[cc + e];
+                if (j + e != i) g *= 2.0;
+                double val, dr2, dp1;
+                fast_core_derivs<KIND>(d, r2[a][2 * bb + e], val, dr2, dp1);
+                acc[0] += g * val;
+                acc[1] += g * d.amp * dr2 * (-2.0 * r2[a][2 * bb + e]);
+                acc[2] += g * d.amp * dp1;
+                if (d.has_white && eq[a][2 * bb + e]) acc[3] += g;
+                acc[4] += g;
+            }
+        }
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        double v = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < 5) {
+        double v = 0.0;
+        for (int w = 0; w < G_THREADS / 32; w++) v += red[w][tid];
+        atomicAdd(out + tid, v);
+    }
+}
+
+// scatter the 5 fast-path sums into the (nfactors x 3) layout of the public ABI
+__global__ void fast_vjp_scatter_kernel(const double *__restrict__ tmp, double *__restrict__ out, int nfactors,
+                                        int pos_white, int pos_const) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 3 * nfactors; i++) out[i] = 0.0;
+        out[0] = tmp[0];
+        out[1] = tmp[1];
+        out[2] = tmp[2];
+        if (pos_white >= 0) out[3 * pos_white] = tmp[3];
+        if (pos_const >= 0) out[3 * pos_const] = tmp[4];
+    }
+}
+
+static bool build_fast(const lgp_factor_t *f, int nf, int ndim, FastDesc &d) {
+    // accepted shape: [main factor in its own term] [+ White term] [+ Constant term], each at most once
+    if (nf < 1 || nf > 3) return false;
+    memset(&d, 0, sizeof(d));
+    int main_i = -1;
+    for (int i = 0; i < nf; i++) {
+        for (int j = 0; j < nf; j++)
+            if (i != j && f[i].term == f[j].term) return false;  // products: general kernel
+        if (f[i].kind == LGP_K_WHITE) {
+            if (d.has_white) return false;
+            d.has_white = 1;
+            d.amp_white = f[i].amp;
+            if (f[i].scale_x != 1.0 || f[i].scale_y != 1.0 || f[i].loc_x != 0.0 || f[i].loc_y != 0.0) return false;
+        } else if (f[i].kind == LGP_K_CONSTANT) {
+            if (d.has_const) return false;
+            d.has_const = 1;
+            d.amp_const = f[i].amp;
+        } else {
+            if (main_i >= 0) return false;
+            main_i = i;
+        }
+    }
+    if (main_i < 0) return false;
+    // term order must be main, white, const so that the sums are rounded in the reference's order
+    int pos_white = -1, pos_const = -1;
+    for (int i = 0; i < nf; i++) {
+        if (f[i].kind == LGP_K_WHITE) pos_white = i;
+        if (f[i].kind == LGP_K_CONSTANT) pos_const = i;
+    }
+    if (main_i != 0) return false;
+    if (pos_white >= 0 && pos_const >= 0 && pos_white > pos_const) return false;
+    const lgp_factor_t &m = f[main_i];
+    if (m.scale_x != m.scale_y || m.loc_x != m.loc_y) return false;
+    if (m.kind != LGP_K_EXPQUAD && m.kind != LGP_K_MATERNP && m.kind != LGP_K_CAUCHY) return false;
+    d.kind = m.kind;
+    d.p = m.ipar;
+    d.scale = m.scale_x;
+    d.loc = m.loc_x;
+    d.par0 = m.par0;
+    d.par1 = m.par1;
+    d.amp = m.amp;
+    if (m.kind == LGP_K_MATERNP) {
+        if (d.p < 0 || d.p > G_MAX_P) return false;
+        for (int k = 0; k < d.p; k++) d.coef[k] = (double)(d.p - k) / (double)((2 * d.p - k) * (k + 1));
+    }
+    for (int dd = 0; dd < ndim; dd++)
+        if (m.dimmask & (1u << dd)) d.dims[d.nd++] = (unsigned char)dd;
+    if (d.nd == 0) return false;
+    if (d.has_white) {
+        if (f[pos_white].dimmask != m.dimmask) return false;
+        d.white_raw = (d.scale != 1.0 || d.loc != 0.0);
+    }
+    return true;
+}
+
+template <int KIND>
+static int launch_fast(cudaStream_t st, const FastDesc &d, const double *x, int64_t ldx, int64_t n, const double *y,
+                       int64_t ldy, int64_t m, double *K, int64_t ldk, bool sym) {
+    size_t smem = (size_t)(2 + (d.white_raw ? 2 : 0)) * d.nd * FT * sizeof(double) + (sym ? FT * (FT + 1) * 8 : 0);
+    int64_t tm = (n + FT - 1) / FT, tn = (m + FT - 1) / FT;
+    int64_t grid = sym ? tm * (tm + 1) / 2 : tm * tn;
+    if (grid > 2147483647LL) return LGP_ERR_UNSUPPORTED;
+    int vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+    if (sym) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(gram_fast_kernel<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gram_fast_kernel<KIND, true><<<(unsigned)grid, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, K, ldk, vec_ok,
+                                                                             (int)tn);
+    } else {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(gram_fast_kernel<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gram_fast_kernel<KIND, false><<<(unsigned)grid, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, K, ldk, vec_ok,
+                                                                              (int)tn);
+    }
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
 __global__ void zero_kernel(double *p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0.0;
@@ -357,11 +782,21 @@ extern "C" {
 int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
                  int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, double *K_out, int64_t ldk,
                  int flags) {
-    (void)flags;
     if (!factors || !K_out || n < 0 || m < 0) return LGP_ERR_BADARG;
     if (n == 0 || m == 0) return LGP_OK;
     if (ndim > 0 && (!x || !y)) return LGP_ERR_BADARG;
     if (ldk < m) return LGP_ERR_BADARG;
+    if (nfactors >= 1 && nfactors <= LGP_MAX_FACTORS && ndim >= 1 && ndim <= LGP_MAX_DIMS &&
+        !(flags & LGP_GRAM_GENERAL)) {
+        FastDesc fd;
+        if (build_fast(factors, nfactors, ndim, fd)) {
+            const bool sym = (flags & LGP_GRAM_SYMMETRIC) && x == y && n == m && ldx == ldy;
+            cudaStream_t st = (cudaStream_t)stream;
+            if (fd.kind == LGP_K_EXPQUAD) return launch_fast<LGP_K_EXPQUAD>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
+            if (fd.kind == LGP_K_MATERNP) return launch_fast<LGP_K_MATERNP>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
+            return launch_fast<LGP_K_CAUCHY>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
+        }
+    }
     GramDesc d;
     int rc = build_desc(factors, nfactors, ndim, d);
     if (rc) return rc;
@@ -384,6 +819,36 @@ int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfact
                      const double *b, int symlower, double *out) {
     if (!factors || !G || !out || n < 1 || m < 1) return LGP_ERR_BADARG;
     if (symlower && (n != m)) return LGP_ERR_BADARG;
+    if (symlower && x == y && ldx == ldy && nfactors <= 3 && ndim >= 1 && ndim <= LGP_MAX_DIMS) {
+        FastDesc fd;
+        if (build_fast(factors, nfactors, ndim, fd)) {
+            cudaStream_t st = (cudaStream_t)stream;
+            int pos_white = -1, pos_const = -1;
+            for (int i = 0; i < nfactors; i++) {
+                if (factors[i].kind == LGP_K_WHITE) pos_white = i;
+                if (factors[i].kind == LGP_K_CONSTANT) pos_const = i;
+            }
+            // the 5 partial sums live in out[0..4] only if nfactors >= 2; use a scratch tail otherwise is not
+            // available (no allocation here), so accumulate in place when the layouts coincide
+            double *tmp = out + 3 * nfactors;  // caller provides 3*nfactors + 8 doubles (see header)
+            zero_kernel<<<1, 32, 0, st>>>(tmp, 8);
+            LGP_CUDA_CHECK_LAUNCH();
+            size_t smem = (size_t)(2 + (fd.white_raw ? 2 : 0)) * fd.nd * FT * sizeof(double);
+            int64_t t = (n + FT - 1) / FT;
+            int64_t nblk = t * (t + 1) / 2;
+            if (nblk > 2147483647LL) return LGP_ERR_UNSUPPORTED;
+            if (fd.kind == LGP_K_EXPQUAD)
+                gram_fast_vjp_kernel<LGP_K_EXPQUAD><<<(unsigned)nblk, G_THREADS, smem, st>>>(fd, x, ldx, n, G, ldg, b, tmp);
+            else if (fd.kind == LGP_K_MATERNP)
+                gram_fast_vjp_kernel<LGP_K_MATERNP><<<(unsigned)nblk, G_THREADS, smem, st>>>(fd, x, ldx, n, G, ldg, b, tmp);
+            else
+                gram_fast_vjp_kernel<LGP_K_CAUCHY><<<(unsigned)nblk, G_THREADS, smem, st>>>(fd, x, ldx, n, G, ldg, b, tmp);
+            LGP_CUDA_CHECK_LAUNCH();
+            fast_vjp_scatter_kernel<<<1, 32, 0, st>>>(tmp, out, nfactors, pos_white, pos_const);
+            LGP_CUDA_CHECK_LAUNCH();
+            return LGP_OK;
+        }
+    }
     GramDesc d;
     int rc = build_desc(factors, nfactors, ndim, d);
     if (rc) return rc;
