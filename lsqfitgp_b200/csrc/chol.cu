@@ -929,8 +929,15 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
         return LGP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     InvCtx c{st, W, ldw, aux + LGP_AUX_INVDIAG(npad), scratch, (int64_t)npad, LGP_OK};
+    const bool trace = getenv("LGP_TRACE") != nullptr;
+    cudaEvent_t t0, t1, t2;
+    if (trace) {
+        cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
+        cudaEventRecord(t0, st);
+    }
     trtri_rec(c, 0, npad / NB);
     if (c.rc) return c.rc;
+    if (trace) cudaEventRecord(t1, st);
     // Kinv[i][j] = sum_{k >= i} X[k][i] X[k][j], j <= i   (LAUUM as one triangular-K SYRK launch)
     int rc = gemm_launch(st, false, false, npad, npad, npad, 1.0, scratch, npad, scratch, npad, Kinv, ldk,
                          GEMM_BETA0 | GEMM_LOWER | GEMM_A_UPPER_K);
@@ -938,6 +945,15 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
     dim3 g((n + 255) / 256, n);
     sym_scale_lower_kernel<<<g, 256, 0, st>>>(Kinv, ldk, n, aux + LGP_AUX_SINV(npad));
     LGP_CUDA_CHECK_LAUNCH();
+    if (trace) {
+        cudaEventRecord(t2, st);
+        cudaEventSynchronize(t2);
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, t0, t1);
+        cudaEventElapsedTime(&b, t1, t2);
+        fprintf(stderr, "[lgp trace] inverse: trtri %.3f ms, lauum+scale %.3f ms\n", a, b);
+        cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+    }
     return LGP_OK;
 }
 
