@@ -180,6 +180,63 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
  * The reductions of Chol.minus_log_normal_density (value), _decomp.py:484-488. */
 int lgp_chol_logdet_quad(lgp_stream_t stream, const double *aux, int64_t n, const double *a, double *out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tile-level building blocks of the 2-D block-cyclic multi-GPU factorisation (one process per GPU; the
+ * collectives are issued by the host code in lsqfitgp_b200/_dist.py through torch.distributed/NCCL).  The reference
+ * is single-device; these distribute Chol.__init__ (src/lsqfitgp/_linalg/_decomp.py:380-393) and the solves
+ * (:398-439) for matrices larger than one GPU's memory.
+ *
+ * Tile (I, J) of the t x t tiling of the (padded) n x n matrix lives on process (I mod nprow, J mod npcol) at local
+ * tile position (I div nprow, J div npcol) of a dense row-major local matrix A (lda).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lgp_grid {
+    int64_t n;    /* true matrix size */
+    int32_t tile; /* t, multiple of 128 */
+    int32_t nprow, npcol, prow, pcol;
+} lgp_grid_t;
+
+/* rows/cols of the local matrix of this process */
+int lgp_dist_local_shape(const lgp_grid_t *grid, int64_t *rows, int64_t *cols);
+/* d[i] = A_ii for the diagonal entries (i < n) stored on this process; other entries of d are left untouched */
+int lgp_dist_diag(lgp_stream_t stream, const lgp_grid_t *grid, const double *A, int64_t lda, double *d);
+/* s_i = 2^rint(log2(d_i)/2) (1 if d_i == 0 or i >= n), sinv = 1/s: diag_scale_pow2, _decomp.py:356-361 */
+int lgp_dist_scale_from_diag(lgp_stream_t stream, const double *d, int64_t n, int64_t npad, double *s, double *sinv);
+/* A <- A/s_i/s_j, identity in the padding rows/columns (global index >= n); rowsum[i] = sum over the LOCAL columns of
+ * |A_ij| for the rows stored here (other entries untouched): the partial Gershgorin sums of eigval_bound,
+ * _decomp.py:349-354, to be summed over processes */
+int lgp_dist_prepare(lgp_stream_t stream, const lgp_grid_t *grid, double *A, int64_t lda, const double *sinv,
+                     double *rowsum);
+/* out[0] = max_i rowsum_i, out[1] = eps = epsrel*out[0] + epsabs (epsrel < 0: 'auto' = n*2^-52), _decomp.py:245-255 */
+int lgp_dist_eps(lgp_stream_t stream, const double *rowsum, int64_t n, double epsrel, double epsabs, double *out);
+/* A_ii += eps[0] for the diagonal entries (i < n) stored on this process (_decomp.py:386-387) */
+int lgp_dist_add_diag(lgp_stream_t stream, const lgp_grid_t *grid, double *A, int64_t lda, const double *eps);
+
+/* Cholesky of one t x t diagonal tile in place (lower triangle), plus the inverted 128x128 diagonal blocks
+ * (invd: t/128 blocks), the diagonal of the factor (dvec[j0 + i], i < t) and info (atomicMin of the 1-based GLOBAL
+ * index j0 + i + 1 of a failed pivot; initialise to INT_MAX). */
+int lgp_tile_potrf(lgp_stream_t stream, double *A, int64_t lda, int64_t t, double *invd, double *dvec, int32_t *info,
+                   int64_t j0);
+/* B (rows x t, ldb) <- B L^-T for a factored diagonal tile L (t x t, ldl) with its inverted diagonal blocks */
+int lgp_tile_trsm_right(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *B,
+                        int64_t ldb, int64_t rows);
+/* b (t contiguous doubles) <- L^-1 b (trans=0) or L^-T b (trans=1) */
+int lgp_tile_trsv(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *b,
+                  int trans);
+/* Trailing update of step k for the local tile columns lj in [lj_begin, lj_end):
+ *   A[I, J] -= L[I, k] L[J, k]^T   for the local tiles with I >= J > k,
+ * panel[r] (r < nprow; HOST array of device pointers) = the tiles L[I, k], I > k, I mod nprow == r, stacked in
+ * increasing I as a contiguous (count*t) x t matrix (what process (r, k mod npcol) broadcasts).  One DMMA GEMM launch
+ * per local tile column. */
+int lgp_dist_trailing_update(lgp_stream_t stream, const lgp_grid_t *grid, double *A, int64_t lda, int64_t k,
+                             const double *const *panel, int64_t lj_begin, int64_t lj_end);
+/* y += alpha * P x (trans=0; P rows x cols, x cols, y rows) or y += alpha * P^T x (trans=1; x rows, y cols):
+ * the HBM-streaming vector updates of the distributed triangular solves */
+int lgp_dgemv(lgp_stream_t stream, int trans, const double *P, int64_t ldp, int64_t rows, int64_t cols,
+              const double *x, double *y, double alpha);
+/* dst (ldd) <- src (lds), rows x cols; ld even, 16-byte aligned bases (panel staging) */
+int lgp_copy2d(lgp_stream_t stream, const double *src, int64_t lds, double *dst, int64_t ldd, int64_t rows,
+               int64_t cols);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,17 +1,33 @@
-"""Multi-GPU: sharding of independent hyperparameter evaluations (one process per GPU, torch.distributed).
+"""Multi-GPU layer: one process per GPU, `torch.distributed` (NCCL over NVLink/NVSwitch) for the plumbing.
 
-The reference has no parallelism of any kind; its optimiser evaluates one hyperparameter
-point at a time (src/lsqfitgp/_fit.py:338).  Batches of evaluations (multi-start fits, line-search fans, grids)
-are independent units: X and y are replicated (n*d*8 bytes), every rank runs the full single-GPU path on its
-share of the points, and one all_gather of (1 + k) doubles per point assembles the result.  There is no
-data-path collective: the Gram/Cholesky kernels never talk across GPUs here.
+The reference has no parallelism of any kind.  Two things shard here:
+
+1. **Batches of hyperparameter evaluations** (`eval_batch_sharded`): independent units, X and y replicated, every
+   rank runs the full single-GPU path on its share of the points, one all_gather of (1 + k) doubles per point.
+   No data-path collective.  (The reference's optimiser evaluates one point at a time, src/lsqfitgp/_fit.py:338.)
+
+2. **One factorisation larger than a GPU** (`DistChol`): `Chol.__init__` and the solves of
+   src/lsqfitgp/_linalg/_decomp.py:380-439 on a 2-D block-cyclic layout over a Pr x Pc process grid.  Tile (I, J) of
+   the T x T tiling lives on process (I mod Pr, J mod Pc); each process stores its tiles as one dense local matrix,
+   generated in place from the replicated points (the Gram matrix is never gathered).  Right-looking factorisation
+   with one-panel look-ahead: the panel chain (diagonal-tile Cholesky -> broadcast -> TRSM -> panel broadcast)
+   runs on a high-priority stream while the previous trailing update (DMMA GEMMs) occupies the main stream.
+   All arithmetic happens in liblgpb200.so (lgp_dist_* / lgp_tile_* entry points); this module is the host
+   orchestration and is backend-neutral: the tile operations come from an `ops` provider (`CudaTileOps` is the
+   product; the CPU test tier drives the same orchestration over gloo with a NumPy provider that lives in tests/).
 """
+
+import contextlib
+import ctypes
+import math
 
 import numpy
 import torch
 import torch.distributed as dist
 
-__all__ = ['shard_indices', 'eval_batch_sharded']
+__all__ = ['shard_indices', 'eval_batch_sharded', 'Layout', 'default_grid', 'DistChol', 'CudaTileOps']
+
+INT_MAX = 2 ** 31 - 1
 
 
 def shard_indices(nitems, rank, world):
@@ -56,3 +72,472 @@ def eval_batch_sharded(fun, thetas, *, group=None, device=None):
         idx = shard_indices(B, r, world)
         out[idx] = gathered[r][:len(idx)].cpu().numpy()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 2-D block-cyclic layout
+# ---------------------------------------------------------------------------------------------------------------
+
+def tiles_before(J, r, P):
+    """ number of tiles I < J with I mod P == r """
+    return (J - r + P - 1) // P if J > r else 0
+
+
+def default_grid(world):
+    """ process grid (Pr, Pc): as square as possible with Pr <= Pc; 2 ranks split the rows (2 x 1) so that the
+    panel TRSM is shared (2x1, 2x2, 2x4) """
+    if world == 2:
+        return 2, 1
+    pr = int(math.isqrt(world))
+    while world % pr:
+        pr -= 1
+    return pr, world // pr
+
+
+class Layout:
+    """ ownership maps of the T x T tiling of an n x n matrix on a Pr x Pc grid (ranks row-major) """
+
+    def __init__(self, n, tile, nprow, npcol, rank):
+        assert n >= 1 and tile >= 128 and tile % 128 == 0 and nprow >= 1 and npcol >= 1
+        assert 0 <= rank < nprow * npcol
+        self.n, self.T, self.Pr, self.Pc, self.rank = int(n), int(tile), int(nprow), int(npcol), int(rank)
+        self.pr, self.pc = divmod(self.rank, self.Pc)
+        self.NT = -(-self.n // self.T)
+        self.npad = self.NT * self.T
+        self.LR = tiles_before(self.NT, self.pr, self.Pr)
+        self.LC = tiles_before(self.NT, self.pc, self.Pc)
+
+    def rank_of(self, r, c):
+        return r * self.Pc + c
+
+    def owner(self, I, J):
+        return self.rank_of(I % self.Pr, J % self.Pc)
+
+    def row_tiles(self, r=None):
+        return list(range(self.pr if r is None else r, self.NT, self.Pr))
+
+    def col_tiles(self, c=None):
+        return list(range(self.pc if c is None else c, self.NT, self.Pc))
+
+    def _glob(self, tiles):
+        T = self.T
+        if not tiles:
+            return numpy.zeros(0, dtype=numpy.int64)
+        return (numpy.asarray(tiles, dtype=numpy.int64)[:, None] * T + numpy.arange(T, dtype=numpy.int64)).reshape(-1)
+
+    def global_rows(self, r=None):
+        """ global index of every local row of process row r """
+        return self._glob(self.row_tiles(r))
+
+    def global_cols(self, c=None):
+        return self._glob(self.col_tiles(c))
+
+    def panel_first(self, k, r=None):
+        """ local tile-row index (in process row r) of the first tile I > k """
+        return tiles_before(k + 1, self.pr if r is None else r, self.Pr)
+
+    def panel_count(self, k, r=None):
+        """ number of tiles I > k in process row r: the height of what (r, k mod Pc) broadcasts at step k """
+        r = self.pr if r is None else r
+        return tiles_before(self.NT, r, self.Pr) - tiles_before(k + 1, r, self.Pr)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUDA tile operations (the product path): thin calls into liblgpb200.so
+# ---------------------------------------------------------------------------------------------------------------
+
+class _NullEvent:
+    def record(self):
+        pass
+
+    def wait(self):
+        pass
+
+
+class CudaTileOps:
+    """ local operations of DistChol on the rank's GPU through the C ABI (include/lgp_b200.h, lgp_dist_*/lgp_tile_*) """
+
+    def __init__(self, device):
+        from . import _lib
+        _lib.require_cuda()
+        self._libmod = _lib
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.main = torch.cuda.current_stream(self.device)
+        lo, hi = -1, 0
+        try:
+            hi, lo = torch.cuda.Stream.priority_range()  # (least, greatest); greatest is the most negative number
+        except Exception:
+            pass
+        self.panel = torch.cuda.Stream(self.device, priority=min(lo, hi))
+
+    # ---- plumbing
+    def zeros(self, *shape, dtype=torch.float64):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def main_stream(self):
+        return torch.cuda.stream(self.main)
+
+    def panel_stream(self):
+        return torch.cuda.stream(self.panel)
+
+    def event(self):
+        ev = torch.cuda.Event()
+
+        class _Ev:
+            def record(self_inner):
+                ev.record(torch.cuda.current_stream())
+
+            def wait(self_inner):
+                torch.cuda.current_stream().wait_event(ev)
+        return _Ev()
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+    def _grid(self, lay):
+        g = self._libmod.Grid()
+        g.n, g.tile, g.nprow, g.npcol, g.prow, g.pcol = lay.n, lay.T, lay.Pr, lay.Pc, lay.pr, lay.pc
+        return g
+
+    def _sp(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ck(self, rc, what):
+        self._libmod.check(rc, what)
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    # ---- matrix generation and preparation
+    def gram_local(self, descs, x, rows, cols, lay):
+        """ local matrix K[rows, cols] generated in place from the replicated points x (ndim, n) """
+        from . import _ops
+        ri = torch.as_tensor(numpy.minimum(rows, lay.n - 1), device=self.device)
+        ci = torch.as_tensor(numpy.minimum(cols, lay.n - 1), device=self.device)
+        ld = max(len(cols), 2)
+        A = self.empty(max(len(rows), 1), ld)[:len(rows), :len(cols)]  # never a null pointer, even leading dimension
+        if len(rows) and len(cols):
+            _ops.gram_iso(descs, x.index_select(1, ri).contiguous(), x.index_select(1, ci).contiguous(), out=A)
+        return A
+
+    def diag(self, lay, A, d):
+        g = self._grid(lay)
+        self._ck(self.lib.lgp_dist_diag(self._sp(), ctypes.byref(g), self._p(A), A.stride(0), self._p(d)), 'lgp_dist_diag')
+
+    def scale_from_diag(self, lay, d):
+        s, sinv = self.empty(lay.npad), self.empty(lay.npad)
+        self._ck(self.lib.lgp_dist_scale_from_diag(self._sp(), self._p(d), lay.n, lay.npad, self._p(s), self._p(sinv)),
+                 'lgp_dist_scale_from_diag')
+        return s, sinv
+
+    def prepare(self, lay, A, sinv, rowsum):
+        g = self._grid(lay)
+        self._ck(self.lib.lgp_dist_prepare(self._sp(), ctypes.byref(g), self._p(A), A.stride(0), self._p(sinv),
+                                           self._p(rowsum)), 'lgp_dist_prepare')
+
+    def eps(self, lay, rowsum, epsrel, epsabs):
+        out = self.empty(2)
+        self._ck(self.lib.lgp_dist_eps(self._sp(), self._p(rowsum), lay.n, float(epsrel), float(epsabs), self._p(out)),
+                 'lgp_dist_eps')
+        return out
+
+    def add_diag(self, lay, A, eps):
+        g = self._grid(lay)
+        self._ck(self.lib.lgp_dist_add_diag(self._sp(), ctypes.byref(g), self._p(A), A.stride(0), self._p(eps)),
+                 'lgp_dist_add_diag')
+
+    # ---- factorisation tiles
+    def potrf_tile(self, tile, invd, dvec, info, j0):
+        T = tile.shape[0]
+        self._ck(self.lib.lgp_tile_potrf(self._sp(), self._p(tile), tile.stride(0), T, self._p(invd), self._p(dvec),
+                                         self._p(info), j0), 'lgp_tile_potrf')
+
+    def trsm_right(self, L, invd, B):
+        T = L.shape[0]
+        if B.shape[0] == 0:
+            return
+        self._ck(self.lib.lgp_tile_trsm_right(self._sp(), self._p(L), L.stride(0), self._p(invd), T, self._p(B),
+                                              B.stride(0), B.shape[0]), 'lgp_tile_trsm_right')
+
+    def copy2d(self, src, dst):
+        rows, cols = src.shape
+        if rows == 0:
+            return
+        self._ck(self.lib.lgp_copy2d(self._sp(), self._p(src), src.stride(0), self._p(dst), dst.stride(0), rows, cols),
+                 'lgp_copy2d')
+
+    def trailing_update(self, lay, A, k, panel, lj_begin, lj_end):
+        g = self._grid(lay)
+        arr = (ctypes.c_void_p * lay.Pr)(*[p.data_ptr() for p in panel])
+        self._ck(self.lib.lgp_dist_trailing_update(self._sp(), ctypes.byref(g), self._p(A), A.stride(0), k, arr,
+                                                   lj_begin, lj_end), 'lgp_dist_trailing_update')
+
+    # ---- solves
+    def trsv_tile(self, L, invd, b, trans):
+        T = L.shape[0]
+        self._ck(self.lib.lgp_tile_trsv(self._sp(), self._p(L), L.stride(0), self._p(invd), T, self._p(b),
+                                        int(bool(trans))), 'lgp_tile_trsv')
+
+    def gemv(self, P, x, y, alpha, trans):
+        """ y += alpha P x (trans False) or y += alpha P^T x """
+        rows, cols = P.shape
+        if rows == 0 or cols == 0:
+            return
+        self._ck(self.lib.lgp_dgemv(self._sp(), int(bool(trans)), self._p(P), P.stride(0), rows, cols, self._p(x),
+                                    self._p(y), float(alpha)), 'lgp_dgemv')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the distributed decomposition
+# ---------------------------------------------------------------------------------------------------------------
+
+class DistChol:
+    """Block-cyclic Cholesky of the Gram matrix of `descs` on the points `x`, sharded over the process group.
+
+    Semantics of lsqfitgp's `Chol(K, epsrel='auto', epsabs=0)` (src/lsqfitgp/_linalg/_decomp.py:380-393):
+    s_i = 2^rint(log2 K_ii / 2); Kt = K/s/s^T; eps = epsrel max_i sum_j |Kt_ij| + epsabs; Kt_ii += eps; Lt = chol(Kt);
+    L = diag(s) Lt.  `x` is the (ndim, n) float64 tensor of points, replicated on every rank; `descs` the kernel
+    descriptor list of `lgp_gram_iso` (see lsqfitgp_b200._Kernel.Kernel.descriptors()).
+
+    Methods (every rank gets the replicated result): `logdet()`, `solve(b)` = K^-1 b, `quad(b)` = b^T K^-1 b,
+    `pinv_correlate(b)` = L^-1 b, `minus_log_normal_density(r)` (value only), properties `n`, `eps`.
+    """
+
+    def __init__(self, descs, x, *, tile=512, grid=None, group=None, epsrel='auto', epsabs=0.0, ops=None,
+                 check=True, timers=None):
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.group = group
+        Pr, Pc = grid if grid is not None else default_grid(self.world)
+        if Pr * Pc != self.world:
+            raise ValueError(f'grid {Pr}x{Pc} does not match the {self.world} processes of the group')
+        n = x.shape[1]
+        self.lay = lay = Layout(n, tile, Pr, Pc, self.rank)
+        self.ops = ops if ops is not None else CudaTileOps(x.device)
+        ops = self.ops
+        self._timers = timers
+
+        # ---- Gram matrix, generated in place by the owner of each tile
+        self._mark('start')
+        self.A = A = ops.gram_local(descs, x, lay.global_rows(), lay.global_cols(), lay)
+        self._mark('gram')
+
+        # ---- equilibration and jitter
+        d = ops.zeros(lay.npad)
+        ops.diag(lay, A, d)
+        self._allreduce(d)
+        self.s, self.sinv = ops.scale_from_diag(lay, d)
+        rowsum = ops.zeros(lay.n)
+        ops.prepare(lay, A, self.sinv, rowsum)
+        self._allreduce(rowsum)
+        er = -1.0 if (isinstance(epsrel, str) and epsrel == 'auto') else float(epsrel)
+        ea = 2.220446049250313e-16 if (isinstance(epsabs, str) and epsabs == 'auto') else float(epsabs)
+        self._epsout = ops.eps(lay, rowsum, er, ea)
+        ops.add_diag(lay, A, self._epsout[1:2])
+        del d, rowsum
+        self._mark('prepare')
+
+        # ---- factorisation
+        self._factor()
+        self._mark('factor')
+        info = self.info.clone()
+        self._allreduce(info, op=dist.ReduceOp.MIN)
+        self._info = int(info.item())
+        if check and self._info != INT_MAX and self._info <= lay.n:
+            raise numpy.linalg.LinAlgError('cholesky decomposition not finite, probably matrix not pos def numerically')
+
+    # ---- collectives (no-ops in a single process)
+    def _mark(self, name):
+        if self._timers is not None:
+            self.ops.synchronize()
+            import time
+            self._timers.append((name, time.perf_counter()))
+
+    def _allreduce(self, t, op=None):
+        if self.world > 1:
+            dist.all_reduce(t, op=op if op is not None else dist.ReduceOp.SUM, group=self.group)
+
+    def _bcast(self, t, src):
+        if self.world > 1:
+            dist.broadcast(t, src=dist.get_global_rank(self.group, src) if self.group is not None else src,
+                           group=self.group)
+
+    # ---- right-looking factorisation with one-panel look-ahead
+    def _factor(self):
+        lay, ops, A = self.lay, self.ops, self.A
+        T, NT, Pr, Pc, pr, pc = lay.T, lay.NT, lay.Pr, lay.Pc, lay.pr, lay.pc
+        nb = T // 128
+        # diagonal tiles owned here: inverted 128x128 diagonal blocks kept for the solves
+        self._mydiag = {k: i for i, k in enumerate(k for k in range(NT) if lay.owner(k, k) == self.rank)}
+        self.invd = ops.empty(max(len(self._mydiag), 1), nb * 128 * 128)
+        self.dvec = ops.zeros(lay.npad)
+        self.info = ops.zeros(1, dtype=torch.int32)
+        self.info.fill_(INT_MAX)
+        TT = T * T
+        # double-buffered broadcast buffers: diagonal tile (+ inverted blocks) and one panel slab per process row
+        diagbuf = [ops.empty(TT + nb * 128 * 128) for _ in range(2)] if Pr > 1 else None
+        slab = [[ops.empty(max(lay.panel_count(0, r), 1) * TT) for r in range(Pr)] for _ in range(2)]
+        col_ready = {0: None}
+        buf_free = [None, None]
+        for k in range(NT):
+            prow, pcol = k % Pr, k % Pc
+            lkr, lkc = k // Pr, k // Pc
+            in_col = pc == pcol
+            own_diag = in_col and pr == prow
+            set_ = k % 2
+            li0 = lay.panel_first(k)
+            # ---------------- panel k (high-priority stream)
+            with ops.panel_stream():
+                if k == 0:
+                    ev0 = ops.event()  # the panel stream starts after the preparation passes on the main stream
+                    with ops.main_stream():
+                        ev0.record()
+                    ev0.wait()
+                if col_ready.get(k) is not None:
+                    col_ready[k].wait()
+                if buf_free[set_] is not None:
+                    buf_free[set_].wait()
+                Lkk = invd_k = None
+                if own_diag:
+                    tile = A[lkr * T:(lkr + 1) * T, lkc * T:(lkc + 1) * T]
+                    invd_k = self.invd[self._mydiag[k]]
+                    ops.potrf_tile(tile, invd_k, self.dvec, self.info, k * T)
+                    Lkk = tile
+                if Pr > 1 and any(lay.panel_count(k, r) for r in range(Pr)):
+                    # the other process rows of this process column need L_kk for their share of the TRSM
+                    db = diagbuf[set_]
+                    if own_diag:
+                        ops.copy2d(Lkk, db[:TT].view(T, T))
+                        db[TT:].copy_(invd_k)
+                    self._bcast(db, lay.rank_of(prow, pcol))
+                    Lkk, invd_k = db[:TT].view(T, T), db[TT:]
+                cnt = lay.panel_count(k)
+                if in_col and cnt > 0:
+                    ops.trsm_right(Lkk, invd_k, A[li0 * T:, lkc * T:(lkc + 1) * T])
+                for r in range(Pr):
+                    c_r = lay.panel_count(k, r)
+                    if c_r == 0:
+                        continue
+                    buf = slab[set_][r][:c_r * TT]
+                    if in_col and pr == r:
+                        ops.copy2d(A[li0 * T:, lkc * T:(lkc + 1) * T], buf.view(c_r * T, T))
+                    self._bcast(buf, lay.rank_of(r, pcol))
+                panel_done = ops.event()
+                panel_done.record()
+            # ---------------- trailing update k (main stream)
+            with ops.main_stream():
+                panel_done.wait()
+                if k + 1 < NT:
+                    panels = slab[set_]
+                    nxt_c = (k + 1) % Pc
+                    lj_next = (k + 1) // Pc
+                    if pc == nxt_c:
+                        # look-ahead: the next panel's tile column first, then release the panel stream
+                        ops.trailing_update(lay, A, k, panels, lj_next, lj_next + 1)
+                        ev = ops.event()
+                        ev.record()
+                        col_ready[k + 1] = ev
+                        ops.trailing_update(lay, A, k, panels, lj_next + 1, lay.LC)
+                    else:
+                        ops.trailing_update(lay, A, k, panels, 0, lay.LC)
+                ev = ops.event()
+                ev.record()
+                buf_free[set_] = ev
+            col_ready.pop(k, None)
+        with ops.main_stream():
+            for ev in buf_free:
+                if ev is not None:
+                    ev.wait()
+        self._allreduce(self.dvec)
+
+    # ---- results
+    @property
+    def n(self):
+        return self.lay.n
+
+    @property
+    def eps(self):
+        """ Chol.eps = eps * min s^2 (_decomp.py:393) """
+        return float(self._epsout[1].item()) * float(self.s[:self.lay.n].min().item()) ** 2
+
+    def logdet(self):
+        """ log det K = 2 sum_i log(Lt_ii s_i) """
+        n = self.lay.n
+        return 2.0 * float(torch.log(self.dvec[:n] * self.s[:n]).sum().item())
+
+    def _vec(self, b):
+        v = self.ops.zeros(self.lay.npad)
+        v[:self.lay.n] = torch.as_tensor(b, dtype=torch.float64).to(v.device).reshape(-1)
+        return v
+
+    def pinv_correlate(self, b, _padded=False):
+        """ L^-1 b (forward substitution), replicated; _decomp.py:437-439 """
+        lay, ops, A = self.lay, self.ops, self.A
+        T, NT, Pr, Pc, pr, pc = lay.T, lay.NT, lay.Pr, lay.Pc, lay.pr, lay.pc
+        z = self._vec(b) * self.sinv
+        acc = ops.zeros(max(lay.LR, 1) * T)
+        y = ops.zeros(lay.npad)
+        for k in range(NT):
+            prow, pcol = k % Pr, k % Pc
+            lkr, lkc = k // Pr, k // Pc
+            part = ops.zeros(T)
+            if pr == prow and k > 0:
+                part.copy_(acc[lkr * T:(lkr + 1) * T])
+            if k > 0:
+                self._allreduce(part)
+            yk = ops.zeros(T)
+            if lay.owner(k, k) == self.rank:
+                yk.copy_(z[k * T:(k + 1) * T] - part)
+                ops.trsv_tile(A[lkr * T:(lkr + 1) * T, lkc * T:(lkc + 1) * T], self.invd[self._mydiag[k]], yk, False)
+            self._bcast(yk, lay.owner(k, k))
+            y[k * T:(k + 1) * T] = yk
+            li0 = lay.panel_first(k)
+            if pc == pcol and lay.LR > li0:
+                ops.gemv(A[li0 * T:, lkc * T:(lkc + 1) * T], yk, acc[li0 * T:], 1.0, False)
+        return y if _padded else y[:lay.n]
+
+    def _back(self, y):
+        """ L^-T y for a padded, replicated y """
+        lay, ops, A = self.lay, self.ops, self.A
+        T, NT, Pr, Pc, pr, pc = lay.T, lay.NT, lay.Pr, lay.Pc, lay.pr, lay.pc
+        xloc = ops.zeros(max(lay.LR, 1) * T)
+        x = ops.zeros(lay.npad)
+        for k in range(NT - 1, -1, -1):
+            prow, pcol = k % Pr, k % Pc
+            lkr, lkc = k // Pr, k // Pc
+            part = ops.zeros(T)
+            li0 = lay.panel_first(k)
+            if k < NT - 1:
+                if pc == pcol and lay.LR > li0:
+                    ops.gemv(A[li0 * T:, lkc * T:(lkc + 1) * T], xloc[li0 * T:], part, 1.0, True)
+                self._allreduce(part)
+            xk = ops.zeros(T)
+            if lay.owner(k, k) == self.rank:
+                xk.copy_(y[k * T:(k + 1) * T] - part)
+                ops.trsv_tile(A[lkr * T:(lkr + 1) * T, lkc * T:(lkc + 1) * T], self.invd[self._mydiag[k]], xk, True)
+            self._bcast(xk, lay.owner(k, k))
+            x[k * T:(k + 1) * T] = xk
+            if pr == prow:
+                xloc[lkr * T:(lkr + 1) * T] = xk
+        return x * self.sinv
+
+    def solve(self, b):
+        """ K^-1 b = L^-T L^-1 b; Chol.ginv_linear for a vector, _decomp.py:398-403 """
+        return self._back(self.pinv_correlate(b, _padded=True))[:self.lay.n]
+
+    def quad(self, b):
+        """ b^T K^-1 b = |L^-1 b|^2; Chol.ginv_quad for a vector, _decomp.py:411-420 """
+        a = self.pinv_correlate(b)
+        return float((a * a).sum().item())
+
+    def minus_log_normal_density(self, r):
+        """ value of Chol.minus_log_normal_density (_decomp.py:484-488): (n log 2pi + log det K + r^T K^-1 r)/2 """
+        n = self.lay.n
+        return 0.5 * (n * math.log(2 * math.pi) + self.logdet() + self.quad(r))

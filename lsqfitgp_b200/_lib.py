@@ -44,6 +44,18 @@ class Factor(ctypes.Structure):
     ]
 
 
+class Grid(ctypes.Structure):
+    """ struct lgp_grid (include/lgp_b200.h) """
+    _fields_ = [
+        ('n', ctypes.c_int64),
+        ('tile', ctypes.c_int32),
+        ('nprow', ctypes.c_int32),
+        ('npcol', ctypes.c_int32),
+        ('prow', ctypes.c_int32),
+        ('pcol', ctypes.c_int32),
+    ]
+
+
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
 _int = ctypes.c_int
@@ -70,6 +82,18 @@ SIGNATURES = {
     'lgp_chol_get_factor': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64]),
     'lgp_chol_inverse': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64]),
     'lgp_chol_logdet_quad': (_int, [_vp, _vp, _i64, _vp, _vp]),
+    'lgp_dist_local_shape': (_int, [ctypes.POINTER(Grid), ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    'lgp_dist_diag': (_int, [_vp, ctypes.POINTER(Grid), _vp, _i64, _vp]),
+    'lgp_dist_scale_from_diag': (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    'lgp_dist_prepare': (_int, [_vp, ctypes.POINTER(Grid), _vp, _i64, _vp, _vp]),
+    'lgp_dist_eps': (_int, [_vp, _vp, _i64, _dbl, _dbl, _vp]),
+    'lgp_dist_add_diag': (_int, [_vp, ctypes.POINTER(Grid), _vp, _i64, _vp]),
+    'lgp_tile_potrf': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64]),
+    'lgp_tile_trsm_right': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64]),
+    'lgp_tile_trsv': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _int]),
+    'lgp_dist_trailing_update': (_int, [_vp, ctypes.POINTER(Grid), _vp, _i64, _i64, ctypes.POINTER(_vp), _i64, _i64]),
+    'lgp_dgemv': (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _vp, _dbl]),
+    'lgp_copy2d': (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64]),
 }
 
 _lib = None

@@ -378,6 +378,7 @@ struct CholCtx {
     double *dvec;
     int32_t *info;
     int rc;
+    int j0base = 0;  // global index of row 0 of W (tile-wise use: pivots and dvec are indexed globally)
 };
 
 #define RC(x)                   \
@@ -391,22 +392,29 @@ struct CholCtx {
 
 static inline double *Wp(const CholCtx &c, int rb, int cb) { return c.W + (int64_t)rb * NB * c.ldw + (int64_t)cb * NB; }
 
-// X * Lt[jb..jb+nb, jb..jb+nb]^T = B in place; B = W[rb.., jb..] with `rows` rows
-static void trsm_right_rec(CholCtx &c, int rb, int rows, int jb, int nb) {
+// X * Lt^T = B in place for the nb-block triangle Lt (pointer to its top-left, ld ldl; inverted 128x128 diagonal
+// blocks in invd); B points at the `rows` x nb*128 block to be solved (ld ldb)
+static void trsm_right_ptr(CholCtx &c, double *B, int64_t ldb, int rows, const double *Lt, int64_t ldl,
+                           const double *invd, int nb) {
     if (c.rc) return;
     if (nb == 1) {
-        double *B = Wp(c, rb, jb);
-        RC(gemm_launch(c.st, true, true, rows, NB, NB, 1.0, B, c.ldw, c.invd + (int64_t)jb * NB * NB, NB, B, c.ldw,
+        RC(gemm_launch(c.st, true, true, rows, NB, NB, 1.0, B, ldb, invd, NB, B, ldb,
                        GEMM_BETA0 | GEMM_B_LOWER_K | GEMM_INPLACE_A));
         return;
     }
     int n1 = nb / 2, n2 = nb - n1;
-    trsm_right_rec(c, rb, rows, jb, n1);
+    trsm_right_ptr(c, B, ldb, rows, Lt, ldl, invd, n1);
     if (c.rc) return;
     // B2 -= B1 * L21^T
-    RC(gemm_launch(c.st, true, true, rows, n2 * NB, n1 * NB, -1.0, Wp(c, rb, jb), c.ldw, Wp(c, jb + n1, jb), c.ldw,
-                   Wp(c, rb, jb + n1), c.ldw, 0));
-    trsm_right_rec(c, rb, rows, jb + n1, n2);
+    RC(gemm_launch(c.st, true, true, rows, n2 * NB, n1 * NB, -1.0, B, ldb, Lt + (int64_t)n1 * NB * ldl, ldl,
+                   B + (int64_t)n1 * NB, ldb, 0));
+    trsm_right_ptr(c, B + (int64_t)n1 * NB, ldb, rows, Lt + (int64_t)n1 * NB * ldl + (int64_t)n1 * NB, ldl,
+                   invd + (int64_t)n1 * NB * NB, n2);
+}
+
+// X * Lt[jb..jb+nb, jb..jb+nb]^T = B in place; B = W[rb.., jb..] with `rows` rows
+static void trsm_right_rec(CholCtx &c, int rb, int rows, int jb, int nb) {
+    trsm_right_ptr(c, Wp(c, rb, jb), c.ldw, rows, Wp(c, jb, jb), c.ldw, c.invd + (int64_t)jb * NB * NB, nb);
 }
 
 static void potrf_rec(CholCtx &c, int jb, int nb) {
@@ -414,7 +422,7 @@ static void potrf_rec(CholCtx &c, int jb, int nb) {
     if (nb == 1) {
         potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, c.st>>>(Wp(c, jb, jb), c.ldw,
                                                                       c.invd + (int64_t)jb * NB * NB, c.dvec, c.info,
-                                                                      jb * NB);
+                                                                      c.j0base + jb * NB);
         count_launch();
         if (cudaGetLastError() != cudaSuccess) c.rc = LGP_ERR_CUDA;
         return;
@@ -721,8 +729,10 @@ static int trsv_inplace(cudaStream_t st, const double *W, int64_t ldw, const dou
     if (!trans) {
         // L^-1 b = Lt^-1 (b / s): the scaling is applied when a block is first read.  Rows below the current
         // block are updated before they are scaled, so scale the whole vector first (one tiny pass).
-        vec_scale_store_kernel<<<(n + 255) / 256, 256, 0, st>>>(b, b, stride, n, sinv);
-        LGP_CUDA_CHECK_LAUNCH();
+        if (sinv) {
+            vec_scale_store_kernel<<<(n + 255) / 256, 256, 0, st>>>(b, b, stride, n, sinv);
+            LGP_CUDA_CHECK_LAUNCH();
+        }
         for (int jb = 0; jb < nblk; jb++) {
             const int j0 = jb * NB;
             trsv_diag_kernel<false><<<1, TRSV_DIAG_THREADS, 0, st>>>(invd + (int64_t)jb * NB * NB, b, stride, j0, n);
@@ -746,8 +756,10 @@ static int trsv_inplace(cudaStream_t st, const double *W, int64_t ldw, const dou
                 LGP_CUDA_CHECK_LAUNCH();
             }
         }
-        vec_scale_store_kernel<<<(n + 255) / 256, 256, 0, st>>>(b, b, stride, n, sinv);
-        LGP_CUDA_CHECK_LAUNCH();
+        if (sinv) {
+            vec_scale_store_kernel<<<(n + 255) / 256, 256, 0, st>>>(b, b, stride, n, sinv);
+            LGP_CUDA_CHECK_LAUNCH();
+        }
     }
     return LGP_OK;
 }
@@ -955,6 +967,45 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
         cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
     }
     return LGP_OK;
+}
+
+// ---- tile-level entry points: building blocks of the block-cyclic multi-GPU factorisation (lsqfitgp_b200/_dist.py)
+static int leaf_attr() {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES) !=
+            cudaSuccess)
+            return LGP_ERR_CUDA;
+        attr = true;
+    }
+    return LGP_OK;
+}
+
+int lgp_tile_potrf(lgp_stream_t stream, double *A, int64_t lda, int64_t t, double *invd, double *dvec, int32_t *info,
+                   int64_t j0) {
+    if (t < NB || t % NB || t > (1 << 20) || !A || !invd || !dvec || !info || j0 < 0) return LGP_ERR_BADARG;
+    if ((lda & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(invd) & 15))
+        return LGP_ERR_ALIGN;
+    if (leaf_attr()) return LGP_ERR_CUDA;
+    CholCtx c{(cudaStream_t)stream, A, lda, invd, dvec, info, LGP_OK};
+    c.j0base = (int)j0;
+    potrf_rec(c, 0, (int)(t / NB));
+    return c.rc;
+}
+
+int lgp_tile_trsm_right(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *B,
+                        int64_t ldb, int64_t rows) {
+    if (t < NB || t % NB || rows < 0 || rows > (1 << 30) || !L || !invd || !B) return LGP_ERR_BADARG;
+    if (rows == 0) return LGP_OK;
+    CholCtx c{(cudaStream_t)stream, nullptr, 0, nullptr, nullptr, nullptr, LGP_OK};
+    trsm_right_ptr(c, B, ldb, (int)rows, L, ldl, invd, (int)(t / NB));
+    return c.rc;
+}
+
+int lgp_tile_trsv(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *b,
+                  int trans) {
+    if (t < NB || t % NB || !L || !invd || !b) return LGP_ERR_BADARG;
+    return trsv_inplace((cudaStream_t)stream, L, ldl, invd, nullptr, (int)t, b, 1, trans);
 }
 
 int lgp_chol_logdet_quad(lgp_stream_t stream, const double *aux, int64_t n64, const double *a, double *out) {

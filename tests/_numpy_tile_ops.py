@@ -1,0 +1,145 @@
+"""NumPy provider of the tile operations of lsqfitgp_b200._dist.DistChol -- TEST INFRASTRUCTURE ONLY.
+
+It lets the CPU test tier run the real host orchestration (ownership maps, panel/trailing ordering, collectives)
+over gloo without a GPU.  The product provider is lsqfitgp_b200._dist.CudaTileOps (C ABI); nothing under
+lsqfitgp_b200/ imports this file.  Each method restates what the corresponding lgp_dist_*/lgp_tile_* entry point of
+include/lgp_b200.h computes.
+"""
+import contextlib
+
+import numpy as np
+import scipy.linalg
+import torch
+
+
+class _Ev:
+    def record(self):
+        pass
+
+    def wait(self):
+        pass
+
+
+class NumpyTileOps:
+    def __init__(self, K):
+        self.K = np.asarray(K, dtype=float)
+
+    def zeros(self, *shape, dtype=torch.float64):
+        return torch.zeros(*shape, dtype=dtype)
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.full(shape if not (len(shape) == 1 and isinstance(shape[0], tuple)) else shape[0], float('nan'),
+                          dtype=dtype) if dtype.is_floating_point else torch.zeros(*shape, dtype=dtype)
+
+    def main_stream(self):
+        return contextlib.nullcontext()
+
+    def panel_stream(self):
+        return contextlib.nullcontext()
+
+    def event(self):
+        return _Ev()
+
+    def synchronize(self):
+        pass
+
+    def gram_local(self, descs, x, rows, cols, lay):
+        n = lay.n
+        r = np.minimum(rows, n - 1)
+        c = np.minimum(cols, n - 1)
+        return torch.from_numpy(np.ascontiguousarray(self.K[np.ix_(r, c)]))
+
+    @staticmethod
+    def _owned_diag(lay):
+        i = np.arange(lay.n)
+        I = i // lay.T
+        m = (I % lay.Pr == lay.pr) & (I % lay.Pc == lay.pc)
+        i = i[m]
+        I = I[m]
+        return i, (I // lay.Pr) * lay.T + i % lay.T, (I // lay.Pc) * lay.T + i % lay.T
+
+    def diag(self, lay, A, d):
+        i, lr, lc = self._owned_diag(lay)
+        d.numpy()[i] = A.numpy()[lr, lc]
+
+    def scale_from_diag(self, lay, d):
+        dn = d.numpy()[:lay.n]
+        s = np.ones(lay.npad)
+        nz = dn != 0
+        s[:lay.n][nz] = np.exp2(np.rint(0.5 * np.log2(dn[nz])))
+        return torch.from_numpy(s), torch.from_numpy(1 / s)
+
+    def prepare(self, lay, A, sinv, rowsum):
+        a = A.numpy()
+        gi, gj = lay.global_rows(), lay.global_cols()
+        si = sinv.numpy()
+        a *= si[gi][:, None]
+        a *= si[gj][None, :]
+        pad = (gi[:, None] >= lay.n) | (gj[None, :] >= lay.n)
+        a[pad] = 0
+        a[(gi[:, None] == gj[None, :]) & pad] = 1
+        rs = np.abs(np.where(pad, 0, a)).sum(axis=1)
+        ok = gi < lay.n
+        rowsum.numpy()[gi[ok]] = rs[ok]
+
+    def eps(self, lay, rowsum, epsrel, epsabs):
+        if epsrel < 0:
+            epsrel = lay.n * np.finfo(float).eps
+        m = rowsum.numpy().max()
+        return torch.tensor([m, epsrel * m + epsabs])
+
+    def add_diag(self, lay, A, eps):
+        i, lr, lc = self._owned_diag(lay)
+        A.numpy()[lr, lc] += float(eps[0])
+
+    def potrf_tile(self, tile, invd, dvec, info, j0):
+        t = tile.numpy()
+        T = t.shape[0]
+        try:
+            L = np.linalg.cholesky(np.tril(t) + np.tril(t, -1).T)
+        except np.linalg.LinAlgError:
+            info[0] = min(int(info[0]), j0 + 1)
+            L = np.full_like(t, np.nan)
+        t[np.tril_indices(T)] = L[np.tril_indices(T)]
+        dvec.numpy()[j0:j0 + T] = np.diag(L)
+        iv = invd.numpy().reshape(T // 128, 128, 128)
+        for b in range(T // 128):
+            blk = L[128 * b:128 * (b + 1), 128 * b:128 * (b + 1)]
+            iv[b] = scipy.linalg.solve_triangular(blk, np.eye(128), lower=True) if np.isfinite(blk).all() else np.nan
+
+    def trsm_right(self, L, invd, B):
+        if B.shape[0] == 0:
+            return
+        b = B.numpy()
+        b[...] = scipy.linalg.solve_triangular(np.tril(L.numpy()), b.T, lower=True, check_finite=False).T
+
+    def copy2d(self, src, dst):
+        dst.copy_(src)
+
+    def trailing_update(self, lay, A, k, panel, lj_begin, lj_end):
+        from lsqfitgp_b200._dist import tiles_before
+        a = A.numpy()
+        T = lay.T
+        li0 = tiles_before(k + 1, lay.pr, lay.Pr)
+        for lj in range(max(lj_begin, 0), min(lj_end, lay.LC)):
+            J = lay.pc + lay.Pc * lj
+            if J <= k:
+                continue
+            li_s = tiles_before(J, lay.pr, lay.Pr)
+            if li_s >= lay.LR:
+                continue
+            rJ = J % lay.Pr
+            Aop = panel[lay.pr].numpy().reshape(-1, T)[(li_s - li0) * T:(lay.LR - li0) * T]
+            off = J // lay.Pr - tiles_before(k + 1, rJ, lay.Pr)
+            Bop = panel[rJ].numpy().reshape(-1, T)[off * T:(off + 1) * T]
+            a[li_s * T:, lj * T:(lj + 1) * T] -= Aop @ Bop.T
+
+    def trsv_tile(self, L, invd, b, trans):
+        bn = b.numpy()
+        bn[...] = scipy.linalg.solve_triangular(np.tril(L.numpy()), bn, lower=True, trans=1 if trans else 0, check_finite=False)
+
+    def gemv(self, P, x, y, alpha, trans):
+        if P.shape[0] == 0 or P.shape[1] == 0:
+            return
+        p = P.numpy()
+        y.numpy()[...] += alpha * ((p.T @ x.numpy()) if trans else (p @ x.numpy()))
