@@ -110,6 +110,64 @@ __device__ __forceinline__ void gemm_load_tile(uint32_t smem_tile, const double 
     }
 }
 
+// Loop-invariant form of gemm_load_tile for k-tiles that lie entirely inside [0, k_total): the source pointer of
+// this thread's first chunk is computed once and advanced by one k-tile per call, the row/column validity is folded
+// into a per-iteration byte count, and the shared-memory offsets of the ITERS chunks differ by compile-time constants.
+// (The generic loader costs ~25 integer instructions and two branches per 16-byte copy, which starved the DMMA pipe.)
+template <bool KMAJ, int ROWS, int THREADS>
+struct TileLoader {
+    static constexpr int CHUNKS = ROWS * GEMM_BK / 2;
+    static constexpr int ITERS = CHUNKS / THREADS;
+    static constexpr int ROWS_PER_IT = KMAJ ? THREADS / 8 : THREADS / (ROWS / 2);  // tile rows (k-major) / k-rows per iter
+    static_assert(CHUNKS % THREADS == 0, "tile chunks must divide evenly among threads");
+    static_assert(!KMAJ || (ROWS_PER_IT % 2 == 0), "swizzle parity must not change between iterations");
+    const char *src;     // global address of chunk 0 of the next k-tile
+    int64_t it_stride;   // bytes between the chunks of consecutive iterations
+    int64_t kt_stride;   // bytes between consecutive k-tiles
+    uint32_t dst;        // shared-memory offset of chunk 0 inside a stage tile
+    uint32_t bytes;      // 4 bits per iteration: valid bytes / 4 (0, 2 or 4); a zero-size copy reads nothing, so
+                         // the addresses of out-of-range rows are never dereferenced
+
+    __device__ __forceinline__ void init(const double *__restrict__ G, int64_t ld, int r0, int rows_total, int k0,
+                                         int tid) {
+        bytes = 0;
+        if (KMAJ) {
+            const int row = tid >> 3, c = tid & 7;
+            dst = row * 128 + ((c ^ ((row & 1) << 2)) << 4);
+            int gr = r0 + row;
+            src = reinterpret_cast<const char *>(G + (int64_t)min(gr, rows_total - 1) * ld + k0 + 2 * c);
+            it_stride = (int64_t)ROWS_PER_IT * ld * 8;
+            kt_stride = GEMM_BK * 8;
+#pragma unroll
+            for (int it = 0; it < ITERS; it++) {
+                int g = gr + it * ROWS_PER_IT;
+                bytes |= (g < rows_total ? 4u : 0u) << (4 * it);
+            }
+        } else {
+            constexpr int CPR = ROWS / 2;
+            const int krow = tid / CPR, c = tid % CPR;
+            dst = krow * ((ROWS + 2) * 8) + c * 16;
+            const int gr = r0 + 2 * c;
+            const int rem = rows_total - gr;
+            const uint32_t b = rem >= 2 ? 4u : (rem == 1 ? 2u : 0u);
+            src = reinterpret_cast<const char *>(G + (int64_t)(k0 + krow) * ld + (b ? gr : 0));
+            it_stride = (int64_t)ROWS_PER_IT * ld * 8;
+            kt_stride = (int64_t)GEMM_BK * ld * 8;
+#pragma unroll
+            for (int it = 0; it < ITERS; it++) bytes |= b << (4 * it);
+        }
+    }
+    __device__ __forceinline__ void load(uint32_t smem_tile) {
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) {
+            constexpr int DST_STRIDE = KMAJ ? ROWS_PER_IT * 128 : ROWS_PER_IT * ((ROWS + 2) * 8);
+            cp_async16(smem_tile + dst + it * DST_STRIDE, src + it * it_stride, ((bytes >> (4 * it)) & 15u) << 2);
+        }
+        src += kt_stride;
+    }
+    __device__ __forceinline__ void skip() { src += kt_stride; }
+};
+
 // Fragment for MMA slot q (= lane%4) within 8-k group g: k = 8g + 2q + t, t in {0,1}.
 template <bool KMAJ, int ROWS>
 __device__ __forceinline__ void gemm_load_frag(const unsigned char *tile, int row, int g, int q, double &v0,
@@ -169,34 +227,37 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS) gemm_dmma_kernel
 #pragma unroll
         for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // k-tiles [0, KT_full) lie entirely inside [k_begin, k_end): loop-invariant loaders; a partial last tile (K not
+    // a multiple of 16) goes through the generic loader
+    const int KT_full = (k_end - k_begin) / GEMM_BK < KT ? (k_end - k_begin) / GEMM_BK : KT;
+    TileLoader<A_KMAJ, BM, Cfg::THREADS> la;
+    TileLoader<B_KMAJ, BN, Cfg::THREADS> lb;
+    la.init(p.A, p.lda, m0, p.M, k_begin, tid);
+    lb.init(p.B, p.ldb, n0, p.N, k_begin, tid);
+    auto load_stage = [&](int nk) {
+        const uint32_t sa = smem_base + (nk % STAGES) * Cfg::STAGE_BYTES;
+        if (nk < KT_full) {
+            la.load(sa);
+            lb.load(sa + Cfg::A_BYTES);
+        } else if (nk < KT) {
+            int k0 = k_begin + nk * GEMM_BK;
+            gemm_load_tile<A_KMAJ, BM, Cfg::THREADS>(sa, p.A, p.lda, m0, p.M, k0, k_end, tid);
+            gemm_load_tile<B_KMAJ, BN, Cfg::THREADS>(sa + Cfg::A_BYTES, p.B, p.ldb, n0, p.N, k0, k_end, tid);
+        }
+    };
+
     // prologue
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-        if (s < KT) {
-            int k0 = k_begin + s * GEMM_BK;
-            gemm_load_tile<A_KMAJ, BM, Cfg::THREADS>(smem_base + s * Cfg::STAGE_BYTES, p.A, p.lda, m0, p.M, k0, k_end,
-                                                     tid);
-            gemm_load_tile<B_KMAJ, BN, Cfg::THREADS>(smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, p.B, p.ldb, n0,
-                                                     p.N, k0, k_end, tid);
-        }
+        load_stage(s);
         cp_async_commit();
     }
 
     for (int kt = 0; kt < KT; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            int nk = kt + STAGES - 1;
-            if (nk < KT) {
-                int s = nk % STAGES;
-                int k0 = k_begin + nk * GEMM_BK;
-                gemm_load_tile<A_KMAJ, BM, Cfg::THREADS>(smem_base + s * Cfg::STAGE_BYTES, p.A, p.lda, m0, p.M, k0,
-                                                         k_end, tid);
-                gemm_load_tile<B_KMAJ, BN, Cfg::THREADS>(smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, p.B, p.ldb,
-                                                         n0, p.N, k0, k_end, tid);
-            }
-            cp_async_commit();
-        }
+        load_stage(kt + STAGES - 1);
+        cp_async_commit();
         const int s = kt % STAGES;
         const unsigned char *at = smem + s * Cfg::STAGE_BYTES;
         const unsigned char *bt = at + Cfg::A_BYTES;

@@ -70,6 +70,6 @@ def _torchrun(nproc, *args, timeout=600):
 def test_distchol_multi_rank_vs_oracle(nproc, grid):
     if torch.cuda.device_count() < nproc:
         pytest.skip(f'needs {nproc} GPUs')
-    res = _torchrun(nproc, '--n', '3000', '--tile', '256', '--grid', grid, '--oracle')
+    res = _torchrun(nproc, '--size', '3000', '--tile', '256', '--grid', grid, '--oracle')
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert 'DIST_CHECK_OK' in res.stdout

@@ -1,8 +1,8 @@
 """torchrun entry: block-cyclic Cholesky on N GPUs (NCCL), checked against the oracle (small n) and/or through
 size-independent properties (residual |Kx - b|/|b| with K regenerated slab-wise on the fly), with timings.
 
-    torchrun --nproc-per-node N tools/dist_check.py --n 3000 --tile 256 --grid 2x1 --oracle
-    torchrun --nproc-per-node 8 tools/dist_check.py --n 150000 --tile 512
+    torchrun --nproc-per-node N tools/dist_check.py --size 3000 --tile 256 --grid 2x1 --oracle
+    torchrun --nproc-per-node 8 tools/dist_check.py --size 150000 --tile 512
 """
 import argparse
 import json
@@ -20,7 +20,7 @@ from lsqfitgp_b200 import _lib, _ops, _dist  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=3000)
+    ap.add_argument('--size', dest='n', type=int, default=3000)
     ap.add_argument('--tile', type=int, default=512)
     ap.add_argument('--grid', default=None)
     ap.add_argument('--oracle', action='store_true')
