@@ -81,14 +81,16 @@ def main():
     t_solve = time.perf_counter() - t0
     logdet = dc.logdet()
 
-    # residual |K x - b| / |b| with K regenerated slab-wise (rows sharded over ranks); checker code, not product
+    # residual |(K + jitter) x - b| / |b| with K regenerated slab-wise (rows sharded over ranks); checker code, not product
     rows = np.array_split(np.arange(n), world)[rank]
     res2 = torch.zeros(1, dtype=torch.float64, device=dev)
     slab = 2048
+    epsj = float(dc._epsout[1].item())
     for r0 in range(0, len(rows), slab):
         idx = torch.as_tensor(rows[r0:r0 + slab], device=dev)
         Ks = _ops.gram_iso(descs, x.index_select(1, idx).contiguous(), x)
-        r = Ks @ sol - bd[idx]
+        # the factor is that of K + eps*diag(s^2) (Chol.__init__ jitter, reference _decomp.py:384-387)
+        r = Ks @ sol + epsj * (dc.s[idx] ** 2) * sol[idx] - bd[idx]
         res2 += (r * r).sum()
     if world > 1:
         dist.all_reduce(res2)
