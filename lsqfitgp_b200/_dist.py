@@ -198,6 +198,11 @@ class CudaTileOps:
     def synchronize(self):
         torch.cuda.synchronize(self.device)
 
+    def timing_event(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(self.main)
+        return ev
+
     def _grid(self, lay):
         g = self._libmod.Grid()
         g.n, g.tile, g.nprow, g.npcol, g.prow, g.pcol = lay.n, lay.T, lay.Pr, lay.Pc, lay.pr, lay.pc
@@ -344,8 +349,11 @@ class DistChol:
         del d, rowsum
         self._mark('prepare')
 
-        # ---- factorisation
+        # ---- factorisation (device-timed on the main stream, which joins the panel stream at the end)
+        t0 = ops.timing_event() if hasattr(ops, 'timing_event') else None
         self._factor()
+        t1 = ops.timing_event() if hasattr(ops, 'timing_event') else None
+        self._factor_events = (t0, t1)
         self._mark('factor')
         info = self.info.clone()
         self._allreduce(info, op=dist.ReduceOp.MIN)
@@ -456,6 +464,14 @@ class DistChol:
                 if ev is not None:
                     ev.wait()
         self._allreduce(self.dvec)
+
+    def factor_ms(self):
+        """ device time of the factorisation loop on this rank (CUDA events on the main stream), or None """
+        t0, t1 = self._factor_events
+        if t0 is None:
+            return None
+        t1.synchronize()
+        return t0.elapsed_time(t1)
 
     # ---- results
     @property
