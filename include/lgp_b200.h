@@ -75,6 +75,7 @@ typedef struct lgp_factor {
  * flags: LGP_GRAM_SYMMETRIC asserts x==y (same pointer): lower tiles are evaluated once and mirrored. */
 #define LGP_GRAM_SYMMETRIC 1
 #define LGP_GRAM_GENERAL 2 /* force the general (sum-of-products) kernel even when the fast path applies */
+#define LGP_GRAM_LIBM 4    /* fast path with CUDA libm exp/sqrt instead of the short in-kernel versions (A/B checks) */
 int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
                  int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, double *K_out, int64_t ldk,
                  int flags);

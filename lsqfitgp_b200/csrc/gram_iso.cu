@@ -11,6 +11,7 @@
 
 #include "../../include/lgp_b200.h"
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace lgp {
 
@@ -507,6 +508,156 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_kernel(const __grid_co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Specialised fast path (ExpQuad, and Matern with nu = P + 1/2, P <= 3): same tiling and the same r2 arithmetic as
+// gram_fast_kernel, but the core is evaluated with the short exp/sqrt of fastmath.cuh (11 + 7 DP instructions instead of
+// libm's ~40 with slow-path calls), the Horner recurrence is unrolled at compile time, and the White term is only
+// examined where r2 == 0.  With symmetry this brings the build from the FP64-ALU bound towards the HBM write bound
+// (DESIGN.md section 3).  Error of the core <= 1 ulp (tests/test_fastmath_cpu.py); sqrt is correctly rounded.
+// ------------------------------------------------------------------------------------------------
+template <int KIND, int P>
+__device__ __forceinline__ double fast2_core(double r2, double nu2, double par0, double c0, double c1, double c2,
+                                             const ExpTab *tab) {
+    if (KIND == LGP_K_EXPQUAD) return fm_exp_neg(__dmul_rn(-0.5, r2), tab);
+    // Maternp: x = sqrt((2p+1) r2 + par0); exp(-x) * poly_p(2x)   (_matern.py:48-49, _bessel.py:103-110)
+    const double z = __dadd_rn(__dmul_rn(nu2, r2), par0);
+    const double x = fm_sqrt(z);
+    const double ex = fm_exp_neg(-x, tab);
+    if (P == 0) return ex;
+    // Horner in the reference's order poly = 1 + ((poly*c_k)*2)*x, the last product-sum fused
+    double poly = 1.0;
+    if (P >= 3) poly = __fma_rn(c2, x, 1.0);                       // c_k here = 2*coef_k (exact doubling)
+    if (P >= 2) poly = __fma_rn(__dmul_rn(poly, c1), x, 1.0);
+    poly = __fma_rn(__dmul_rn(poly, c0), x, 1.0);
+    return __dmul_rn(ex, poly);
+}
+
+template <int KIND, int P, bool SYM>
+__global__ void __launch_bounds__(G_THREADS, 2) gram_fast2_kernel(const __grid_constant__ FastDesc d,
+                                                                  const double *__restrict__ x, int64_t ldx, int64_t n,
+                                                                  const double *__restrict__ y, int64_t ldy, int64_t m,
+                                                                  double *__restrict__ K, int64_t ldk, int vec_ok,
+                                                                  int tiles_n) {
+    extern __shared__ __align__(16) double fsm[];
+    // layout: exp table (64 x 16 B), su[nd][64], sv[nd][64], raw copies ru, rv (White with a rescaled main factor),
+    // transpose buffer T[64][65] in symmetric mode
+    const int nd = d.nd;
+    ExpTab *tab = reinterpret_cast<ExpTab *>(fsm);
+    double *su = fsm + 128, *sv = su + nd * FT;
+    double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
+    double *T = rv + (d.white_raw ? nd * FT : 0);
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    int tm, tn;
+    if (SYM) {
+        long long b = blockIdx.x;
+        tm = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+        while ((long long)(tm + 1) * (tm + 2) / 2 <= b) tm++;
+        while ((long long)tm * (tm + 1) / 2 > b) tm--;
+        tn = (int)(b - (long long)tm * (tm + 1) / 2);
+    } else {
+        tm = blockIdx.x / tiles_n;
+        tn = blockIdx.x % tiles_n;
+    }
+    const int64_t i0 = (int64_t)tm * FT, j0 = (int64_t)tn * FT;
+    if (tid < 64) tab[tid] = EXP_TAB_DEV[tid];
+    for (int idx = tid; idx < nd * FT; idx += G_THREADS) {
+        const int s = idx / FT, r = idx % FT;
+        const int64_t i = i0 + r, j = j0 + r;
+        double xr = (i < n) ? x[(int64_t)d.dims[s] * ldx + i] : 0.0;
+        double yr = (j < m) ? y[(int64_t)d.dims[s] * ldy + j] : 0.0;
+        su[idx] = __ddiv_rn(__dsub_rn(xr, d.loc), d.scale);
+        sv[idx] = __ddiv_rn(__dsub_rn(yr, d.loc), d.scale);
+        if (d.white_raw) {
+            ru[idx] = xr;
+            rv[idx] = yr;
+        }
+    }
+    __syncthreads();
+
+    double r2[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) r2[a][c] = 0.0;
+    for (int s = 0; s < nd; s++) {
+        double uu[4], vv[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) uu[a] = su[s * FT + ty + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            double2 t = *reinterpret_cast<const double2 *>(&sv[s * FT + 2 * tx + 32 * b]);
+            vv[2 * b] = t.x;
+            vv[2 * b + 1] = t.y;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double df = __dsub_rn(uu[a], vv[c]);
+                r2[a][c] = __dadd_rn(r2[a][c], __dmul_rn(df, df));
+            }
+    }
+    const double nu2 = (double)(2 * P + 1), par0 = d.par0, amp = d.amp;
+    const double c0 = 2.0 * d.coef[0], c1 = 2.0 * d.coef[1], c2 = 2.0 * d.coef[2];
+    const double *wu = d.white_raw ? ru : su, *wv = d.white_raw ? rv : sv;
+    double val[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            double v = __dmul_rn(amp, fast2_core<KIND, P>(r2[a][c], nu2, par0, c0, c1, c2, tab));
+            if (d.has_white) {
+                double w = 0.0;
+                if (r2[a][c] == 0.0) {  // necessary for equal coordinates; rare off the diagonal
+                    bool eq = true;
+                    const int col = 2 * tx + 32 * (c >> 1) + (c & 1);
+                    for (int s = 0; s < nd; s++) eq = eq && (wu[s * FT + ty + 16 * a] == wv[s * FT + col]);
+                    if (eq) w = d.amp_white;
+                }
+                v = __dadd_rn(v, w);
+            }
+            if (d.has_const) v = __dadd_rn(v, d.amp_const);
+            val[a][c] = v;
+        }
+    // direct tile
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        int64_t i = i0 + ty + 16 * a;
+        if (i >= n) continue;
+        double *krow = K + i * ldk;
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            int64_t j = j0 + 2 * tx + 32 * b;
+            if (j >= m) continue;
+            if (vec_ok && j + 1 < m) {
+                *reinterpret_cast<double2 *>(krow + j) = make_double2(val[a][2 * b], val[a][2 * b + 1]);
+            } else {
+                krow[j] = val[a][2 * b];
+                if (j + 1 < m) krow[j + 1] = val[a][2 * b + 1];
+            }
+        }
+    }
+    if (SYM && tm != tn) {
+        // mirrored tile: K[j][i] = K[i][j]
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) T[(2 * tx + 32 * (c >> 1) + (c & 1)) * (FT + 1) + ty + 16 * a] = val[a][c];
+        __syncthreads();
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int rr = warp; rr < FT; rr += G_THREADS / 32) {
+            int64_t j = j0 + rr;  // row of the mirrored tile
+            if (j >= m) break;
+            double *krow = K + j * ldk + i0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int cidx = lane + 32 * h;
+                if (i0 + cidx < n) krow[cidx] = T[rr * (FT + 1) + cidx];
+            }
+        }
+    }
+}
+
 // d core / d r2 for the fast path (value returned through `val`)
 template <int KIND>
 __device__ __forceinline__ void fast_core_derivs(const FastDesc &d, double r2, double &val, double &dr2,
@@ -768,6 +919,29 @@ static int launch_fast(cudaStream_t st, const FastDesc &d, const double *x, int6
     return LGP_OK;
 }
 
+template <int KIND, int P>
+static int launch_fast2(cudaStream_t st, const FastDesc &d, const double *x, int64_t ldx, int64_t n, const double *y,
+                        int64_t ldy, int64_t m, double *K, int64_t ldk, bool sym) {
+    size_t smem = 1024 + (size_t)(2 + (d.white_raw ? 2 : 0)) * d.nd * FT * sizeof(double) + (sym ? FT * (FT + 1) * 8 : 0);
+    int64_t tm = (n + FT - 1) / FT, tn = (m + FT - 1) / FT;
+    int64_t grid = sym ? tm * (tm + 1) / 2 : tm * tn;
+    if (grid > 2147483647LL) return LGP_ERR_UNSUPPORTED;
+    int vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+    if (sym) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(gram_fast2_kernel<KIND, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gram_fast2_kernel<KIND, P, true><<<(unsigned)grid, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, K, ldk,
+                                                                                 vec_ok, (int)tn);
+    } else {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(gram_fast2_kernel<KIND, P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gram_fast2_kernel<KIND, P, false><<<(unsigned)grid, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, K, ldk,
+                                                                                  vec_ok, (int)tn);
+    }
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
 __global__ void zero_kernel(double *p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0.0;
@@ -792,6 +966,18 @@ int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors,
         if (build_fast(factors, nfactors, ndim, fd)) {
             const bool sym = (flags & LGP_GRAM_SYMMETRIC) && x == y && n == m && ldx == ldy;
             cudaStream_t st = (cudaStream_t)stream;
+            if (!(flags & LGP_GRAM_LIBM)) {
+                if (fd.kind == LGP_K_EXPQUAD)
+                    return launch_fast2<LGP_K_EXPQUAD, 0>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
+                if (fd.kind == LGP_K_MATERNP && fd.p == 0)
+                    return launch_fast2<LGP_K_MATERNP, 0>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
+                if (fd.kind == LGP_K_MATERNP && fd.p == 1)
+                    return launch_fast2<LGP_K_MATERNP, 1>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
+                if (fd.kind == LGP_K_MATERNP && fd.p == 2)
+                    return launch_fast2<LGP_K_MATERNP, 2>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
+                if (fd.kind == LGP_K_MATERNP && fd.p == 3)
+                    return launch_fast2<LGP_K_MATERNP, 3>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
+            }
             if (fd.kind == LGP_K_EXPQUAD) return launch_fast<LGP_K_EXPQUAD>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
             if (fd.kind == LGP_K_MATERNP) return launch_fast<LGP_K_MATERNP>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
             return launch_fast<LGP_K_CAUCHY>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);

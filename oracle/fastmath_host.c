@@ -1,0 +1,22 @@
+/* TEST INFRASTRUCTURE: host build of lsqfitgp_b200/csrc/fastmath.cuh (the short exp/sqrt of the Gram kernels) so that
+ * tests/test_fastmath_cpu.py can measure their error against glibc without a GPU.  Compiled as C++ by oracle/Makefile
+ * (g++ -x c++).  The hardware reciprocal-square-root estimate (MUFU.RSQ64H: upper 32 input bits, ~2^-21 relative) is
+ * emulated by truncating the argument and the result to 20 mantissa bits. */
+#include "../lsqfitgp_b200/csrc/fastmath.cuh"
+
+static double trunc20(double v) {
+    uint64_t u = lgp::fm_to_bits(v) & ~((1ull << 32) - 1);
+    return lgp::fm_from_bits(u);
+}
+
+extern "C" {
+void lgp_host_exp_neg(const double *a, double *out, long n) {
+    for (long i = 0; i < n; i++) out[i] = lgp::fm_exp_neg(a[i], lgp::EXP_TAB_HOST);
+}
+void lgp_host_sqrt(const double *z, double *out, long n) {
+    for (long i = 0; i < n; i++) {
+        double y0 = trunc20(1.0 / sqrt(trunc20(z[i])));
+        out[i] = lgp::fm_sqrt_from_rsqrt(z[i], y0);
+    }
+}
+}
