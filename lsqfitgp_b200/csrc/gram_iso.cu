@@ -515,14 +515,16 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_kernel(const __grid_co
 // examined where r2 == 0.  With symmetry this brings the build from the FP64-ALU bound towards the HBM write bound
 // (DESIGN.md section 3).  Error of the core <= 1 ulp (tests/test_fastmath_cpu.py); sqrt is correctly rounded.
 // ------------------------------------------------------------------------------------------------
+// Hot path: no branches, no range checks: the caller tracks the smallest and largest r2 of the thread (as unsigned high
+// words, which order like the non-negative doubles) and redoes out-of-range entries on the slow path.
 template <int KIND, int P>
 __device__ __forceinline__ double fast2_core(double r2, double nu2, double par0, double c0, double c1, double c2,
                                              const ExpTab *tab) {
-    if (KIND == LGP_K_EXPQUAD) return fm_exp_neg(__dmul_rn(-0.5, r2), tab);
+    if (KIND == LGP_K_EXPQUAD) return fm_exp_neg_fast(__dmul_rn(-0.5, r2), tab);
     // Maternp: x = sqrt((2p+1) r2 + par0); exp(-x) * poly_p(2x)   (_matern.py:48-49, _bessel.py:103-110)
     const double z = __dadd_rn(__dmul_rn(nu2, r2), par0);
-    const double x = fm_sqrt(z);
-    const double ex = fm_exp_neg(-x, tab);
+    const double x = fm_sqrt_fast(z);
+    const double ex = fm_exp_neg_fast(-x, tab);
     if (P == 0) return ex;
     // Horner in the reference's order poly = 1 + ((poly*c_k)*2)*x, the last product-sum fused
     double poly = 1.0;
@@ -532,8 +534,34 @@ __device__ __forceinline__ double fast2_core(double r2, double nu2, double par0,
     return __dmul_rn(ex, poly);
 }
 
+// Is r2 outside the range where fast2_core is valid (or does it need the White comparison)?
+//   ExpQuad: exp(-r2/2) leaves the normal range beyond r2 = 1416; r2 < 2^-1022 (high word 0, includes r2 == 0) matters
+//            only for White but is always sent to the slow path.
+//   Maternp: 2^-960 <= z = (2p+1) r2 + par0 <= 501264 (x <= 708; the lower end keeps the reciprocal-square-root estimate
+//            in range and catches z == 0); with a White term also r2 == 0.
+template <int KIND>
+__device__ __forceinline__ bool fast2_out_of_range(double r2, double nu2, double par0, bool white) {
+    const unsigned hr = (unsigned)__double2hiint(r2);
+    if (KIND == LGP_K_EXPQUAD) return (hr - 1u) > (0x40962000u - 1u);
+    const unsigned hz = (unsigned)__double2hiint(__dadd_rn(__dmul_rn(nu2, r2), par0));
+    return ((hz - 0x03f00000u) > (0x411e9840u - 0x03f00000u)) || (white && hr == 0u);
+}
+
+// Slow path for one entry (rare: diagonal, duplicated points, underflowing tails): libm core + White comparison
+template <int KIND>
+__device__ __noinline__ double fast2_slow_entry(const FastDesc &d, double r2, const double *wu, const double *wv,
+                                                int row, int col) {
+    double v = __dmul_rn(d.amp, fast_core<KIND>(d, r2));
+    if (d.has_white) {
+        bool eq = (r2 == 0.0);
+        for (int s = 0; s < d.nd && eq; s++) eq = (wu[s * FT + row] == wv[s * FT + col]);
+        v = __dadd_rn(v, eq ? d.amp_white : 0.0);
+    }
+    return v;
+}
+
 template <int KIND, int P, bool SYM>
-__global__ void __launch_bounds__(G_THREADS, 2) gram_fast2_kernel(const __grid_constant__ FastDesc d,
+__global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_constant__ FastDesc d,
                                                                   const double *__restrict__ x, int64_t ldx, int64_t n,
                                                                   const double *__restrict__ y, int64_t ldy, int64_t m,
                                                                   double *__restrict__ K, int64_t ldk, int vec_ok,
@@ -550,7 +578,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast2_kernel(const __grid_c
     int tm, tn;
     if (SYM) {
         long long b = blockIdx.x;
-        tm = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+        tm = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);  // single precision + exact integer fix-up
         while ((long long)(tm + 1) * (tm + 2) / 2 <= b) tm++;
         while ((long long)tm * (tm + 1) / 2 > b) tm--;
         tn = (int)(b - (long long)tm * (tm + 1) / 2);
@@ -574,75 +602,97 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast2_kernel(const __grid_c
     }
     __syncthreads();
 
-    double r2[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) r2[a][c] = 0.0;
-    for (int s = 0; s < nd; s++) {
-        double uu[4], vv[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) uu[a] = su[s * FT + ty + 16 * a];
-#pragma unroll
-        for (int b = 0; b < 2; b++) {
-            double2 t = *reinterpret_cast<const double2 *>(&sv[s * FT + 2 * tx + 32 * b]);
-            vv[2 * b] = t.x;
-            vv[2 * b + 1] = t.y;
-        }
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                double df = __dsub_rn(uu[a], vv[c]);
-                r2[a][c] = __dadd_rn(r2[a][c], __dmul_rn(df, df));
-            }
-    }
     const double nu2 = (double)(2 * P + 1), par0 = d.par0, amp = d.amp;
     const double c0 = 2.0 * d.coef[0], c1 = 2.0 * d.coef[1], c2 = 2.0 * d.coef[2];
     const double *wu = d.white_raw ? ru : su, *wv = d.white_raw ? rv : sv;
-    double val[4][4];
+    const bool white = d.has_white != 0;
+    const bool mirror = SYM && tm != tn;
+
+    // The 4 x 4 entries of a thread are produced in two batches of 2 rows x 4 columns: half the live registers of a
+    // full 16-entry batch (3 CTAs per SM without spills), still 8 independent dependency chains per thread.
+#pragma unroll 1
+    for (int a0 = 0; a0 < 4; a0 += 2) {
+        double r2[2][4];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+        for (int a = 0; a < 2; a++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            double v = __dmul_rn(amp, fast2_core<KIND, P>(r2[a][c], nu2, par0, c0, c1, c2, tab));
-            if (d.has_white) {
-                double w = 0.0;
-                if (r2[a][c] == 0.0) {  // necessary for equal coordinates; rare off the diagonal
-                    bool eq = true;
-                    const int col = 2 * tx + 32 * (c >> 1) + (c & 1);
-                    for (int s = 0; s < nd; s++) eq = eq && (wu[s * FT + ty + 16 * a] == wv[s * FT + col]);
-                    if (eq) w = d.amp_white;
+            for (int c = 0; c < 4; c++) r2[a][c] = 0.0;
+        for (int s = 0; s < nd; s++) {
+            double uu[2], vv[4];
+#pragma unroll
+            for (int a = 0; a < 2; a++) uu[a] = su[s * FT + ty + 16 * (a0 + a)];
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                double2 t = *reinterpret_cast<const double2 *>(&sv[s * FT + 2 * tx + 32 * b]);
+                vv[2 * b] = t.x;
+                vv[2 * b + 1] = t.y;
+            }
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    double df = __dsub_rn(uu[a], vv[c]);
+                    r2[a][c] = __dadd_rn(r2[a][c], __dmul_rn(df, df));
                 }
-                v = __dadd_rn(v, w);
-            }
-            if (d.has_const) v = __dadd_rn(v, d.amp_const);
-            val[a][c] = v;
         }
-    // direct tile
+        double val[2][4];
+        unsigned hmin = 0xffffffffu, hmax = 0u;  // high words of the smallest / largest r2 (monotone for r2 >= 0)
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-        int64_t i = i0 + ty + 16 * a;
-        if (i >= n) continue;
-        double *krow = K + i * ldk;
+        for (int a = 0; a < 2; a++)
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
-            int64_t j = j0 + 2 * tx + 32 * b;
-            if (j >= m) continue;
-            if (vec_ok && j + 1 < m) {
-                *reinterpret_cast<double2 *>(krow + j) = make_double2(val[a][2 * b], val[a][2 * b + 1]);
-            } else {
-                krow[j] = val[a][2 * b];
-                if (j + 1 < m) krow[j + 1] = val[a][2 * b + 1];
+            for (int c = 0; c < 4; c++) {
+                const unsigned hr = (unsigned)__double2hiint(r2[a][c]);
+                hmin = min(hmin, hr);
+                hmax = max(hmax, hr);
+                val[a][c] = __dmul_rn(amp, fast2_core<KIND, P>(r2[a][c], nu2, par0, c0, c1, c2, tab));
             }
+        // the range test is monotone in r2: test the two extremes (the high word rounds r2 down, which only makes the
+        // test stricter at the low end; at the high end the bounds are far inside the true limits)
+        if (fast2_out_of_range<KIND>(__hiloint2double((int)hmin, 0), nu2, par0, white) ||
+            fast2_out_of_range<KIND>(__hiloint2double((int)hmax, 0xffffffff), nu2, par0, white)) {
+            // some entry of this thread left the fast range: redo exactly those with the library path
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (fast2_out_of_range<KIND>(r2[a][c], nu2, par0, white))
+                        val[a][c] = fast2_slow_entry<KIND>(d, r2[a][c], wu, wv, ty + 16 * (a0 + a),
+                                                           2 * tx + 32 * (c >> 1) + (c & 1));
+        }
+        if (d.has_const) {
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) val[a][c] = __dadd_rn(val[a][c], d.amp_const);
+        }
+        // direct tile
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            int64_t i = i0 + ty + 16 * (a0 + a);
+            if (i >= n) continue;
+            double *krow = K + i * ldk;
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                int64_t j = j0 + 2 * tx + 32 * b;
+                if (j >= m) continue;
+                if (vec_ok && j + 1 < m) {
+                    *reinterpret_cast<double2 *>(krow + j) = make_double2(val[a][2 * b], val[a][2 * b + 1]);
+                } else {
+                    krow[j] = val[a][2 * b];
+                    if (j + 1 < m) krow[j + 1] = val[a][2 * b + 1];
+                }
+            }
+        }
+        if (mirror) {
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    T[(2 * tx + 32 * (c >> 1) + (c & 1)) * (FT + 1) + ty + 16 * (a0 + a)] = val[a][c];
         }
     }
-    if (SYM && tm != tn) {
+    if (mirror) {
         // mirrored tile: K[j][i] = K[i][j]
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) T[(2 * tx + 32 * (c >> 1) + (c & 1)) * (FT + 1) + ty + 16 * a] = val[a][c];
         __syncthreads();
         const int warp = tid >> 5, lane = tid & 31;
         for (int rr = warp; rr < FT; rr += G_THREADS / 32) {

@@ -13,6 +13,9 @@ extern "C" {
 void lgp_host_exp_neg(const double *a, double *out, long n) {
     for (long i = 0; i < n; i++) out[i] = lgp::fm_exp_neg(a[i], lgp::EXP_TAB_HOST);
 }
+void lgp_host_exp_neg_fast(const double *a, double *out, long n) {
+    for (long i = 0; i < n; i++) out[i] = lgp::fm_exp_neg_fast(a[i], lgp::EXP_TAB_HOST);
+}
 void lgp_host_sqrt(const double *z, double *out, long n) {
     for (long i = 0; i < n; i++) {
         double y0 = trunc20(1.0 / sqrt(trunc20(z[i])));
