@@ -560,6 +560,8 @@ __device__ __noinline__ double fast2_slow_entry(const FastDesc &d, double r2, co
     return v;
 }
 
+constexpr int F2_TS = FT + 2;  // row stride of the transpose buffer: 16-byte aligned rows for the bulk stores
+
 template <int KIND, int P, bool SYM>
 __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_constant__ FastDesc d,
                                                                   const double *__restrict__ x, int64_t ldx, int64_t n,
@@ -607,6 +609,7 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
     const double *wu = d.white_raw ? ru : su, *wv = d.white_raw ? rv : sv;
     const bool white = d.has_white != 0;
     const bool mirror = SYM && tm != tn;
+    const bool interior = vec_ok && i0 + FT <= n && j0 + FT <= m;  // whole tile inside the matrix: no bounds checks
 
     // The 4 x 4 entries of a thread are produced in two batches of 2 rows x 4 columns: half the live registers of a
     // full 16-entry batch (3 CTAs per SM without spills), still 8 independent dependency chains per thread.
@@ -666,6 +669,15 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
                 for (int c = 0; c < 4; c++) val[a][c] = __dadd_rn(val[a][c], d.amp_const);
         }
         // direct tile
+        if (interior) {
+            double *kp = K + (i0 + ty + 16 * a0) * ldk + j0 + 2 * tx;
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                *reinterpret_cast<double2 *>(kp) = make_double2(val[a][0], val[a][1]);
+                *reinterpret_cast<double2 *>(kp + 32) = make_double2(val[a][2], val[a][3]);
+                kp += 16 * ldk;
+            }
+        } else
 #pragma unroll
         for (int a = 0; a < 2; a++) {
             int64_t i = i0 + ty + 16 * (a0 + a);
@@ -688,13 +700,27 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
             for (int a = 0; a < 2; a++)
 #pragma unroll
                 for (int c = 0; c < 4; c++)
-                    T[(2 * tx + 32 * (c >> 1) + (c & 1)) * (FT + 1) + ty + 16 * (a0 + a)] = val[a][c];
+                    T[(2 * tx + 32 * (c >> 1) + (c & 1)) * F2_TS + ty + 16 * (a0 + a)] = val[a][c];
         }
     }
     if (mirror) {
         // mirrored tile: K[j][i] = K[i][j]
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         const int warp = tid >> 5, lane = tid & 31;
+        if (interior) {
+            // TMA bulk stores: one 512-byte row of the transposed tile per copy, issued by 64 threads; the copies read
+            // shared memory through the async proxy (made visible by the fence before the barrier above)
+            if (tid < FT) {
+                const uint32_t src = smem_u32(T + tid * F2_TS);
+                double *dst = K + (j0 + tid) * ldk + i0;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                             "r"(FT * 8)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else
         for (int rr = warp; rr < FT; rr += G_THREADS / 32) {
             int64_t j = j0 + rr;  // row of the mirrored tile
             if (j >= m) break;
@@ -702,7 +728,7 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 int cidx = lane + 32 * h;
-                if (i0 + cidx < n) krow[cidx] = T[rr * (FT + 1) + cidx];
+                if (i0 + cidx < n) krow[cidx] = T[rr * F2_TS + cidx];
             }
         }
     }
@@ -972,7 +998,7 @@ static int launch_fast(cudaStream_t st, const FastDesc &d, const double *x, int6
 template <int KIND, int P>
 static int launch_fast2(cudaStream_t st, const FastDesc &d, const double *x, int64_t ldx, int64_t n, const double *y,
                         int64_t ldy, int64_t m, double *K, int64_t ldk, bool sym) {
-    size_t smem = 1024 + (size_t)(2 + (d.white_raw ? 2 : 0)) * d.nd * FT * sizeof(double) + (sym ? FT * (FT + 1) * 8 : 0);
+    size_t smem = 1024 + (size_t)(2 + (d.white_raw ? 2 : 0)) * d.nd * FT * sizeof(double) + (sym ? FT * F2_TS * 8 : 0);
     int64_t tm = (n + FT - 1) / FT, tn = (m + FT - 1) / FT;
     int64_t grid = sym ? tm * (tm + 1) / 2 : tm * tn;
     if (grid > 2147483647LL) return LGP_ERR_UNSUPPORTED;
