@@ -785,7 +785,21 @@ struct InvCtx {
     int64_t ldx;
     int rc;
 };
-static void trtri_rec(InvCtx &c, int jb, int nb) {
+// The two halves of a node are independent until its two combining products: down to TRTRI_FORK_DEPTH the right half
+// runs on a side stream, so that the small, latency-bound products near the leaves of different subtrees overlap and
+// fill the GPU (the recursion issues ~3 launches per 128-block, strictly ordered on a single stream otherwise).
+constexpr int TRTRI_FORK_DEPTH = 4;
+static cudaStream_t trtri_side_stream(int idx) {
+    static cudaStream_t pool[1 << TRTRI_FORK_DEPTH];
+    static bool init[1 << TRTRI_FORK_DEPTH];
+    if (!init[idx]) {
+        if (cudaStreamCreateWithFlags(&pool[idx], cudaStreamNonBlocking) != cudaSuccess) pool[idx] = nullptr;
+        init[idx] = true;
+    }
+    return pool[idx];
+}
+
+static void trtri_rec(InvCtx &c, int jb, int nb, int depth = 0, int path = 1) {
     if (c.rc) return;
     if (nb == 1) {
         dim3 g((NB + 127) / 128, NB);
@@ -796,8 +810,26 @@ static void trtri_rec(InvCtx &c, int jb, int nb) {
         return;
     }
     int n1 = nb / 2, n2 = nb - n1;
-    trtri_rec(c, jb, n1);
-    trtri_rec(c, jb + n1, n2);
+    cudaStream_t side = (depth < TRTRI_FORK_DEPTH && nb >= 4) ? trtri_side_stream(path) : nullptr;
+    if (side) {
+        cudaEvent_t fork, join;
+        cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+        cudaEventRecord(fork, c.st);
+        cudaStreamWaitEvent(side, fork, 0);
+        InvCtx cs = c;
+        cs.st = side;
+        trtri_rec(c, jb, n1, depth + 1, 2 * path);
+        trtri_rec(cs, jb + n1, n2, depth + 1, 2 * path + 1);
+        cudaEventRecord(join, side);
+        cudaStreamWaitEvent(c.st, join, 0);
+        cudaEventDestroy(fork);
+        cudaEventDestroy(join);
+        if (cs.rc) c.rc = cs.rc;
+    } else {
+        trtri_rec(c, jb, n1, depth + 1, 2 * path);
+        trtri_rec(c, jb + n1, n2, depth + 1, 2 * path + 1);
+    }
     if (c.rc) return;
     const double *L21 = c.W + (int64_t)(jb + n1) * NB * c.ldw + (int64_t)jb * NB;
     double *X11 = c.X + (int64_t)jb * NB * c.ldx + (int64_t)jb * NB;

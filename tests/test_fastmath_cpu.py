@@ -1,0 +1,88 @@
+"""Accuracy of the short in-kernel exp/sqrt of the Gram kernels (lsqfitgp_b200/csrc/fastmath.cuh), measured on the
+host against glibc: the header is plain C++ and oracle/fastmath_host.c builds it with g++ (oracle/Makefile).  The
+Gram parity bar is 1e-13 relative (BASELINE.json north_star); the functions must stay below 1 ulp = 2.2e-16."""
+
+import ctypes
+import pathlib
+
+import numpy as np
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope='module')
+def host():
+    path = ROOT / 'oracle' / 'libfastmath_host.so'
+    if not path.exists():
+        import subprocess
+        subprocess.run(['make', '-C', str(ROOT / 'oracle')], check=True)
+    lib = ctypes.CDLL(str(path))
+    for name in ('lgp_host_exp_neg', 'lgp_host_exp_neg_fast', 'lgp_host_sqrt'):
+        getattr(lib, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+        getattr(lib, name).restype = None
+
+    def call(name, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        out = np.empty_like(a)
+        getattr(lib, name)(a.ctypes.data, out.ctypes.data, a.size)
+        return out
+    return call
+
+
+def ulps(got, ref):
+    return np.abs(got - ref) / np.spacing(np.abs(ref))
+
+
+def test_exp_neg_full_range(host):
+    rng = np.random.default_rng(11)
+    a = -np.concatenate([rng.uniform(0, 40, 400000), rng.uniform(0, 708, 400000), 10.0 ** rng.uniform(-320, 2.8, 200000),
+                         [0.0, 5e-324, 1e-300, 0.5, 1.0, 707.9, 708.0]])
+    got = host('lgp_host_exp_neg', a)
+    ref = np.exp(a)
+    assert np.max(ulps(got, ref)) <= 1.0  # glibc itself is within 1 ulp, not correctly rounded
+    assert got[-7] == 1.0
+
+
+def test_exp_neg_underflow_and_nan(host):
+    a = np.array([-708.5, -720.0, -744.0, -745.0, -745.13, -745.2, -746.0, -1e3, -np.inf, np.nan])
+    got = host('lgp_host_exp_neg', a)
+    ref = np.exp(a)
+    sub = 5e-324
+    assert np.all(np.abs(got[:-1] - ref[:-1]) <= sub)  # subnormal results: within one subnormal step
+    assert np.all(got[6:9] == 0.0)
+    assert np.isnan(got[-1])
+
+
+def test_exp_neg_fast_in_range(host):
+    rng = np.random.default_rng(12)
+    a = -np.concatenate([rng.uniform(0, 50, 500000), rng.uniform(0, 708, 500000), [0.0, 708.0]])
+    got = host('lgp_host_exp_neg_fast', a)
+    assert np.max(ulps(got, np.exp(a))) <= 1.0
+    # same bits as the guarded version wherever both apply
+    assert np.array_equal(got, host('lgp_host_exp_neg', a))
+
+
+def test_sqrt_with_emulated_estimate(host):
+    rng = np.random.default_rng(13)
+    z = np.concatenate([rng.uniform(0, 100, 500000), 10.0 ** rng.uniform(-289, 290, 500000), [1.0, 4.0, 2.0, 1e-289, 1e290]])
+    got = host('lgp_host_sqrt', z)
+    ref = np.sqrt(z)
+    assert np.max(ulps(got, ref)) <= 1.0   # faithfully rounded
+    assert np.mean(got != ref) < 0.2       # and correctly rounded most of the time
+    assert got[-5] == 1.0 and got[-4] == 2.0
+
+
+def test_true_error_against_mpmath(host):
+    """error against the exact value (mpmath, 40 digits) on a sample: below 1 ulp for both functions"""
+    import mpmath
+    mpmath.mp.dps = 40
+    rng = np.random.default_rng(14)
+    a = -rng.uniform(0, 700, 1500)
+    got = host('lgp_host_exp_neg_fast', a)
+    err = [abs(mpmath.mpf(float(g)) - mpmath.exp(mpmath.mpf(float(x)))) / mpmath.mpf(float(np.spacing(g))) for g, x in zip(got, a)]
+    assert max(err) < 1.0
+    z = 10.0 ** rng.uniform(-200, 200, 1500)
+    got = host('lgp_host_sqrt', z)
+    err = [abs(mpmath.mpf(float(g)) - mpmath.sqrt(mpmath.mpf(float(x)))) / mpmath.mpf(float(np.spacing(g))) for g, x in zip(got, z)]
+    assert max(err) < 1.0
