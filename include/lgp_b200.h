@@ -56,6 +56,9 @@ long long lgp_launch_count(void);
 #define LGP_K_CAUCHY 2   /* (1 + r2^(par0/2)/par1)^(-par1/par0)           _basic.py:339-343 */
 #define LGP_K_WHITE 3    /* prod_d (x_d == y_d)                           _basic.py:59 */
 #define LGP_K_CONSTANT 4 /* 1                                             _basic.py:46 */
+#define LGP_K_MATERN 5   /* Matern of real order nu = par0 in [0, 100]: 2/Gamma(nu) (x/2)^nu K_nu(x), x = sqrt(2 nu r2),
+                            K_nu evaluated in the kernel (Temme series / Steed CF2); the reference calls
+                            scipy.special.kv on the host            _matern.py:55-76, _special/_bessel.py:70-99 */
 
 #define LGP_MAX_FACTORS 8
 #define LGP_MAX_DIMS 32
@@ -93,6 +96,19 @@ int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors,
 int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
                      int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, const double *G, int64_t ldg,
                      const double *b, int symlower, double *out);
+
+/* Forward-mode derivative of the Gram build (what jax.jacfwd of decomp.matrix() gives the reference for the Fisher
+ * matrix, src/lsqfitgp/_fit.py:676-683, _linalg/_decomp.py:535-558), one tangent direction at a time:
+ *   D[i][j] = sum_f tangent[3f+0] dK_ij/d amp_f + tangent[3f+1] dK_ij/d log(scale_f) + tangent[3f+2] dK_ij/d par1_f
+ * `tangent` is HOST memory (3*nfactors doubles, same layout as the output of lgp_gram_iso_vjp). */
+int lgp_gram_iso_jvp(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
+                     int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, const double *tangent,
+                     double *D_out, int64_t ldd);
+
+/* out[0] = sum_{i<rows, j<cols} A[i*lda+j] * B[i*ldb+j]: the contraction einsum('kij,qij->kq') of the Fisher matrix
+ * (src/lsqfitgp/_linalg/_decomp.py:553), one (k, q) pair per call.  out: device memory, 1 double. */
+int lgp_frob_dot(lgp_stream_t stream, const double *A, int64_t lda, const double *B, int64_t ldb, int64_t rows,
+                 int64_t cols, double *out);
 
 /* ------------------------------------------------------------------------------------------------
  * BART Gram (fast path of BART._correlation: src/lsqfitgp/_kernels/_bart.py:628-757, with the

@@ -117,6 +117,41 @@ class _GramFn(torch.autograd.Function):
             grads.append(g.to(tensor.device, tensor.dtype).reshape(tensor.shape))
         return (None, None, None, None, *grads)
 
+    @staticmethod
+    def jvp(ctx, _kern, _xd, _yd, _labels, *tangents):
+        """ forward mode (torch.autograd.forward_ad): dK along the tangent of the hyperparameters, one pass of
+        lgp_gram_iso_jvp; what jax.jacfwd of the Gram build gives the reference's Fisher path (_fit.py:676-683) """
+        kern, xd, yd, labels = ctx.kern, ctx.xd, ctx.yd, ctx.labels
+        hyper = kern._hyperparams()
+        assert len(hyper) == len(tangents)
+        D = None
+        if kern._terms:
+            descs, index = kern._descriptor(labels)
+            pos = {tf: i for i, tf in enumerate(index)}
+            tan = numpy.zeros((len(descs), 3))
+            for (kind, ti, fi, tensor), t in zip(hyper, tangents):
+                if t is None or kind == 'bart_amp':
+                    continue
+                tv = float(t)
+                if kind == 'amp':
+                    tan[pos[(ti, 0)], 0] += tv
+                elif kind == 'scale':
+                    tan[pos[(ti, fi)], 1] += tv / float(tensor)
+                elif kind == 'par1':
+                    tan[pos[(ti, fi)], 2] += tv
+                else:  # pragma: no cover
+                    raise NotImplementedError(kind)
+            D = _ops.gram_iso_jvp(descs, xd, yd, tan)
+        for (kind, ti, fi, tensor), t in zip(hyper, tangents):
+            if kind == 'bart_amp' and t is not None:
+                spec = ti
+                corr = spec.scaled(1.0 / float(spec.amp)).gram_device(xd, yd, labels)
+                corr *= float(t)
+                D = corr if D is None else D.add_(corr)
+        if D is None:
+            D = torch.zeros(xd.shape[1], yd.shape[1], dtype=f64, device=xd.device)
+        return D
+
 
 class _NegLogDensityFn(torch.autograd.Function):
     """ value = 1/2 (n log 2pi + log det K + r' K^-1 r)  (reference _decomp.py:484-488);
@@ -682,6 +717,20 @@ class GP:
         self._check_ycov(ycov)
         decomp = self._solver(inkeys, ycov, **kw)
         return decomp, ymean
+
+    def _prior_matrix(self, given, givencov=None):
+        """ (Kxx + ycov, flattened data) as torch tensors attached to the autograd graph of the hyperparameters: the
+        argument of the decomposition in `_prior_decomp`, before decomposing (reference _compute.py:45-94,336-367).
+        Used by the Fisher path of empbayes_fit, which needs its forward-mode derivative. """
+        ylist, inkeys, ycovblocks = self._flatgiven(given, givencov)
+        ymean = torch.cat(ylist)
+        self._check_ymean(ymean)
+        ycov = self._block(ycovblocks) if ycovblocks is not None else None
+        self._check_ycov(ycov)
+        Kxx = self._assemblecovblocks(inkeys)
+        if ycov is not None:
+            Kxx = Kxx + ycov
+        return Kxx, ymean
 
     def marginal_likelihood(self, given, givencov=None, **kw):
         """ Logarithm of the probability of the data (reference _compute.py:383-422).

@@ -11,7 +11,10 @@ without JAX:
     kernel from them with torch operations; the objective
         -logML(hp(p)) + 1/2 (k log 2pi + p.p) + additional_loss(hp)          (reference _fit.py:659-668,718-721)
     is differentiated by torch.autograd, whose backward runs the CUDA inverse-from-factor and Gram-VJP kernels;
-  * the same scipy.optimize.minimize drivers are used: 'nograd' -> Nelder-Mead, 'gradient' -> BFGS.
+  * the same scipy.optimize.minimize drivers are used: 'nograd' -> Nelder-Mead, 'gradient' -> BFGS,
+    'fisher' -> dogleg with the Fisher information plus the prior precision as hessian (reference _fit.py:732-743,
+    756-772): dK/dp comes from torch forward-mode AD through the Gram JVP kernel (lgp_gram_iso_jvp), the matrix
+    itself from Chol.minus_log_normal_density(fisher=True) (two blocked TRSMs per parameter on the DMMA path).
 """
 
 import math
@@ -116,7 +119,46 @@ class empbayes_fit(Logger):
             grad, = torch.autograd.grad(total, pt, allow_unused=True)
             if grad is None:
                 grad = torch.zeros_like(pt)
-            return float(total), grad.numpy().astype(float)
+            return float(total.detach()), grad.numpy().astype(float)
+
+        def fisher(p):
+            """ Fisher information of the hyperparameters plus prior precision (reference _fit.py:732-743) """
+            import torch.autograd.forward_ad as fwAD
+            if additional_loss is not None:
+                raise NotImplementedError('Fisher matrix not implemented with additional_loss')
+            self._ncalls['fisher'] = self._ncalls.get('fisher', 0) + 1
+            p = numpy.asarray(p, dtype=float)
+            k = len(p)
+            K0 = r0 = None
+            dKs, drs = [], []
+            for q in range(k):
+                pt = torch.tensor(p, dtype=f64, requires_grad=True)
+                e = torch.zeros(k, dtype=f64)
+                e[q] = 1.0
+                with fwAD.dual_level():
+                    hp = hpunflat(fwAD.make_dual(pt, e))
+                    gp = gpfactory(hp, **gpfactorykw)
+                    args = data(hp, **gpfactorykw) if cachedargs is None else cachedargs
+                    if not isinstance(args, tuple):
+                        args = (args,)
+                    K, r = gp._prior_matrix(*args)
+                    Kp, Kt = fwAD.unpack_dual(K)
+                    rp, rt = fwAD.unpack_dual(r)
+                    if K0 is None:
+                        K0, r0 = Kp.detach(), rp.detach()
+                    dKs.append(torch.zeros_like(K0) if Kt is None else Kt.detach())
+                    drs.append(torch.zeros_like(r0) if rt is None else rt.detach().to(r0.device))
+                del K, Kp, Kt
+            solverkw = dict(getattr(gp, '_solverkw', {}))
+            solverkw.update(mlkw)
+            dec = _linalg.Chol(K0, **solverkw)
+            del K0
+            lkw = dict(dK=dKs)
+            if any(bool(torch.any(d != 0)) for d in drs):
+                lkw.update(dr=torch.stack(drs, dim=1))
+            _, _, _, fm, _ = dec.minus_log_normal_density(r0, fisher=True, **lkw)
+            fm = fm.cpu().numpy() if isinstance(fm, torch.Tensor) else numpy.asarray(fm)
+            return fm + numpy.eye(k)
 
         def fun(p):
             self._ncalls['fun'] += 1
@@ -137,7 +179,8 @@ class empbayes_fit(Logger):
         elif method == 'gradient':
             minargs.update(method='bfgs')
         elif method == 'fisher':
-            raise NotImplementedError("method='fisher' (Fisher-matrix Newton steps) is not implemented yet")
+            # dogleg requires positive definiteness; the Fisher matrix is p.s.d. and the prior precision is the identity
+            minargs.update(hess=fisher, method='dogleg')
         else:
             raise KeyError(method)
         self.log(f'method {method!r}', 2)
@@ -168,7 +211,7 @@ class empbayes_fit(Logger):
             else:
                 self.log(msg)
 
-        cov = self._posterior_covariance(covariance, result)
+        cov = self._posterior_covariance(method, covariance, result, fisher)
         self.log(f'calls: {self._ncalls}; total time {total:.3g} s; in marginal_likelihood '
                  f'{self._times["gp&cov+decomp+likelihood"]:.3g} s')
 
@@ -349,12 +392,14 @@ class empbayes_fit(Logger):
             off += size
         return out
 
-    def _posterior_covariance(self, covariance, result):
-        """ reference _fit.py:808-845 (without the Fisher option) """
+    def _posterior_covariance(self, method, covariance, result, fisher_func):
+        """ reference _fit.py:808-845 """
         if covariance == 'auto':
             covariance = 'minhess' if (hasattr(result, 'hess_inv') or hasattr(result, 'hess')) else 'none'
         if covariance == 'fisher':
-            raise NotImplementedError("covariance='fisher'")
+            self.log('use fisher plus prior precision as precision', 2)
+            prec = result.hess if method == 'fisher' else fisher_func(result.x)
+            return _linalg.Chol(prec).ginv()
         if covariance == 'minhess':
             if hasattr(result, 'hess_inv'):
                 hessinv = result.hess_inv

@@ -63,16 +63,22 @@ class Matern(IsotropicKernel):
     """ Matern kernel of real order nu (reference _kernels/_matern.py:55-76).
 
     Half-integer orders are evaluated in closed form (same polynomial as Maternp without the 1e-30 offset,
-    equal to 2/Gamma(nu) (x/2)^nu K_nu(x) to ~1e-15).  Other orders need a device Bessel K
-    and are not implemented yet. """
+    equal to 2/Gamma(nu) (x/2)^nu K_nu(x) to ~1e-15).  Other orders, 0 <= nu <= 100, evaluate
+    the modified Bessel function K_nu inside the Gram kernel (csrc/bessel_k.cuh: Temme series / Steed continued
+    fraction), where the reference calls scipy.special.kv on the host through jax.pure_callback
+    (_special/_bessel.py:35,70-82).  As in the reference, nu itself is not differentiable. """
     _kind = _lib.K_MATERNP
 
     def __new__(cls, nu=None, **kw):
         assert nu is not None and 0 <= _f(nu) < numpy.inf, nu
+        if isinstance(nu, torch.Tensor) and nu.requires_grad:
+            raise NotImplementedError('Matern: derivatives with respect to nu are not implemented (nor in the reference)')
         p = _f(nu) - 0.5
-        if p < 0 or p != int(p):
-            raise NotImplementedError(f'Matern(nu={nu!r}): only half-integer orders are implemented on the device')
-        return cls._make(cls._kind, ipar=int(p), par0=0.0, **kw)
+        if p >= 0 and p == int(p) and p <= 8:
+            return cls._make(_lib.K_MATERNP, ipar=int(p), par0=0.0, **kw)
+        if _f(nu) > 100:
+            raise NotImplementedError(f'Matern(nu={nu!r}): orders above 100 are not implemented on the device')
+        return cls._make(_lib.K_MATERN, par0=_f(nu), **kw)
 
 
 # -------------------------------------------------------------------------------------------------

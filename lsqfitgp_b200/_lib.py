@@ -20,7 +20,7 @@ ERRORS = {-1: 'bad argument', -2: 'misaligned pointer or odd leading dimension',
           -4: 'unsupported configuration'}
 
 # kernel kinds (lgp_b200.h)
-K_EXPQUAD, K_MATERNP, K_CAUCHY, K_WHITE, K_CONSTANT = range(5)
+K_EXPQUAD, K_MATERNP, K_CAUCHY, K_WHITE, K_CONSTANT, K_MATERN = range(6)
 MAX_FACTORS = 8
 MAX_DIMS = 32
 
@@ -69,6 +69,9 @@ SIGNATURES = {
     'lgp_gram_iso': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int]),
     'lgp_gram_iso_vjp': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64,
                                 _vp, _int, _vp]),
+    'lgp_gram_iso_jvp': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, c_double_p,
+                                _vp, _i64]),
+    'lgp_frob_dot': (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     'lgp_gram_bart': (_int, [_vp, _int, c_int32_p, c_double_p, c_double_p, _int, _int, _dbl, _dbl, _vp,
                              _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int]),
     'lgp_bart_digamma_table': (_int, [c_double_p, _i64]),

@@ -352,15 +352,25 @@ class Chol(Decomposition):
         if fisher:
             fm = 0
             if dK is not None:
-                dKd = todev(dK)
-                k = dKd.shape[2]
+                # B_q = L⁻¹ dK_q L⁻ᵀ (two blocked TRSMs on the DMMA GEMM path), F_kq = 1/2 sum_ij B_k,ij B_q,ij
+                # (_decomp.py:547-554).  dK: (n, n, k) array as in the reference, or a sequence of k (n, n) matrices.
+                if isinstance(dK, (list, tuple)):
+                    dlist = [todev(m) for m in dK]
+                else:
+                    dKd = todev(dK)
+                    dlist = [dKd[:, :, q] for q in range(dKd.shape[2])]
                 mats = []
-                for q in range(k):
-                    t1 = self._solve(dKd[:, :, q].contiguous(), False)       # L⁻¹ dK_q
-                    t2 = self._solve(t1.T.contiguous(), False)                # L⁻¹ (L⁻¹ dK_q)'
+                for m in dlist:
+                    t1 = self._solve(_ops.as_aligned(m), False)      # L⁻¹ dK_q
+                    t2 = self._solve(_ops.as_aligned(t1.T), False)   # L⁻¹ (L⁻¹ dK_q)'
+                    del t1
                     mats.append(t2)
-                stack = torch.stack(mats)
-                fm = fm + 1 / 2 * torch.einsum('kij,qij->kq', stack, stack)
+                k = len(mats)
+                fm = torch.zeros(k, k, dtype=f64, device=rd.device)
+                for a in range(k):
+                    for b in range(a + 1):
+                        fm[a, b] = fm[b, a] = 0.5 * _ops.frob_dot(mats[a], mats[b])[0]
+                del mats
             if dr is not None:
                 invLdr = self._solve(todev(dr), False)
                 fm = fm + self._matmul_tn(invLdr, invLdr)

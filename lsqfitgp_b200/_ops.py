@@ -121,6 +121,35 @@ def gram_iso_vjp_general(descs, x, y, G):
     return buf[:3 * len(descs)].reshape(len(descs), 3)
 
 
+def gram_iso_jvp(descs, x, y, tangent, out=None):
+    """ forward-mode derivative of the Gram build along `tangent` ((nfactors, 3) host array: d amp, d log scale,
+    d par1 per factor, the layout of gram_iso_vjp); returns the dense (n, m) matrix (see lgp_b200.h) """
+    lib = _lib.load()
+    ndim, n = x.shape
+    m = y.shape[1]
+    x = x.contiguous() if x.stride(1) != 1 else x
+    y = y.contiguous() if y.stride(1) != 1 else y
+    if out is None:
+        out = aligned_empty(n, m, x.device)
+    tan = numpy.ascontiguousarray(numpy.asarray(tangent, dtype=numpy.float64).reshape(-1))
+    assert tan.size == 3 * len(descs)
+    facs = make_factors(descs)
+    check(lib.lgp_gram_iso_jvp(stream_ptr(), facs, len(descs), ndim, ptr(x), x.stride(0) if ndim else 0, n,
+                               ptr(y), y.stride(0) if ndim else 0, m, tan.ctypes.data_as(_lib.c_double_p),
+                               ptr(out), out.stride(0)), 'lgp_gram_iso_jvp')
+    return out
+
+
+def frob_dot(A, B):
+    """ sum_ij A_ij B_ij as a 1-element device tensor (A, B: 2-D, unit column stride) """
+    lib = _lib.load()
+    assert A.shape == B.shape and A.ndim == 2 and A.stride(1) == 1 and B.stride(1) == 1
+    out = torch.empty(1, dtype=f64, device=A.device)
+    check(lib.lgp_frob_dot(stream_ptr(), ptr(A), A.stride(0), ptr(B), B.stride(0), A.shape[0], A.shape[1], ptr(out)),
+          'lgp_frob_dot')
+    return out
+
+
 _psi_cache = {}
 
 

@@ -12,6 +12,7 @@
 #include "../../include/lgp_b200.h"
 #include "common.cuh"
 #include "fastmath.cuh"
+#include "bessel_k.cuh"
 
 namespace lgp {
 
@@ -31,6 +32,7 @@ struct GramDesc {
     double scale_x[LGP_MAX_FACTORS], scale_y[LGP_MAX_FACTORS], loc_x[LGP_MAX_FACTORS], loc_y[LGP_MAX_FACTORS];
     double par0[LGP_MAX_FACTORS], par1[LGP_MAX_FACTORS], amp[LGP_MAX_FACTORS];
     double coef[LGP_MAX_FACTORS][G_MAX_P];  // Maternp Horner ratios c_{k+1}/c_k, k = 0..p-1
+    double mat[LGP_MAX_FACTORS][MATERN_NPAR];  // Matern of real order: host-computed constants (bessel_k.cuh)
     unsigned char slot_dim[G_MAX_SLOTS];
     unsigned char slot_factor[G_MAX_SLOTS];
 };
@@ -49,7 +51,8 @@ static int build_desc(const lgp_factor_t *f, int nf, int ndim, GramDesc &d) {
         d.loc_x[i] = f[i].loc_x; d.loc_y[i] = f[i].loc_y;
         d.par0[i] = f[i].par0; d.par1[i] = f[i].par1; d.amp[i] = f[i].amp;
         d.slot0[i] = slots;
-        if (f[i].kind < 0 || f[i].kind > LGP_K_CONSTANT) return LGP_ERR_UNSUPPORTED;
+        if (f[i].kind < 0 || f[i].kind > LGP_K_MATERN) return LGP_ERR_UNSUPPORTED;
+        if (f[i].kind == LGP_K_MATERN && !matern_nu_setup(f[i].par0, d.mat[i])) return LGP_ERR_UNSUPPORTED;
         if (f[i].kind == LGP_K_MATERNP) {
             int p = f[i].ipar;
             if (p < 0 || p > G_MAX_P) return LGP_ERR_UNSUPPORTED;
@@ -91,6 +94,11 @@ __device__ __forceinline__ double core_value(const GramDesc &d, int f, double r2
         }
         case LGP_K_WHITE:
             return r2 == 0.0 ? 1.0 : 0.0;
+        case LGP_K_MATERN: {
+            double val, dr2;
+            matern_nu_core(d.mat[f], r2, false, val, dr2);
+            return val;
+        }
         default:
             return 1.0;
     }
@@ -141,6 +149,9 @@ __device__ __forceinline__ void core_derivs(const GramDesc &d, int f, double r2,
         case LGP_K_WHITE:
             val = r2 == 0.0 ? 1.0 : 0.0;
             dr2 = 0.0;
+            return;
+        case LGP_K_MATERN:
+            matern_nu_core(d.mat[f], r2, true, val, dr2);
             return;
         default:
             val = 1.0;
@@ -344,6 +355,84 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_vjp_kernel(const __grid_co
     }
 }
 
+// Forward-mode derivative of the Gram build: D_ij = sum_f sum_c tan[3f+c] dK_ij/d(param c of factor f), c = amp, log scale,
+// par1 (same layout as the VJP output).  One pass over the tile; every factor is evaluated once per entry with its
+// derivatives, the product rule is applied inside each term.  Used by the Fisher-information path
+// (src/lsqfitgp/_fit.py:676-683: jax.jacfwd of decomp.matrix(); _linalg/_decomp.py:535-558).
+struct GramTangent {
+    double t[3 * LGP_MAX_FACTORS];
+};
+
+__global__ void __launch_bounds__(G_THREADS) gram_iso_jvp_kernel(const __grid_constant__ GramDesc d,
+                                                                 const __grid_constant__ GramTangent tan,
+                                                                 const double *__restrict__ x, int64_t ldx, int64_t n,
+                                                                 const double *__restrict__ y, int64_t ldy, int64_t m,
+                                                                 double *__restrict__ D, int64_t ldd) {
+    extern __shared__ __align__(16) double gsm[];
+    double *su = gsm;
+    double *sv = gsm + (size_t)d.nslots * GT;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t i0 = (int64_t)blockIdx.y * GT, j0 = (int64_t)blockIdx.x * GT;
+    stage_points(d, su, x, ldx, n, i0, false, tid);
+    stage_points(d, sv, y, ldy, m, j0, true, tid);
+    __syncthreads();
+#pragma unroll 1
+    for (int a = 0; a < 4; a++) {
+        const int64_t i = i0 + ty + 16 * a;
+        if (i >= n) continue;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            const int cc = 2 * tx + 32 * (c >> 1) + (c & 1);
+            const int64_t j = j0 + cc;
+            if (j >= m) continue;
+            double total = 0.0;
+            // walk the terms: value of the term P = prod_f amp_f v_f, derivative sum_f (dlog-free product rule)
+            int f = 0;
+            while (f < d.nfactors) {
+                const int term = d.term[f];
+                double prod = 1.0;   // product of amp_h * val_h over the factors seen so far
+                double dsum = 0.0;   // derivative of that product along the tangent
+                for (; f < d.nfactors && d.term[f] == term; f++) {
+                    double r2 = 0.0;
+                    for (int s = d.slot0[f]; s < d.slot0[f] + d.nslot[f]; s++) {
+                        const double df = su[s * GT + ty + 16 * a] - sv[s * GT + cc];
+                        r2 += df * df;
+                    }
+                    double val, dr2, dp1;
+                    core_derivs(d, f, r2, val, dr2, dp1);
+                    const double v = d.amp[f] * val;
+                    const double dv = tan.t[3 * f] * val + d.amp[f] * (tan.t[3 * f + 1] * dr2 * (-2.0 * r2) + tan.t[3 * f + 2] * dp1);
+                    dsum = dsum * v + prod * dv;
+                    prod *= v;
+                }
+                total += dsum;
+            }
+            D[i * ldd + j] = total;
+        }
+    }
+}
+
+// out[0] += sum_{i<rows, j<cols} A[i*lda + j] * B[i*ldb + j]   (Frobenius inner product; the k x k Fisher contraction
+// einsum('kij,qij->kq') of _decomp.py:553 is k(k+1)/2 of these)
+__global__ void __launch_bounds__(256) frob_dot_kernel(const double *__restrict__ A, int64_t lda,
+                                                       const double *__restrict__ B, int64_t ldb, int64_t rows,
+                                                       int64_t cols, double *__restrict__ out) {
+    __shared__ double red[8];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x; i < rows; i += gridDim.x) {
+        const double *a = A + i * lda, *b = B + i * ldb;
+        for (int64_t j = threadIdx.x; j < cols; j += 256) acc += a[j] * b[j];
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < 8; w++) v += red[w];
+        atomicAdd(out, v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fast path: K = amp * core(r2 / scale^2) [+ amp_w * White] [+ const], one isotropic factor over the same fields
 // for x and y.  Symmetric mode evaluates only tiles on or below the diagonal and mirrors them through shared
@@ -355,6 +444,7 @@ struct FastDesc {
     int has_white, has_const, white_raw;
     double scale, loc, par0, par1, amp, amp_white, amp_const;
     double coef[G_MAX_P];
+    double coef2[G_MAX_P];  // 2 * coef (exact), precomputed on the host for the fast path
     unsigned char dims[LGP_MAX_DIMS];
 };
 
@@ -528,9 +618,12 @@ __device__ __forceinline__ double fast2_core(double r2, double nu2, double par0,
     if (P == 0) return ex;
     // Horner in the reference's order poly = 1 + ((poly*c_k)*2)*x, the last product-sum fused
     double poly = 1.0;
-    if (P >= 3) poly = __fma_rn(c2, x, 1.0);                       // c_k here = 2*coef_k (exact doubling)
-    if (P >= 2) poly = __fma_rn(__dmul_rn(poly, c1), x, 1.0);
-    poly = __fma_rn(__dmul_rn(poly, c0), x, 1.0);
+    // (c_k here = 2*coef_k, an exact doubling; the first step has poly == 1, so poly*c == c without a multiplication)
+    if (P >= 3) poly = __fma_rn(c2, x, 1.0);
+    if (P == 2) poly = __fma_rn(c1, x, 1.0);
+    if (P >= 3) poly = __fma_rn(__dmul_rn(poly, c1), x, 1.0);
+    if (P == 1) poly = __fma_rn(c0, x, 1.0);
+    if (P >= 2) poly = __fma_rn(__dmul_rn(poly, c0), x, 1.0);
     return __dmul_rn(ex, poly);
 }
 
@@ -605,7 +698,7 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
     __syncthreads();
 
     const double nu2 = (double)(2 * P + 1), par0 = d.par0, amp = d.amp;
-    const double c0 = 2.0 * d.coef[0], c1 = 2.0 * d.coef[1], c2 = 2.0 * d.coef[2];
+    const double c0 = d.coef2[0], c1 = d.coef2[1], c2 = d.coef2[2];
     const double *wu = d.white_raw ? ru : su, *wv = d.white_raw ? rv : sv;
     const bool white = d.has_white != 0;
     const bool mirror = SYM && tm != tn;
@@ -771,9 +864,42 @@ __device__ __forceinline__ void fast_core_derivs(const FastDesc &d, double r2, d
     }
 }
 
+// Fast-math value and d core / d r2 (ExpQuad, Maternp with compile-time P), arguments inside the range accepted by
+// fast2_out_of_range; same formulas as fast_core_derivs.
+template <int KIND, int P>
+__device__ __forceinline__ void fast2_core_derivs(const FastDesc &d, double r2, const ExpTab *tab, double &val,
+                                                  double &dr2) {
+    if (KIND == LGP_K_EXPQUAD) {
+        val = fm_exp_neg_fast(-0.5 * r2, tab);
+        dr2 = -0.5 * val;
+        return;
+    }
+    constexpr int PP = P < 0 ? 0 : P;
+    constexpr double nu2 = (double)(2 * PP + 1);
+    const double z = nu2 * r2 + d.par0;
+    const double x = fm_sqrt_fast(z);
+    const double ex = fm_exp_neg_fast(-x, tab);
+    if (PP == 0) {
+        val = ex;
+        dr2 = -nu2 * ex / (2.0 * x);
+        return;
+    }
+    double poly = 1.0;
+#pragma unroll
+    for (int k = PP - 1; k >= 0; k--) poly = fma(poly * d.coef2[k], x, 1.0);
+    val = ex * poly;
+    constexpr int pm = PP - 1;
+    double polym = 1.0;
+#pragma unroll
+    for (int k = pm - 1; k >= 0; k--)
+        polym = fma(polym * (2.0 * (double)(pm - k) / (double)((2 * pm - k) * (k + 1))), x, 1.0);
+    dr2 = (-nu2 / (4.0 * ((double)PP - 0.5))) * ex * polym;
+}
+
 // Fast symmetric VJP over the lower triangle: out[0..2] main factor (d amp, d log scale, d par1),
 // out[3] = d/d amp_white, out[4] = d/d amp_const.  G_ij = w_ij (Ginv_ij - b_i b_j).
-template <int KIND>
+// P >= 0 (ExpQuad: 0; Maternp: the order): short in-kernel exp/sqrt for in-range entries; P < 0: library path only.
+template <int KIND, int P>
 __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_vjp_kernel(const __grid_constant__ FastDesc d,
                                                                      const double *__restrict__ x, int64_t ldx,
                                                                      int64_t n, const double *__restrict__ G,
@@ -785,7 +911,9 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_vjp_kernel(const __gri
     double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
     __shared__ double sbi[FT], sbj[FT];
     __shared__ double red[G_THREADS / 32][5];
+    __shared__ ExpTab tab[64];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    if (P >= 0 && tid < 64) tab[tid] = EXP_TAB_DEV[tid];
     long long b = blockIdx.x;
     int tm = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
     while ((long long)(tm + 1) * (tm + 2) / 2 <= b) tm++;
@@ -880,8 +1008,11 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_vjp_kernel(const __gri
                 if (e == 1 && !second) continue;
                 double g = (e ? g1 : g0) - bi * sbj[cc + e];
                 if (j + e != i) g *= 2.0;
-                double val, dr2, dp1;
-                fast_core_derivs<KIND>(d, r2[a][2 * bb + e], val, dr2, dp1);
+                double val, dr2, dp1 = 0.0;
+                if (P >= 0 && !fast2_out_of_range<KIND>(r2[a][2 * bb + e], (double)(2 * P + 1), d.par0, false))
+                    fast2_core_derivs<KIND, P>(d, r2[a][2 * bb + e], tab, val, dr2);
+                else
+                    fast_core_derivs<KIND>(d, r2[a][2 * bb + e], val, dr2, dp1);
                 acc[0] += g * val;
                 acc[1] += g * d.amp * dr2 * (-2.0 * r2[a][2 * bb + e]);
                 acc[2] += g * d.amp * dp1;
@@ -960,7 +1091,10 @@ static bool build_fast(const lgp_factor_t *f, int nf, int ndim, FastDesc &d) {
     d.amp = m.amp;
     if (m.kind == LGP_K_MATERNP) {
         if (d.p < 0 || d.p > G_MAX_P) return false;
-        for (int k = 0; k < d.p; k++) d.coef[k] = (double)(d.p - k) / (double)((2 * d.p - k) * (k + 1));
+        for (int k = 0; k < d.p; k++) {
+            d.coef[k] = (double)(d.p - k) / (double)((2 * d.p - k) * (k + 1));
+            d.coef2[k] = 2.0 * d.coef[k];
+        }
     }
     for (int dd = 0; dd < ndim; dd++)
         if (m.dimmask & (1u << dd)) d.dims[d.nd++] = (unsigned char)dd;
@@ -1099,12 +1233,23 @@ int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfact
             int64_t t = (n + FT - 1) / FT;
             int64_t nblk = t * (t + 1) / 2;
             if (nblk > 2147483647LL) return LGP_ERR_UNSUPPORTED;
+#define LGP_VJP_LAUNCH(KIND, P) \
+    gram_fast_vjp_kernel<KIND, P><<<(unsigned)nblk, G_THREADS, smem, st>>>(fd, x, ldx, n, G, ldg, b, tmp)
             if (fd.kind == LGP_K_EXPQUAD)
-                gram_fast_vjp_kernel<LGP_K_EXPQUAD><<<(unsigned)nblk, G_THREADS, smem, st>>>(fd, x, ldx, n, G, ldg, b, tmp);
+                LGP_VJP_LAUNCH(LGP_K_EXPQUAD, 0);
+            else if (fd.kind == LGP_K_MATERNP && fd.p == 0)
+                LGP_VJP_LAUNCH(LGP_K_MATERNP, 0);
+            else if (fd.kind == LGP_K_MATERNP && fd.p == 1)
+                LGP_VJP_LAUNCH(LGP_K_MATERNP, 1);
+            else if (fd.kind == LGP_K_MATERNP && fd.p == 2)
+                LGP_VJP_LAUNCH(LGP_K_MATERNP, 2);
+            else if (fd.kind == LGP_K_MATERNP && fd.p == 3)
+                LGP_VJP_LAUNCH(LGP_K_MATERNP, 3);
             else if (fd.kind == LGP_K_MATERNP)
-                gram_fast_vjp_kernel<LGP_K_MATERNP><<<(unsigned)nblk, G_THREADS, smem, st>>>(fd, x, ldx, n, G, ldg, b, tmp);
+                LGP_VJP_LAUNCH(LGP_K_MATERNP, -1);
             else
-                gram_fast_vjp_kernel<LGP_K_CAUCHY><<<(unsigned)nblk, G_THREADS, smem, st>>>(fd, x, ldx, n, G, ldg, b, tmp);
+                LGP_VJP_LAUNCH(LGP_K_CAUCHY, -1);
+#undef LGP_VJP_LAUNCH
             LGP_CUDA_CHECK_LAUNCH();
             fast_vjp_scatter_kernel<<<1, 32, 0, st>>>(tmp, out, nfactors, pos_white, pos_const);
             LGP_CUDA_CHECK_LAUNCH();
@@ -1128,6 +1273,42 @@ int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfact
     if (nblk > 2147483647LL) return LGP_ERR_UNSUPPORTED;
     gram_iso_vjp_kernel<<<(unsigned)nblk, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, G, ldg, b, symlower, (int)tn,
                                                                  out);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+int lgp_gram_iso_jvp(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
+                     int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, const double *tangent,
+                     double *D_out, int64_t ldd) {
+    if (!factors || !tangent || !D_out || n < 1 || m < 1 || ldd < m) return LGP_ERR_BADARG;
+    GramDesc d;
+    int rc = build_desc(factors, nfactors, ndim, d);
+    if (rc) return rc;
+    GramTangent tan;
+    memset(&tan, 0, sizeof(tan));
+    for (int i = 0; i < 3 * nfactors; i++) tan.t[i] = tangent[i];
+    size_t smem = (size_t)2 * d.nslots * GT * sizeof(double);
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(gram_iso_jvp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return LGP_ERR_CUDA;
+    }
+    dim3 grid((unsigned)((m + GT - 1) / GT), (unsigned)((n + GT - 1) / GT));
+    if (grid.y > 65535) return LGP_ERR_UNSUPPORTED;
+    gram_iso_jvp_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(d, tan, x, ldx, n, y, ldy, m, D_out, ldd);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+int lgp_frob_dot(lgp_stream_t stream, const double *A, int64_t lda, const double *B, int64_t ldb, int64_t rows,
+                 int64_t cols, double *out) {
+    if (!A || !B || !out || rows < 0 || cols < 0 || lda < cols || ldb < cols) return LGP_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    zero_kernel<<<1, 32, 0, st>>>(out, 1);
+    LGP_CUDA_CHECK_LAUNCH();
+    if (rows == 0 || cols == 0) return LGP_OK;
+    const unsigned grid = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
+    frob_dot_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, rows, cols, out);
     LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
 }

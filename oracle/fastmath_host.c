@@ -23,3 +23,16 @@ void lgp_host_sqrt(const double *z, double *out, long n) {
     }
 }
 }
+
+/* host build of the general-order Matern core (lsqfitgp_b200/csrc/bessel_k.cuh) for tests/test_bessel_cpu.py */
+#include "../lsqfitgp_b200/csrc/bessel_k.cuh"
+
+extern "C" {
+int lgp_host_matern_nu(double nu, const double *r2, double *val, double *dr2, long n) {
+    double par[lgp::MATERN_NPAR];
+    if (!lgp::matern_nu_setup(nu, par)) return 1;
+    for (long i = 0; i < n; i++) lgp::matern_nu_core(par, r2[i], true, val[i], dr2[i]);
+    return 0;
+}
+int lgp_host_matern_nu_par(double nu, double *par) { return lgp::matern_nu_setup(nu, par) ? 0 : 1; }
+}

@@ -324,3 +324,80 @@ def test_kernel_call_broadcasting():
                                rtol=1e-13)
     with pytest.raises(ValueError):
         ka(x, x)
+
+
+@pytest.mark.parametrize('nu', [0.3, 1.3, 4.2])
+def test_matern_real_order_vs_oracle(nu):
+    """ Matern of non-half-integer order: K_nu evaluated in the Gram kernel (csrc/bessel_k.cuh) where the reference
+    calls scipy.special.kv on the host (_special/_bessel.py:35,70-99).  The oracle follows the reference route (scipy kv,
+    AMOS), which is itself up to ~1e-13 from the exact value (tests/test_bessel_cpu.py): Gram tolerance 2e-13 here. """
+    rng = np.random.default_rng(int(nu * 10))
+    n = 700
+    X = rng.uniform(0, 10, (n, 3))
+    y = np.sin(X[:, 0]) + np.cos(X[:, 1]) * X[:, 2] / 10 + 0.1 * rng.standard_normal(n)
+    xs = lgp.unstructured_to_structured(X, names=['f0', 'f1', 'f2'])
+    theta = torch.tensor([np.log(1.5), 0.0, np.log(0.1)], dtype=torch.float64, requires_grad=True)
+    kern = torch.exp(theta[1]) ** 2 * lgp.Matern(nu=nu, scale=torch.exp(theta[0])) + torch.exp(theta[2]) ** 2 * lgp.White()
+    gp = lgp.GP(kern, checkpos=False, checksym=False).addx(xs, 'data')
+    ml = gp.marginal_likelihood({'data': y})
+    g, = torch.autograd.grad(ml, theta)
+    terms = [(1.0, [dict(kind='matern', nu=nu, scale=1.5)]), (0.01, [dict(kind='white')])]
+    Kg = gp.prior('data', raw=True)
+    Ko = ogp.gram(terms, X.T.copy(), X.T.copy())
+    assert np.max(np.abs(Kg - Ko) / np.abs(Ko)) < 2e-13
+    val_o, grad_o = ogp.logml_and_grad(terms, X.T.copy(), y, [('logscale', 0, 0), ('amp', 0), ('amp', 1)])
+    grad_o = np.array([grad_o[0], grad_o[1] * 2.0, grad_o[2] * 2 * 0.01])
+    assert abs(float(ml.detach()) + val_o) / abs(val_o) < 1e-9
+    assert rel(-g.numpy(), grad_o) < 1e-9
+
+
+def test_matern_order_edge_cases():
+    x = np.linspace(0, 3, 40)
+    # nu = 0: white noise (_matern.py:74); half-integer orders keep the closed form; nu > 100 refused, never a CPU fallback
+    K0 = lgp.Matern(nu=0)(x[:, None], x[None, :])
+    assert np.array_equal(K0, np.eye(40))
+    Kh = lgp.Matern(nu=1.5)(x[:, None], x[None, :])
+    Kc = lgp.Matern(nu=1.5 + 1e-9)(x[:, None], x[None, :])
+    assert np.max(np.abs(Kh - Kc)) < 1e-8
+    with pytest.raises(NotImplementedError):
+        lgp.Matern(nu=150.0)
+
+
+def test_empbayes_fit_fisher_vs_oracle():
+    """ method='fisher' (dogleg with Fisher information + prior precision as hessian; reference _fit.py:732-743,
+    765-769) reaches the same optimum as BFGS; the Fisher matrix equals the oracle's
+    1/2 tr(K^-1 dK_i K^-1 dK_j) + I (reference _decomp.py:535-558) with dK by central differences of the oracle Gram """
+    rng = np.random.default_rng(3005)
+    n = 300
+    X3 = rng.uniform(0, 100, (n, 2))
+    K3 = ogp.gram([(1.3 ** 2, [dict(kind='expquad', scale=8.0)])], X3.T.copy(), X3.T.copy())
+    y3 = np.linalg.cholesky(K3 + 1e-10 * np.eye(n)) @ rng.standard_normal(n) + 0.2 * rng.standard_normal(n)
+    x3 = lgp.unstructured_to_structured(X3, names=['a', 'b'])
+    hyperprior = {'log(ell)': (np.log(3), 1.0), 'log(sf)': (0.0, 1.0), 'log(sn)': (np.log(0.1), 1.0)}
+
+    def gpfactory(hp):
+        k = hp['sf'] ** 2 * lgp.ExpQuad(scale=hp['ell']) + hp['sn'] ** 2 * lgp.White()
+        return lgp.GP(k, checkpos=False, checksym=False).addx(x3, 'data')
+    fitg = lgp.empbayes_fit(hyperprior, gpfactory, {'data': y3}, raises=False)
+    fitf = lgp.empbayes_fit(hyperprior, gpfactory, {'data': y3}, raises=False, method='fisher', covariance='fisher')
+    assert np.max(np.abs(fitf.minresult.x - fitg.minresult.x)) < 1e-4
+    assert abs(fitf.minresult.fun - fitg.minresult.fun) / abs(fitg.minresult.fun) < 1e-8
+
+    def Kof(p):
+        hp = np.array([np.log(3), 0.0, np.log(0.1)]) + p
+        terms = [(np.exp(hp[1]) ** 2, [dict(kind='expquad', scale=np.exp(hp[0]))]),
+                 (np.exp(hp[2]) ** 2, [dict(kind='white')])]
+        return ogp.gram(terms, X3.T.copy(), X3.T.copy())
+    p = fitf.minresult.x
+    h = 1e-5
+    dK = np.stack([(Kof(p + h * e) - Kof(p - h * e)) / (2 * h) for e in np.eye(3)], axis=2)
+    do = odecomp.Chol(Kof(p))
+    fo = do.minus_log_normal_density(y3, dK=dK, fisher=True)[3] + np.eye(3)
+    assert rel(fitf.minresult.hess, fo) < 1e-6          # limited by the finite differences of the check
+    # covariance='fisher': inverse of that matrix, mapped to the hyperparameters (prior sdev 1: identity jacobian)
+    cov = np.array([[fitf.pcov[a, b] for b in hyperprior] for a in hyperprior])
+    assert rel(cov, np.linalg.inv(fo)) < 1e-5
+    # covariance='fisher' after a gradient fit evaluates the Fisher matrix at the optimum
+    fitc = lgp.empbayes_fit(hyperprior, gpfactory, {'data': y3}, raises=False, covariance='fisher')
+    covc = np.array([[fitc.pcov[a, b] for b in hyperprior] for a in hyperprior])
+    assert rel(covc, cov) < 1e-3

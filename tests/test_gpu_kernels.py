@@ -229,3 +229,61 @@ def test_gram_vjp_matches_finite_differences():
     full = _ops.gram_iso_vjp_general(descs(*p0), xd, xd, _ops.as_aligned(torch.tensor(Gs - np.outer(b, b)).to(dev())))
     low = _ops.gram_iso_vjp(descs(*p0), xd, _ops.as_aligned(torch.tensor(Gs).to(dev())), torch.tensor(b).to(dev()))
     np.testing.assert_allclose(low.cpu().numpy(), full.cpu().numpy(), rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize('kind,p', [('expquad', 0), ('maternp', 0), ('maternp', 1), ('maternp', 2), ('maternp', 3),
+                                    ('maternp', 4)])
+def test_gram_fast_vjp_vs_general(kind, p):
+    """the fused symmetric VJP (short in-kernel exp/sqrt where in range, library path elsewhere: diagonal, duplicated
+    points, far tails) against the general descriptor kernel on the same symmetric weights"""
+    rng = np.random.default_rng(14 + p)
+    n, d = 333, 3
+    x = rng.uniform(0, 10, (d, n))
+    x[:, 7] = x[:, 3]           # duplicated point: r2 == 0 off the diagonal
+    x[:, 11] = x[:, 12] + 400   # far point: exp underflows for ExpQuad
+    xd = torch.tensor(x).to(dev())
+    G = rng.standard_normal((n, n))
+    G = G + G.T
+    b = rng.standard_normal(n)
+    main = dict(kind=_lib.K_EXPQUAD if kind == 'expquad' else _lib.K_MATERNP, term=0, dimmask=7, ipar=p, par0=1e-30 if p % 2 else 0.0,
+                scale_x=1.7, scale_y=1.7, amp=1.3)
+    descs = [main, dict(kind=_lib.K_WHITE, term=1, dimmask=7, amp=0.01)]
+    low = _ops.gram_iso_vjp(descs, xd, _ops.as_aligned(torch.tensor(G).to(dev())), torch.tensor(b).to(dev())).cpu().numpy()
+    full = _ops.gram_iso_vjp_general(descs, xd, xd, _ops.as_aligned(torch.tensor(G - np.outer(b, b)).to(dev()))).cpu().numpy()
+    np.testing.assert_allclose(low, full, rtol=1e-11, atol=1e-11 * np.abs(full).max())
+
+
+def test_gram_jvp_matches_finite_differences_and_vjp():
+    """ lgp_gram_iso_jvp: dK along a tangent of (amp, log scale, par1) per factor; checked against central differences of
+    the Gram build and against the reverse-mode kernel through <G, JVP(t)> == <VJP(G), t> """
+    rng = np.random.default_rng(21)
+    n, m, d = 130, 97, 2
+    xd = torch.tensor(rng.uniform(0, 5, (d, n))).to(dev())
+    yd = torch.tensor(rng.uniform(0, 5, (d, m))).to(dev())
+
+    def descs(amp0, ls0, beta, amp2, ls2):
+        return [dict(kind=_lib.K_CAUCHY, term=0, dimmask=3, par0=2.0, par1=beta, scale_x=np.exp(ls0), scale_y=np.exp(ls0), amp=amp0),
+                dict(kind=_lib.K_MATERN, term=0, dimmask=1, par0=1.3, scale_x=2 * np.exp(ls0), scale_y=2 * np.exp(ls0)),
+                dict(kind=_lib.K_MATERNP, term=1, dimmask=2, ipar=2, par0=1e-30, scale_x=np.exp(ls2), scale_y=np.exp(ls2), amp=amp2),
+                dict(kind=_lib.K_WHITE, term=2, dimmask=3, amp=0.1)]
+    p0 = np.array([1.3, np.log(0.8), 2.5, 0.7, np.log(1.9)])
+    t = rng.standard_normal(5)
+    # tangent in the (nfactors, 3) layout: log scale of factors 0 and 1 move together
+    tan = np.zeros((4, 3))
+    tan[0] = [t[0], t[1], t[2]]
+    tan[1, 1] = t[1]
+    tan[2] = [t[3], t[4], 0.0]
+    D = _ops.gram_iso_jvp(descs(*p0), xd, yd, tan).cpu().numpy()
+    h = 1e-6
+    Kp = _ops.gram_iso(descs(*(p0 + h * t)), xd, yd).cpu().numpy()
+    Km = _ops.gram_iso(descs(*(p0 - h * t)), xd, yd).cpu().numpy()
+    fd = (Kp - Km) / (2 * h)
+    assert np.max(np.abs(D - fd)) < 1e-7 * np.max(np.abs(fd))
+    G = rng.standard_normal((n, m))
+    vjp = _ops.gram_iso_vjp_general(descs(*p0), xd, yd, _ops.as_aligned(torch.tensor(G).to(dev()))).cpu().numpy()
+    np.testing.assert_allclose((G * D).sum(), (vjp * tan).sum(), rtol=1e-11)
+    # Frobenius inner product kernel (Fisher contraction)
+    A = _ops.as_aligned(torch.tensor(G).to(dev()))
+    B = _ops.as_aligned(torch.tensor(D).to(dev()))
+    np.testing.assert_allclose(float(_ops.frob_dot(A, B)[0]), (G * D).sum(), rtol=1e-12)
+    np.testing.assert_allclose(float(_ops.frob_dot(A[:50, :33], B[:50, :33])[0]), (G[:50, :33] * D[:50, :33]).sum(), rtol=1e-12)

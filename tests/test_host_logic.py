@@ -29,7 +29,8 @@ def test_kernel_algebra_descriptor():
 
 def test_kernel_errors():
     with pytest.raises(NotImplementedError):
-        lgp.Matern(nu=1.3)
+        lgp.Matern(nu=130.0)
+    assert lgp.Matern(nu=1.3)._terms[0].factors[0].kind == 5 and lgp.Matern(nu=1.5)._terms[0].factors[0].kind == 1
     with pytest.raises(AssertionError):
         lgp.ExpQuad(scale=-1)
     with pytest.raises(AssertionError):
