@@ -236,6 +236,25 @@ int lgp_tile_potrf(lgp_stream_t stream, double *A, int64_t lda, int64_t t, doubl
 /* B (rows x t, ldb) <- B L^-T for a factored diagonal tile L (t x t, ldl) with its inverted diagonal blocks */
 int lgp_tile_trsm_right(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *B,
                         int64_t ldb, int64_t rows);
+
+/* Fused panel solve + broadcast over peer memory (block-cyclic Cholesky, step "TRSM -> broadcast of the panel slab"):
+ * same result in B as lgp_tile_trsm_right, and every final entry B[i][j] is also stored by the epilogue of the last
+ * product at dst[d] + i*ld_dst + j for d < n_dst (<= 8).  dst[d] are device addresses valid on THIS GPU: local buffers,
+ * buffers of peer GPUs mapped over NVLink (one store per peer), or, with multimem != 0, ONE NVSwitch multicast address
+ * (n_dst == 1; a single multimem.st reaches the buffer of every GPU of the group, the local one included).
+ * `dst` is a HOST array.  Replaces copy + ncclBroadcast of the slab; order readers with lgp_flag_signal/lgp_flag_wait. */
+int lgp_tile_trsm_right_bcast(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *B,
+                              int64_t ldb, int64_t rows, int n_dst, void *const *dst, int64_t ld_dst, int multimem);
+
+/* Cross-GPU ordering for the peer stores: monotone 64-bit counters living in peer-mapped memory.
+ * lgp_flag_signal: after everything enqueued before it on `stream` (system-scope fence), store `value` with release
+ *   semantics to each of the n (<= LGP_MAX_FLAGS) addresses flag_ptrs[i] (HOST array of device addresses, local or peer).
+ * lgp_flag_wait: block `stream` until flags[i] >= value for all i < n (acquire loads on LOCAL memory); after
+ *   timeout_ms without progress it gives up and sets *err = 1 (device int32, caller-initialised to 0) instead of
+ *   spinning forever. */
+#define LGP_MAX_FLAGS 16
+int lgp_flag_signal(lgp_stream_t stream, void *const *flag_ptrs, int n, uint64_t value);
+int lgp_flag_wait(lgp_stream_t stream, const uint64_t *flags, int n, uint64_t value, int64_t timeout_ms, int32_t *err);
 /* b (t contiguous doubles) <- L^-1 b (trans=0) or L^-T b (trans=1) */
 int lgp_tile_trsv(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *b,
                   int trans);

@@ -154,6 +154,27 @@ class _NullEvent:
         pass
 
 
+class _PeerBuffer:
+    """ one symmetric allocation: `nflags` 64-bit counters followed by doubles; addresses of the same offset on every
+    rank (peer mappings) and, where the NVSwitch supports it, through the multicast mapping """
+
+    def __init__(self, tensor, handle, nflags):
+        self.tensor, self.handle, self.nflags = tensor, handle, nflags
+        self.ptrs = [int(p) for p in handle.buffer_ptrs]
+        mc = getattr(handle, 'multicast_ptr', 0)
+        self.multicast = int(mc) if mc else 0
+        self.data = tensor[nflags:]
+
+    def flag_addr(self, rank, idx):
+        assert 0 <= idx < self.nflags
+        return self.ptrs[rank] + 8 * idx
+
+    def data_addr(self, rank, offset):
+        """ address on `rank` (or through the multicast mapping: rank = 'mc') of double `offset` of the data area """
+        base = self.multicast if rank == 'mc' else self.ptrs[rank]
+        return base + 8 * (self.nflags + offset)
+
+
 class CudaTileOps:
     """ local operations of DistChol on the rank's GPU through the C ABI (include/lgp_b200.h, lgp_dist_*/lgp_tile_*) """
 
@@ -282,6 +303,36 @@ class CudaTileOps:
         self._ck(self.lib.lgp_dist_trailing_update(self._sp(), ctypes.byref(g), self._p(A), A.stride(0), k, arr,
                                                    lj_begin, lj_end), 'lgp_dist_trailing_update')
 
+    # ---- peer memory (fused panel solve + broadcast)
+    NFLAGS = 64  # 64-bit counters at the head of the symmetric buffer
+
+    def peer_setup(self, count, group):
+        """ symmetric buffer of NFLAGS counters + `count` doubles on every rank of the group, mapped into every
+        peer over NVLink (torch symmetric memory is the allocator/rendezvous plumbing; all data movement and
+        signalling on it is done by liblgpb200 kernels).  Returns a _PeerBuffer or raises. """
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(self.NFLAGS + count, dtype=torch.float64, device=self.device)
+        t[:self.NFLAGS].zero_()
+        h = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+        return _PeerBuffer(t, h, self.NFLAGS)
+
+    def trsm_right_bcast(self, L, invd, B, dst_ptrs, ld_dst, multimem):
+        T = L.shape[0]
+        if B.shape[0] == 0:
+            return
+        arr = (ctypes.c_void_p * len(dst_ptrs))(*dst_ptrs)
+        self._ck(self.lib.lgp_tile_trsm_right_bcast(self._sp(), self._p(L), L.stride(0), self._p(invd), T, self._p(B),
+                                                    B.stride(0), B.shape[0], len(dst_ptrs), arr, ld_dst,
+                                                    int(bool(multimem))), 'lgp_tile_trsm_right_bcast')
+
+    def flag_signal(self, ptrs, value):
+        arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        self._ck(self.lib.lgp_flag_signal(self._sp(), arr, len(ptrs), int(value)), 'lgp_flag_signal')
+
+    def flag_wait(self, addr, n, value, timeout_ms, err):
+        self._ck(self.lib.lgp_flag_wait(self._sp(), ctypes.c_void_p(addr), n, int(value), int(timeout_ms),
+                                        self._p(err)), 'lgp_flag_wait')
+
     # ---- solves
     def trsv_tile(self, L, invd, b, trans):
         T = L.shape[0]
@@ -314,7 +365,7 @@ class DistChol:
     """
 
     def __init__(self, descs, x, *, tile=512, grid=None, group=None, epsrel='auto', epsabs=0.0, ops=None,
-                 check=True, timers=None):
+                 check=True, timers=None, peer='auto'):
         if dist.is_available() and dist.is_initialized():
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         else:
@@ -328,6 +379,7 @@ class DistChol:
         self.ops = ops if ops is not None else CudaTileOps(x.device)
         ops = self.ops
         self._timers = timers
+        self._peer_opt = peer
 
         # ---- Gram matrix, generated in place by the owner of each tile
         self._mark('start')
@@ -391,7 +443,17 @@ class DistChol:
         TT = T * T
         # double-buffered broadcast buffers: diagonal tile (+ inverted blocks) and one panel slab per process row
         diagbuf = [ops.empty(TT + nb * 128 * 128) for _ in range(2)] if Pr > 1 else None
-        slab = [[ops.empty(max(lay.panel_count(0, r), 1) * TT) for r in range(Pr)] for _ in range(2)]
+        slab_cap = max(max(lay.panel_count(0, r) for r in range(Pr)), 1) * TT
+        pb = self._peer_init(2 * Pr * slab_cap)
+        self.peer_mode = 'nccl' if pb is None else ('multimem' if self._multimem else 'p2p')
+        if pb is None:
+            slab = [[ops.empty(max(lay.panel_count(0, r), 1) * TT) for r in range(Pr)] for _ in range(2)]
+        else:
+            # slabs live in the symmetric buffer: the panel TRSM stores its result straight into the slab of every GPU
+            soff = lambda s_, r_: (s_ * Pr + r_) * slab_cap
+            slab = [[pb.data[soff(s_, r_):soff(s_, r_) + slab_cap] for r_ in range(Pr)] for s_ in range(2)]
+            READY, DONE = 0, 16  # counter indices: READY + process row (slab landed), DONE + rank (update finished)
+            perr = self._peer_err
         col_ready = {0: None}
         buf_free = [None, None]
         for k in range(NT):
@@ -427,21 +489,38 @@ class DistChol:
                     self._bcast(db, lay.rank_of(prow, pcol))
                     Lkk, invd_k = db[:TT].view(T, T), db[TT:]
                 cnt = lay.panel_count(k)
-                if in_col and cnt > 0:
-                    ops.trsm_right(Lkk, invd_k, A[li0 * T:, lkc * T:(lkc + 1) * T])
-                for r in range(Pr):
-                    c_r = lay.panel_count(k, r)
-                    if c_r == 0:
-                        continue
-                    buf = slab[set_][r][:c_r * TT]
-                    if in_col and pr == r:
-                        ops.copy2d(A[li0 * T:, lkc * T:(lkc + 1) * T], buf.view(c_r * T, T))
-                    self._bcast(buf, lay.rank_of(r, pcol))
+                if pb is not None:
+                    # fused solve + broadcast: the epilogue of the TRSM stores every solved entry into slab (set, pr) of
+                    # ALL GPUs (one multimem.st through the NVSwitch, or one NVLink store per peer), then a release
+                    # store of the step counter tells every consumer that the slab has landed
+                    if in_col and cnt > 0:
+                        if k >= 2:  # the slab set of step k - 2 is reused: every GPU must be done reading it
+                            ops.flag_wait(pb.flag_addr(self.rank, DONE), self.world, k - 1, self.PEER_TIMEOUT_MS, perr)
+                        off = soff(set_, pr)
+                        dst = [pb.data_addr('mc', off)] if self._multimem else \
+                            [pb.data_addr(q, off) for q in range(self.world)]
+                        ops.trsm_right_bcast(Lkk, invd_k, A[li0 * T:, lkc * T:(lkc + 1) * T], dst, T, self._multimem)
+                        ops.flag_signal([pb.flag_addr(q, READY + pr) for q in range(self.world)], k + 1)
+                else:
+                    if in_col and cnt > 0:
+                        ops.trsm_right(Lkk, invd_k, A[li0 * T:, lkc * T:(lkc + 1) * T])
+                    for r in range(Pr):
+                        c_r = lay.panel_count(k, r)
+                        if c_r == 0:
+                            continue
+                        buf = slab[set_][r][:c_r * TT]
+                        if in_col and pr == r:
+                            ops.copy2d(A[li0 * T:, lkc * T:(lkc + 1) * T], buf.view(c_r * T, T))
+                        self._bcast(buf, lay.rank_of(r, pcol))
                 panel_done = ops.event()
                 panel_done.record()
             # ---------------- trailing update k (main stream)
             with ops.main_stream():
                 panel_done.wait()
+                if pb is not None and k + 1 < NT:
+                    for r in range(Pr):
+                        if lay.panel_count(k, r) > 0:
+                            ops.flag_wait(pb.flag_addr(self.rank, READY + r), 1, k + 1, self.PEER_TIMEOUT_MS, perr)
                 if k + 1 < NT:
                     panels = slab[set_]
                     nxt_c = (k + 1) % Pc
@@ -458,12 +537,60 @@ class DistChol:
                 ev = ops.event()
                 ev.record()
                 buf_free[set_] = ev
+                if pb is not None:
+                    ops.flag_signal([pb.flag_addr(q, DONE + self.rank) for q in range(self.world)], k + 1)
             col_ready.pop(k, None)
         with ops.main_stream():
             for ev in buf_free:
                 if ev is not None:
                     ev.wait()
+        if pb is not None:
+            # peers may still be storing counters into this GPU's buffer: nobody releases it before everybody is done
+            ops.synchronize()
+            dist.barrier(group=self.group)
+            bad = perr.clone()
+            self._allreduce(bad, op=dist.ReduceOp.MAX)
+            self._peer_buffer = pb
+            if int(bad.item()):
+                raise RuntimeError('DistChol: timed out waiting for a peer GPU (panel slab / completion counter)')
         self._allreduce(self.dvec)
+
+    PEER_TIMEOUT_MS = 30000
+
+    def _peer_init(self, count):
+        """ symmetric (peer-mapped) slab buffers for the fused TRSM -> broadcast path, or None to use NCCL broadcasts.
+        peer='auto' (default): use peer memory when the provider offers it and every rank managed to set it up;
+        True: require it; False: never.  Environment: LGP_DIST_PEER=0/1 overrides 'auto', LGP_DIST_MULTIMEM=0 forces
+        one NVLink store per peer instead of NVSwitch multicast stores. """
+        import os
+        opt = self._peer_opt
+        if opt == 'auto' and os.environ.get('LGP_DIST_PEER') is not None:
+            opt = os.environ['LGP_DIST_PEER'] not in ('0', 'false', 'no', '')
+        self._multimem = False
+        capable = self.world > 1 and self.world <= 8 and hasattr(self.ops, 'peer_setup')
+        if opt is False or not capable:
+            if opt is True and self.world > 1:
+                raise RuntimeError('DistChol(peer=True): peer memory is not available with this provider / world size')
+            return None
+        pb, ok = None, 1
+        try:
+            pb = self.ops.peer_setup(count, self.group)
+        except Exception:
+            if opt is True:
+                raise
+            ok = 0
+        mc = 1 if (pb is not None and pb.multicast and os.environ.get('LGP_DIST_MULTIMEM', '1') != '0') else 0
+        flags = torch.tensor([ok, mc], dtype=torch.int32, device=self.ops.device)
+        self._allreduce(flags, op=dist.ReduceOp.MIN)
+        ok, mc = (int(v) for v in flags.cpu())
+        if not ok:
+            return None
+        self._multimem = bool(mc)
+        self._peer_err = self.ops.zeros(1, dtype=torch.int32)
+        # every rank has zeroed its counters before anyone signals
+        self.ops.synchronize()
+        dist.barrier(group=self.group)
+        return pb
 
     def factor_ms(self):
         """ device time of the factorisation loop on this rank (CUDA events on the main stream), or None """

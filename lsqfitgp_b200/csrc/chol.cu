@@ -379,6 +379,12 @@ struct CholCtx {
     int32_t *info;
     int rc;
     int j0base = 0;  // global index of row 0 of W (tile-wise use: pivots and dvec are indexed globally)
+    GemmMirror mir = {};  // extra destinations of the solved panel (lgp_tile_trsm_right_bcast); column 0 = column 0 of B
+};
+
+struct FlagPtrs {
+    int n;
+    unsigned long long *p[LGP_MAX_FLAGS];
 };
 
 #define RC(x)                   \
@@ -394,22 +400,31 @@ static inline double *Wp(const CholCtx &c, int rb, int cb) { return c.W + (int64
 
 // X * Lt^T = B in place for the nb-block triangle Lt (pointer to its top-left, ld ldl; inverted 128x128 diagonal
 // blocks in invd); B points at the `rows` x nb*128 block to be solved (ld ldb)
+// `col0`: column of B relative to the panel origin (offset of the mirror destinations, which receive the final value of
+// every 128-column block from the epilogue of its last product)
 static void trsm_right_ptr(CholCtx &c, double *B, int64_t ldb, int rows, const double *Lt, int64_t ldl,
-                           const double *invd, int nb) {
+                           const double *invd, int nb, int col0 = 0) {
     if (c.rc) return;
     if (nb == 1) {
+        if (c.mir.n) {
+            GemmMirror m = c.mir;
+            for (int i = 0; i < m.n; i++) m.dst[i] += col0;
+            RC(gemm_launch(c.st, true, true, rows, NB, NB, 1.0, B, ldb, invd, NB, B, ldb,
+                           GEMM_BETA0 | GEMM_B_LOWER_K | GEMM_INPLACE_A, &m));
+            return;
+        }
         RC(gemm_launch(c.st, true, true, rows, NB, NB, 1.0, B, ldb, invd, NB, B, ldb,
                        GEMM_BETA0 | GEMM_B_LOWER_K | GEMM_INPLACE_A));
         return;
     }
     int n1 = nb / 2, n2 = nb - n1;
-    trsm_right_ptr(c, B, ldb, rows, Lt, ldl, invd, n1);
+    trsm_right_ptr(c, B, ldb, rows, Lt, ldl, invd, n1, col0);
     if (c.rc) return;
     // B2 -= B1 * L21^T
     RC(gemm_launch(c.st, true, true, rows, n2 * NB, n1 * NB, -1.0, B, ldb, Lt + (int64_t)n1 * NB * ldl, ldl,
                    B + (int64_t)n1 * NB, ldb, 0));
     trsm_right_ptr(c, B + (int64_t)n1 * NB, ldb, rows, Lt + (int64_t)n1 * NB * ldl + (int64_t)n1 * NB, ldl,
-                   invd + (int64_t)n1 * NB * NB, n2);
+                   invd + (int64_t)n1 * NB * NB, n2, col0 + n1 * NB);
 }
 
 // X * Lt[jb..jb+nb, jb..jb+nb]^T = B in place; B = W[rb.., jb..] with `rows` rows
@@ -1032,6 +1047,76 @@ int lgp_tile_trsm_right(lgp_stream_t stream, const double *L, int64_t ldl, const
     CholCtx c{(cudaStream_t)stream, nullptr, 0, nullptr, nullptr, nullptr, LGP_OK};
     trsm_right_ptr(c, B, ldb, (int)rows, L, ldl, invd, (int)(t / NB));
     return c.rc;
+}
+
+int lgp_tile_trsm_right_bcast(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *B,
+                              int64_t ldb, int64_t rows, int n_dst, void *const *dst, int64_t ld_dst, int multimem) {
+    if (t < NB || t % NB || rows < 0 || rows > (1 << 30) || !L || !invd || !B) return LGP_ERR_BADARG;
+    if (n_dst < 0 || n_dst > GEMM_MAX_MIRRORS || (n_dst && (!dst || ld_dst < t)) || (multimem && n_dst != 1))
+        return LGP_ERR_BADARG;
+    if (rows == 0) return LGP_OK;
+    CholCtx c{(cudaStream_t)stream, nullptr, 0, nullptr, nullptr, nullptr, LGP_OK};
+    c.mir.n = n_dst;
+    c.mir.multimem = multimem ? 1 : 0;
+    c.mir.ld = ld_dst;
+    for (int i = 0; i < n_dst; i++) {
+        if (!dst[i]) return LGP_ERR_BADARG;
+        c.mir.dst[i] = (double *)dst[i];
+    }
+    trsm_right_ptr(c, B, ldb, (int)rows, L, ldl, invd, (int)(t / NB));
+    return c.rc;
+}
+
+// ---- cross-GPU flags (monotone counters in peer-mapped memory) ordering the peer stores above against their readers
+__global__ void flag_signal_kernel(FlagPtrs f, unsigned long long value) {
+    const int i = threadIdx.x;
+    if (i < f.n) {
+        __threadfence_system();  // stores of the preceding kernels of this stream (kernel boundary) before the flag
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.p[i]), "l"(value) : "memory");
+    }
+}
+
+__global__ void flag_wait_kernel(const unsigned long long *flags, int n, unsigned long long value,
+                                 unsigned long long timeout_ns, int *err) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + i) : "memory");
+        if (v >= value) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+            atomicExch(err, 1);  // the caller checks this flag: never spin forever on a peer that will not arrive
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
+int lgp_flag_signal(lgp_stream_t stream, void *const *flag_ptrs, int n, uint64_t value) {
+    if (n < 0 || n > LGP_MAX_FLAGS || (n && !flag_ptrs)) return LGP_ERR_BADARG;
+    if (n == 0) return LGP_OK;
+    FlagPtrs f;
+    f.n = n;
+    for (int i = 0; i < n; i++) {
+        if (!flag_ptrs[i] || (reinterpret_cast<uintptr_t>(flag_ptrs[i]) & 7)) return LGP_ERR_BADARG;
+        f.p[i] = (unsigned long long *)flag_ptrs[i];
+    }
+    flag_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, (unsigned long long)value);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+int lgp_flag_wait(lgp_stream_t stream, const uint64_t *flags, int n, uint64_t value, int64_t timeout_ms, int32_t *err) {
+    if (n < 0 || n > LGP_MAX_FLAGS || (n && !flags) || !err || timeout_ms < 0) return LGP_ERR_BADARG;
+    if (n == 0) return LGP_OK;
+    flag_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long *)flags, n, (unsigned long long)value,
+                                                         (unsigned long long)timeout_ms * 1000000ull, err);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
 }
 
 int lgp_tile_trsv(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *b,

@@ -1,6 +1,7 @@
 // Launcher for the FP64 DMMA GEMM (see gemm_dmma.cuh).
 #include "gemm_dmma.cuh"
 #include "internal.h"
+#include <string.h>
 
 namespace lgp {
 
@@ -33,8 +34,9 @@ static int launch_layout(cudaStream_t stream, bool a_kmaj, bool b_kmaj, GemmPara
 
 // Host-side launcher (internal; the C ABI wrapper is lgp_dgemm in capi.cu).
 int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int K, double alpha, const double *A,
-                int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int flags) {
+                int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int flags, const GemmMirror *mir) {
     if (M <= 0 || N <= 0) return LGP_OK;
+    if (mir && (mir->n < 0 || mir->n > GEMM_MAX_MIRRORS || (mir->multimem && mir->n != 1))) return LGP_ERR_BADARG;
     if ((lda & 1) || (ldb & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return LGP_ERR_ALIGN;
     if ((flags & GEMM_LOWER) && M != N) return LGP_ERR_BADARG;
@@ -46,6 +48,10 @@ int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.alpha = alpha;
     p.flags = flags;
+    if (mir)
+        p.mir = *mir;
+    else
+        memset(&p.mir, 0, sizeof(p.mir));
     // tile configuration: the in-place products need the aliased dimension inside one tile
     if (flags & GEMM_INPLACE_B) {
         if (a_kmaj && !b_kmaj) return launch_cfg<GemmWide, true, false>(stream, p);

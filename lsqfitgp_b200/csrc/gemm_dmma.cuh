@@ -34,6 +34,18 @@ enum GemmFlags : int {
     GEMM_FORCE_BIG = 256,  // always use the 128x128 configuration
 };
 
+// Extra destinations of the epilogue (fused compute -> broadcast over peer memory): every C entry is also stored at
+// dst[i] + row*ld + col.  dst[i] are device pointers valid on THIS GPU: local memory, peer memory mapped over
+// NVLink (unicast, one store per peer), or ONE NVSwitch multicast address (`multimem` != 0: a single multimem.st
+// reaches every GPU of the group).  Used by the panel TRSM of the block-cyclic Cholesky (dist.cu).
+constexpr int GEMM_MAX_MIRRORS = 8;
+struct GemmMirror {
+    int n;         // number of destinations (0: none)
+    int multimem;  // destinations are multicast addresses
+    int64_t ld;
+    double *dst[GEMM_MAX_MIRRORS];
+};
+
 struct GemmParams {
     const double *A;
     const double *B;
@@ -43,7 +55,16 @@ struct GemmParams {
     double alpha;
     int flags;
     int tiles_m, tiles_n;
+    GemmMirror mir;
 };
+
+__device__ __forceinline__ void gemm_mirror_store(const GemmMirror &m, int64_t off, double v) {
+    if (m.multimem) {
+        asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(m.dst[0] + off), "d"(v) : "memory");
+    } else {
+        for (int i = 0; i < m.n; i++) m.dst[i][off] = v;
+    }
+}
 
 constexpr int GEMM_BK = 16;
 
@@ -310,6 +331,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS) gemm_dmma_kernel
                     if (!beta0) v1 += crow[col + 1];
                     crow[col + 1] = v1;
                 }
+            }
+            if (p.mir.n) {
+                const int64_t off = (int64_t)row * p.mir.ld + col;
+                gemm_mirror_store(p.mir, off, v0);
+                if (col + 1 < cmax) gemm_mirror_store(p.mir, off + 1, v1);
             }
         }
     }

@@ -67,9 +67,11 @@ def _torchrun(nproc, *args, timeout=600):
 
 
 @pytest.mark.parametrize('nproc,grid', [(2, '2x1'), (2, '1x2'), (4, '2x2'), (8, '2x4')])
-def test_distchol_multi_rank_vs_oracle(nproc, grid):
+@pytest.mark.parametrize('peer', ['off', 'on'])
+def test_distchol_multi_rank_vs_oracle(nproc, grid, peer):
+    """ peer=off: NCCL panel broadcasts; peer=on: fused TRSM -> peer-memory stores (multimem / NVLink) with counters """
     if torch.cuda.device_count() < nproc:
         pytest.skip(f'needs {nproc} GPUs')
-    res = _torchrun(nproc, '--size', '3000', '--tile', '256', '--grid', grid, '--oracle')
+    res = _torchrun(nproc, '--size', '3000', '--tile', '256', '--grid', grid, '--oracle', '--peer', peer)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert 'DIST_CHECK_OK' in res.stdout
