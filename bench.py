@@ -38,6 +38,9 @@ FP64_DMMA_PEAK_TFLOPS = 37.0   # measured on this pool's B200 with tools/peaks_f
                                # MEASURED_PEAKS.json has no FP64 entry
 
 
+CHOL_TRAFFIC_BYTES_N20000 = 62.88e9  # measured, see roofline.traffic_source
+
+
 def make_data(n, seed=2002):
     """ SURVEY.md section 8(d), config C2 """
     rng = np.random.default_rng(seed)
@@ -151,6 +154,7 @@ def dist_chol_measure(n, tile, dev, rank, world, reps=1):
     w = _dist.DistChol(descs, Xh[:, :4096].to(dev), tile=min(tile, 512))
     w.solve(bh[:4096].to(dev))
     del w
+    _dist.peer_reserve(n, tile, dev)  # pooled peer-mapped slab buffers of the fused TRSM -> broadcast path (allocation)
     best = None
     for _ in range(reps):
         sync()
@@ -179,17 +183,20 @@ def dist_chol_measure(n, tile, dev, rank, world, reps=1):
         r = Ks @ sol + float(dc._epsout[1].item()) * (dc.s[idx] ** 2) * sol[idx] - bh.to(dev)[idx]
         best['resid_sampled'] = float(r.norm().item() / bh[idx.cpu()].norm().item())
         grid = [dc.lay.Pr, dc.lay.Pc]
+        peer_mode = getattr(dc, 'peer_mode', 'nccl')
         del dc, sol, Ks
         torch.cuda.empty_cache()
     flops = n ** 3 / 3
     tf = flops / (best['factor_ms'] * 1e-3) / 1e12
-    return dict(n=n, tile=tile, grid=grid, n_gpus=world, factor_ms=best['factor_ms'], factor_TFLOPs=tf,
+    return dict(n=n, tile=tile, grid=grid, n_gpus=world, panel_broadcast=peer_mode, factor_ms=best['factor_ms'],
+                factor_TFLOPs=tf,
                 per_gpu_TFLOPs=tf / world, frac_of_dmma_peak=tf / world / FP64_DMMA_PEAK_TFLOPS,
                 e2e_ms=best['e2e_ms'], e2e_TFLOPs=flops / (best['e2e_ms'] * 1e-3) / 1e12,
                 solve_ms=best['solve_ms'], logdet=best['logdet'], resid_sampled=best['resid_sampled'],
                 h2d_bytes=n * 2 * 8, d2h_bytes=8,
                 note='n^3/3 flop; Gram generated in place by tile owners; e2e = H2D of points + Gram + equilibration + '
-                     'factor + logdet readback')
+                     'factor + logdet readback; panel_broadcast: multimem = TRSM epilogue stores through the NVSwitch '
+                     'multicast mapping, p2p = one NVLink store per peer, nccl = copy + ncclBroadcast')
 
 
 class ClockSampler(threading.Thread):
@@ -355,6 +362,46 @@ def run_gpu(args):
     t_e2e = time.perf_counter() - t0
     barrier()
 
+    # ---- batch arm (extra key, not the headline): independent hyperparameter points of one batch kept `in_flight` at a
+    # time on this GPU (one host thread + stream per slot, lsqfitgp_b200._dist.eval_concurrent): throughput of the same
+    # evaluations when the panel chains of one factorisation overlap the GEMMs of another
+    batch = None
+    if args.in_flight > 1:
+        from lsqfitgp_b200 import _dist
+        nb = max(args.steps, 2 * args.in_flight)
+        Ks = [K] + [_ops.aligned_empty(n, n, dev) for _ in range(args.in_flight - 1)]
+
+        def batch_fun(item):
+            i, theta = item
+            descs = descs_for(theta)
+            Ki = Ks[i % args.in_flight]
+            _ops.gram_iso(descs, xd, xd, out=Ki, symmetric=True)
+            st = _ops.chol_factor(Ki)
+            a = _ops.chol_solve(st, yd[:, None], False)
+            ldq = _ops.chol_logdet_quad(st, a[:, 0].contiguous())
+            b = _ops.chol_solve(st, a, True, inplace=True)
+            Kinv = _ops.chol_inverse(st)
+            vjp = _ops.gram_iso_vjp(descs, xd, Kinv, b[:, 0].contiguous())
+            return finish(theta, ldq, vjp)
+        items = [(i, theta_for(rank, i)) for i in range(nb)]
+        _dist.eval_concurrent(batch_fun, items[:args.in_flight], args.in_flight, dev)  # warm-up: per-stream setup
+        barrier()
+        t0 = time.perf_counter()
+        res = _dist.eval_concurrent(batch_fun, items, args.in_flight, dev)
+        torch.cuda.synchronize()
+        t_batch = time.perf_counter() - t0
+        barrier()
+        v0, g0 = finish(items[0][1], *results[0]) if args.steps else (None, None)
+        if v0 is not None:  # same point as step 0 of the device arm: same value
+            assert abs(res[0][0] - v0) <= 1e-12 * abs(v0), (res[0][0], v0)
+        del Ks
+        if world > 1:
+            tb = torch.tensor([t_batch], dtype=torch.float64, device=dev)
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+            t_batch = float(tb.item())
+        batch = dict(value=nb * world / t_batch, unit=UNIT, in_flight=args.in_flight, evaluations_per_gpu=nb,
+                     timing='host wall clock between device synchronisations (several streams)')
+
     if world > 1:
         tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -388,7 +435,12 @@ def run_gpu(args):
             gpu_launches=int(launches),
             roofline=dict(bound='tensor', kernel='gemm_dmma_kernel (Cholesky phase: lgp_chol_factor)',
                           achieved=chol_tflops, peak=FP64_DMMA_PEAK_TFLOPS, unit='TFLOP/s',
-                          frac=chol_tflops / FP64_DMMA_PEAK_TFLOPS, traffic=None,
+                          frac=chol_tflops / FP64_DMMA_PEAK_TFLOPS,
+                          traffic=CHOL_TRAFFIC_BYTES_N20000 if n == 20000 else None,
+                          traffic_source='ncu dram__bytes_read.sum + dram__bytes_write.sum over the kernels of one '
+                                         'lgp_chol_factor call at n=20000 (profiles/traffic_chol20k_r1.txt): 42.8 GB read + '
+                                         '20.1 GB written; the rank-512 right-looking update inherently re-reads the '
+                                         'trailing matrix once per panel (~43 GB); tensor-bound, not HBM-bound',
                           peak_source='measured FP64 DMMA.8x8x4 register-resident loop, tools/peaks_fp64.cu '
                                       '(MEASURED_PEAKS.json has no FP64 entry)',
                           algorithmic_flops_per_launch=n ** 3 / 3),
@@ -399,6 +451,8 @@ def run_gpu(args):
                              vjp_GBps=4 * n * n / (phase_ms['vjp'] * 1e-3) / 1e9,
                              step_TFLOPs=n ** 3 / (t_dev / args.steps) / 1e12 / world * world),
         )
+        if batch is not None:
+            line['batch_throughput'] = batch
         if dist_chol is not None:
             line['dist_chol'] = dist_chol
         if world == 1 and not args.no_cpu_baseline:
@@ -421,6 +475,8 @@ def main():
     ap.add_argument('--dist-n', type=int, default=150000,
                     help='N > 1 only: size of the block-cyclic multi-GPU Cholesky reported under "dist_chol" (0 = skip)')
     ap.add_argument('--dist-tile', type=int, default=1024)
+    ap.add_argument('--in-flight', type=int, default=2,
+                    help='extra key batch_throughput: the same evaluations with this many in flight per GPU (0: skip)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

@@ -25,7 +25,7 @@ import numpy
 import torch
 import torch.distributed as dist
 
-__all__ = ['shard_indices', 'eval_batch_sharded', 'Layout', 'default_grid', 'DistChol', 'CudaTileOps']
+__all__ = ['shard_indices', 'eval_concurrent', 'eval_batch_sharded', 'peer_reserve', 'Layout', 'default_grid', 'DistChol', 'CudaTileOps']
 
 INT_MAX = 2 ** 31 - 1
 
@@ -35,12 +35,53 @@ def shard_indices(nitems, rank, world):
     return list(range(rank, nitems, world))
 
 
-def eval_batch_sharded(fun, thetas, *, group=None, device=None):
+def eval_concurrent(fun, items, in_flight, device=None):
+    """[fun(item) for item in items] with up to `in_flight` evaluations in flight on one GPU: one host thread and one
+    CUDA stream per slot (slot c takes items c, c + in_flight, ...).  Independent evaluations overlap on the device: the
+    latency-bound panel chains and recursion leaves of one factorisation fill the SMs left idle by another (measured
+    on B200, logML+gradient: n = 4096 +78 %, n = 10000 +33 %, n = 20000 +4 % with 2-4 in flight).  `fun` must not
+    share mutable state between calls; the C library keeps one panel stream per caller stream."""
+    items = list(items)
+    in_flight = max(1, min(int(in_flight), len(items)))
+    if in_flight == 1:
+        return [fun(it) for it in items]
+    import threading
+    out = [None] * len(items)
+    errors = []
+    cuda = device is not None and torch.device(device).type == 'cuda'
+
+    def worker(slot):
+        try:
+            if cuda:
+                stream = torch.cuda.Stream(device)
+                with torch.cuda.device(device), torch.cuda.stream(stream):
+                    for i in range(slot, len(items), in_flight):
+                        out[i] = fun(items[i])
+                    stream.synchronize()
+            else:
+                for i in range(slot, len(items), in_flight):
+                    out[i] = fun(items[i])
+        except BaseException as e:  # re-raised in the caller's thread
+            errors.append(e)
+    if cuda:
+        torch.cuda.synchronize(device)  # work queued by the caller precedes the workers' streams
+    threads = [threading.Thread(target=worker, args=(c,)) for c in range(in_flight)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out
+
+
+def eval_batch_sharded(fun, thetas, *, group=None, device=None, in_flight=1):
     """Evaluate ``fun(theta) -> 1-d array of fixed length`` on every row of `thetas`, sharded over the ranks of
     the process group; every rank returns the full (B, len) array.
 
     Works without an initialised process group (single process).  With the NCCL backend pass the rank's CUDA
-    device as `device`; with gloo leave it None (CPU tensors)."""
+    device as `device`; with gloo leave it None (CPU tensors).  `in_flight` > 1 keeps that many of the rank's
+    evaluations in flight at once (see `eval_concurrent`)."""
     thetas = numpy.asarray(thetas, dtype=float)
     B = thetas.shape[0]
     if dist.is_available() and dist.is_initialized():
@@ -48,7 +89,8 @@ def eval_batch_sharded(fun, thetas, *, group=None, device=None):
     else:
         rank, world = 0, 1
     mine = shard_indices(B, rank, world)
-    local = [numpy.asarray(fun(thetas[i]), dtype=float).reshape(-1) for i in mine]
+    local = [numpy.asarray(v, dtype=float).reshape(-1)
+             for v in eval_concurrent(fun, [thetas[i] for i in mine], in_flight, device)]
     width = None
     if local:
         width = local[0].size
@@ -361,6 +403,25 @@ class CudaTileOps:
 # ---------------------------------------------------------------------------------------------------------------
 # the distributed decomposition
 # ---------------------------------------------------------------------------------------------------------------
+
+def peer_reserve(n, tile, device, *, grid=None, group=None):
+    """ Allocate (or grow) the pooled peer-mapped slab buffers that `DistChol(..., tile=tile)` of size n will use, so
+    that the allocation + rendezvous (about a second) does not land inside a timed factorisation.  Collective over
+    the group; a no-op without a process group or when peer memory is unavailable. """
+    if not (dist.is_available() and dist.is_initialized()):
+        return False
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world < 2 or world > 8:
+        return False
+    Pr, Pc = grid if grid is not None else default_grid(world)
+    lay = Layout(n, tile, Pr, Pc, rank)
+    slab_cap = max(max(lay.panel_count(0, r) for r in range(Pr)), 1) * lay.T * lay.T
+    try:
+        CudaTileOps(device).peer_setup(2 * Pr * slab_cap, group)
+        return True
+    except Exception:
+        return False
+
 
 class DistChol:
     """Block-cyclic Cholesky of the Gram matrix of `descs` on the points `x`, sharded over the process group.

@@ -4,6 +4,7 @@
 // Reference semantics: src/lsqfitgp/_linalg/_decomp.py:245-255 (_parseeps), :349-361
 // (eigval_bound, diag_scale_pow2), :380-393 (Chol.__init__), :398-439 (solves), :466-472.
 #include <limits.h>
+#include <mutex>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -455,20 +456,33 @@ static void potrf_rec(CholCtx &c, int jb, int nb) {
 //   panel stream (high priority): diagonal-block potrf + TRSM of the block column below it;
 //   main stream: trailing SYRK, split into "next block column" (releases the next panel) and "rest".
 // The panel chain of small launches overlaps the big trailing update of the previous panel.
-static cudaStream_t panel_stream() {
-    static cudaStream_t s = nullptr;
-    static bool init = false;
-    if (!init) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) s = nullptr;
-        init = true;
+// One panel stream per caller stream (up to 8; concurrent factorisations issued from different streams / host threads, e.g.
+// a batch of hyperparameter points in flight, must not serialise their panel chains behind each other).
+static cudaStream_t panel_stream(cudaStream_t caller) {
+    static std::mutex mu;
+    static struct {
+        cudaStream_t caller, s;
+        bool used;
+    } pool[8];
+    std::lock_guard<std::mutex> lock(mu);
+    int free_slot = -1;
+    for (int i = 0; i < 8; i++) {
+        if (pool[i].used && pool[i].caller == caller) return pool[i].s;
+        if (!pool[i].used && free_slot < 0) free_slot = i;
     }
+    if (free_slot < 0) return pool[0].s;  // more than 8 caller streams: share (still correct, ordered by events)
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    pool[free_slot].caller = caller;
+    pool[free_slot].s = s;
+    pool[free_slot].used = true;
     return s;
 }
 
 static int potrf_lookahead(CholCtx &cm, int nblk, int pb) {
-    cudaStream_t ps = panel_stream();
+    cudaStream_t ps = panel_stream(cm.st);
     if (!ps || nblk <= pb) {
         potrf_rec(cm, 0, nblk);
         return cm.rc;
@@ -805,8 +819,10 @@ struct InvCtx {
 // fill the GPU (the recursion issues ~3 launches per 128-block, strictly ordered on a single stream otherwise).
 constexpr int TRTRI_FORK_DEPTH = 4;
 static cudaStream_t trtri_side_stream(int idx) {
+    static std::mutex mu;
     static cudaStream_t pool[1 << TRTRI_FORK_DEPTH];
     static bool init[1 << TRTRI_FORK_DEPTH];
+    std::lock_guard<std::mutex> lock(mu);
     if (!init[idx]) {
         if (cudaStreamCreateWithFlags(&pool[idx], cudaStreamNonBlocking) != cudaSuccess) pool[idx] = nullptr;
         init[idx] = true;

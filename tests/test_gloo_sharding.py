@@ -3,6 +3,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -76,3 +77,27 @@ def test_two_ranks_gloo():
             assert calls == len(_dist.shard_indices(B, rank, 2))
             ncalls += calls
         assert ncalls == B  # every point evaluated exactly once
+
+
+def test_eval_concurrent_host_logic():
+    """ slot assignment, ordering and error propagation of the in-flight evaluator (CPU: threads only, no streams) """
+    import threading
+    seen = {}
+
+    def fun(t):
+        seen.setdefault(threading.current_thread().name, []).append(int(t[0]))
+        return _fun(t)
+    thetas = np.arange(21.0).reshape(7, 3)
+    out = _dist.eval_concurrent(fun, thetas, 3)
+    np.testing.assert_array_equal(np.stack(out), np.stack([_fun(t) for t in thetas]))
+    assert sorted(sorted(v) for v in seen.values()) == [[0, 9, 18], [3, 12], [6, 15]]
+    assert _dist.eval_concurrent(_fun, [], 4) == []
+    out1 = _dist.eval_batch_sharded(_fun, thetas, in_flight=2)
+    np.testing.assert_array_equal(out1, np.stack([_fun(t) for t in thetas]))
+
+    def bad(t):
+        if t[0] == 9:
+            raise ValueError('boom')
+        return _fun(t)
+    with pytest.raises(ValueError):
+        _dist.eval_concurrent(bad, thetas, 2)

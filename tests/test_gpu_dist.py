@@ -75,3 +75,75 @@ def test_distchol_multi_rank_vs_oracle(nproc, grid, peer):
     res = _torchrun(nproc, '--size', '3000', '--tile', '256', '--grid', grid, '--oracle', '--peer', peer)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert 'DIST_CHECK_OK' in res.stdout
+
+
+def test_trsm_bcast_epilogue_and_flags_single_gpu():
+    """ the fused panel solve -> broadcast entry points on ONE GPU (the multi-rank cases above need more):
+    lgp_tile_trsm_right_bcast with local buffers as the extra destinations must give lgp_tile_trsm_right's result in
+    place and the same values in every destination; lgp_flag_signal / lgp_flag_wait order streams through counters in
+    device memory and give up (err = 1) instead of spinning forever """
+    import ctypes
+    dev = torch.device('cuda:0')
+    ops = _dist.CudaTileOps(dev)
+    T, rows = 256, 300
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((T, T))
+    A = A @ A.T + T * np.eye(T)
+    tile = _ops.as_aligned(torch.tensor(A).to(dev))
+    invd = ops.empty(T // 128 * 128 * 128)
+    dvec = ops.zeros(T)
+    info = ops.zeros(1, dtype=torch.int32)
+    info.fill_(2 ** 31 - 1)
+    ops.potrf_tile(tile, invd, dvec, info, 0)
+    B0 = torch.tensor(rng.standard_normal((rows, T))).to(dev)
+    B1 = _ops.as_aligned(B0.clone())
+    ops.trsm_right(tile, invd, B1)
+    L = np.linalg.cholesky(A)
+    np.testing.assert_allclose(B1.cpu().numpy(), np.linalg.solve(L, B0.cpu().numpy().T).T, rtol=1e-10, atol=1e-12)
+    B2 = _ops.as_aligned(B0.clone())
+    d1 = torch.zeros(rows, T, dtype=torch.float64, device=dev)
+    ops.trsm_right_bcast(tile, invd, B2, [d1.data_ptr()], T, False)
+    assert torch.equal(B2, B1) and torch.equal(d1, B1)
+    # two destinations with a wider leading dimension: the columns beyond T stay untouched
+    B3 = _ops.as_aligned(B0.clone())
+    w1 = torch.full((rows, T + 2), 7.0, dtype=torch.float64, device=dev)
+    w2 = torch.full((rows, T + 2), 7.0, dtype=torch.float64, device=dev)
+    ops.trsm_right_bcast(tile, invd, B3, [w1.data_ptr(), w2.data_ptr()], T + 2, False)
+    for w in (w1, w2):
+        assert torch.equal(w[:, :T], B1) and bool((w[:, T:] == 7.0).all())
+    # argument errors are reported, not executed
+    lib = _lib.load()
+
+    def call(ndst, ptrs, ld, mm):
+        arr = (ctypes.c_void_p * max(len(ptrs), 1))(*ptrs)
+        return lib.lgp_tile_trsm_right_bcast(_lib.stream_ptr(), _lib.ptr(tile), tile.stride(0), _lib.ptr(invd), T,
+                                             _lib.ptr(B3), B3.stride(0), rows, ndst, arr, ld, mm)
+    assert call(9, [w1.data_ptr()] * 9, T + 2, 0) == -1          # more than 8 destinations
+    assert call(1, [w1.data_ptr()], T - 2, 0) == -1              # leading dimension shorter than the panel
+    assert call(2, [w1.data_ptr(), w2.data_ptr()], T + 2, 1) == -1   # multicast takes exactly one address
+    assert call(1, [w1.data_ptr() + 8], T + 2, 0) != 0           # misaligned destination
+    torch.cuda.synchronize()
+
+    # counters: a release store on one stream lets the acquire-wait on another stream pass (the signal is enqueued
+    # first: a spinning kernel must never sit in front of the work that releases it in a shared hardware queue);
+    # an unreachable value times out with err = 1 instead of hanging
+    import time
+    flags = torch.zeros(4, dtype=torch.int64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    side = torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        ops.flag_signal([flags.data_ptr(), flags.data_ptr() + 8], 5)
+    ops.flag_wait(flags.data_ptr(), 2, 5, 20000, err)
+    t0 = time.perf_counter()
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 10.0
+    assert flags.tolist() == [5, 5, 0, 0] and int(err.item()) == 0
+    ops.flag_wait(flags.data_ptr(), 2, 4, 20000, err)   # counters are monotone: a smaller value passes at once
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    t0 = time.perf_counter()
+    ops.flag_wait(flags.data_ptr(), 3, 5, 300, err)   # flags[2] never reaches 5: gives up after 300 ms
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 >= 0.25
+    assert int(err.item()) == 1
