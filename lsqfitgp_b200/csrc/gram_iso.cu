@@ -7,6 +7,7 @@
 //   src/lsqfitgp/_special/_bessel.py:101-122 (kvmodx2_hi and its derivative),
 //   src/lsqfitgp/_Kernel/_alg.py:48-82 (sum / product / scalar multiple).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/lgp_b200.h"
@@ -827,6 +828,166 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Symmetric fast path, version 3: same arithmetic as gram_fast2_kernel<.., true>, different data movement.
+//   * lanes of a half-warp run along ROWS of the tile (ty = tid & 15), so that the transposed copy of the tile is
+//     written to shared memory with consecutive addresses (conflict-free; the column-major lane order of version 2
+//     put 8 wavefronts on every one of those stores);
+//   * BOTH the tile and its mirror image are staged in shared memory (row stride 66 doubles: 16-byte aligned rows,
+//     conflict-free 128-bit row stores) and leave through TMA bulk stores, one 512-byte row per copy: the SM issues
+//     128 bulk copies per tile instead of 4096 scattered 16-byte stores, and no thread waits on a global store.
+// Edge tiles (not fully inside the matrix) fall back to bounds-checked stores.
+// ------------------------------------------------------------------------------------------------
+template <int KIND, int P>
+__global__ void __launch_bounds__(G_THREADS, 3) gram_fast3_kernel(const __grid_constant__ FastDesc d,
+                                                                  const double *__restrict__ x, int64_t ldx, int64_t n,
+                                                                  double *__restrict__ K, int64_t ldk, int vec_ok) {
+    extern __shared__ __align__(16) double fsm[];
+    const int nd = d.nd;
+    ExpTab *tab = reinterpret_cast<ExpTab *>(fsm);
+    double *su = fsm + 128, *sv = su + nd * FT;
+    double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
+    double *D = rv + (d.white_raw ? nd * FT : 0);  // D[row][col], stride F2_TS
+    double *T = D + FT * F2_TS;                    // T[col][row]
+    const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
+    long long b = blockIdx.x;
+    int tm = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);  // single precision + exact integer fix-up
+    while ((long long)(tm + 1) * (tm + 2) / 2 <= b) tm++;
+    while ((long long)tm * (tm + 1) / 2 > b) tm--;
+    const int tn = (int)(b - (long long)tm * (tm + 1) / 2);
+    const int64_t i0 = (int64_t)tm * FT, j0 = (int64_t)tn * FT;
+    if (tid < 64) tab[tid] = EXP_TAB_DEV[tid];
+    for (int idx = tid; idx < nd * FT; idx += G_THREADS) {
+        const int s = idx / FT, r = idx % FT;
+        const int64_t i = i0 + r, j = j0 + r;
+        double xr = (i < n) ? x[(int64_t)d.dims[s] * ldx + i] : 0.0;
+        double yr = (j < n) ? x[(int64_t)d.dims[s] * ldx + j] : 0.0;
+        su[idx] = __ddiv_rn(__dsub_rn(xr, d.loc), d.scale);
+        sv[idx] = __ddiv_rn(__dsub_rn(yr, d.loc), d.scale);
+        if (d.white_raw) {
+            ru[idx] = xr;
+            rv[idx] = yr;
+        }
+    }
+    __syncthreads();
+
+    const double nu2 = (double)(2 * P + 1), par0 = d.par0, amp = d.amp;
+    const double c0 = d.coef2[0], c1 = d.coef2[1], c2 = d.coef2[2];
+    const double *wu = d.white_raw ? ru : su, *wv = d.white_raw ? rv : sv;
+    const bool white = d.has_white != 0;
+    const bool mirror = tm != tn;
+    const bool interior = vec_ok && i0 + FT <= n && j0 + FT <= n;
+
+#pragma unroll 1
+    for (int a0 = 0; a0 < 4; a0 += 2) {
+        double r2[2][4];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) r2[a][c] = 0.0;
+        for (int s = 0; s < nd; s++) {
+            double uu[2], vv[4];
+#pragma unroll
+            for (int a = 0; a < 2; a++) uu[a] = su[s * FT + ty + 16 * (a0 + a)];
+#pragma unroll
+            for (int bb = 0; bb < 2; bb++) {
+                double2 t = *reinterpret_cast<const double2 *>(&sv[s * FT + 2 * tx + 32 * bb]);
+                vv[2 * bb] = t.x;
+                vv[2 * bb + 1] = t.y;
+            }
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    double df = __dsub_rn(uu[a], vv[c]);
+                    r2[a][c] = __dadd_rn(r2[a][c], __dmul_rn(df, df));
+                }
+        }
+        double val[2][4];
+        unsigned hmin = 0xffffffffu, hmax = 0u;
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const unsigned hr = (unsigned)__double2hiint(r2[a][c]);
+                hmin = min(hmin, hr);
+                hmax = max(hmax, hr);
+                val[a][c] = __dmul_rn(amp, fast2_core<KIND, P>(r2[a][c], nu2, par0, c0, c1, c2, tab));
+            }
+        if (fast2_out_of_range<KIND>(__hiloint2double((int)hmin, 0), nu2, par0, white) ||
+            fast2_out_of_range<KIND>(__hiloint2double((int)hmax, 0xffffffff), nu2, par0, white)) {
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (fast2_out_of_range<KIND>(r2[a][c], nu2, par0, white))
+                        val[a][c] = fast2_slow_entry<KIND>(d, r2[a][c], wu, wv, ty + 16 * (a0 + a),
+                                                           2 * tx + 32 * (c >> 1) + (c & 1));
+        }
+        if (d.has_const) {
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) val[a][c] = __dadd_rn(val[a][c], d.amp_const);
+        }
+        if (interior) {
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                double *dp = D + (ty + 16 * (a0 + a)) * F2_TS + 2 * tx;
+                *reinterpret_cast<double2 *>(dp) = make_double2(val[a][0], val[a][1]);
+                *reinterpret_cast<double2 *>(dp + 32) = make_double2(val[a][2], val[a][3]);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                int64_t i = i0 + ty + 16 * (a0 + a);
+                if (i >= n) continue;
+                double *krow = K + i * ldk;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    int64_t j = j0 + 2 * tx + 32 * (c >> 1) + (c & 1);
+                    if (j < n) krow[j] = val[a][c];
+                }
+            }
+        }
+        if (mirror) {
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    T[(2 * tx + 32 * (c >> 1) + (c & 1)) * F2_TS + ty + 16 * (a0 + a)] = val[a][c];
+        }
+    }
+    if (interior) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        // rows of the tile by threads 0..63, rows of its mirror image by threads 64..127
+        const int r = tid & 63;
+        if (tid < FT || (mirror && tid < 2 * FT)) {
+            const bool second = tid >= FT;
+            const uint32_t src = smem_u32((second ? T : D) + r * F2_TS);
+            double *dst = second ? K + (j0 + r) * ldk + i0 : K + (i0 + r) * ldk + j0;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(FT * 8)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else if (mirror) {
+        __syncthreads();
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int rr = warp; rr < FT; rr += G_THREADS / 32) {
+            int64_t j = j0 + rr;
+            if (j >= n) break;
+            double *krow = K + j * ldk + i0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int cidx = lane + 32 * h;
+                if (i0 + cidx < n) krow[cidx] = T[rr * F2_TS + cidx];
+            }
+        }
+    }
+}
+
 // d core / d r2 for the fast path (value returned through `val`)
 template <int KIND>
 __device__ __forceinline__ void fast_core_derivs(const FastDesc &d, double r2, double &val, double &dr2,
@@ -1137,7 +1298,12 @@ static int launch_fast2(cudaStream_t st, const FastDesc &d, const double *x, int
     int64_t grid = sym ? tm * (tm + 1) / 2 : tm * tn;
     if (grid > 2147483647LL) return LGP_ERR_UNSUPPORTED;
     int vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
-    if (sym) {
+    static const bool v3 = !(getenv("LGP_GRAM_V3") && getenv("LGP_GRAM_V3")[0] == '0');  // A/B switch (experiments only)
+    if (sym && v3) {
+        smem += (size_t)FT * F2_TS * 8;  // second staging tile
+        cudaFuncSetAttribute(gram_fast3_kernel<KIND, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gram_fast3_kernel<KIND, P><<<(unsigned)grid, G_THREADS, smem, st>>>(d, x, ldx, n, K, ldk, vec_ok);
+    } else if (sym) {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(gram_fast2_kernel<KIND, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         gram_fast2_kernel<KIND, P, true><<<(unsigned)grid, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, K, ldk,
