@@ -132,11 +132,11 @@ class _GramFn(torch.autograd.Function):
             for (kind, ti, fi, tensor), t in zip(hyper, tangents):
                 if t is None or kind == 'bart_amp':
                     continue
-                tv = float(t)
+                tv = float(t.detach())
                 if kind == 'amp':
                     tan[pos[(ti, 0)], 0] += tv
                 elif kind == 'scale':
-                    tan[pos[(ti, fi)], 1] += tv / float(tensor)
+                    tan[pos[(ti, fi)], 1] += tv / float(tensor.detach())
                 elif kind == 'par1':
                     tan[pos[(ti, fi)], 2] += tv
                 else:  # pragma: no cover
@@ -145,8 +145,8 @@ class _GramFn(torch.autograd.Function):
         for (kind, ti, fi, tensor), t in zip(hyper, tangents):
             if kind == 'bart_amp' and t is not None:
                 spec = ti
-                corr = spec.scaled(1.0 / float(spec.amp)).gram_device(xd, yd, labels)
-                corr *= float(t)
+                corr = spec.scaled(1.0 / float(spec.amp.detach() if isinstance(spec.amp, torch.Tensor) else spec.amp)).gram_device(xd, yd, labels)
+                corr *= float(t.detach())
                 D = corr if D is None else D.add_(corr)
         if D is None:
             D = torch.zeros(xd.shape[1], yd.shape[1], dtype=f64, device=xd.device)

@@ -401,3 +401,54 @@ def test_empbayes_fit_fisher_vs_oracle():
     fitc = lgp.empbayes_fit(hyperprior, gpfactory, {'data': y3}, raises=False, covariance='fisher')
     covc = np.array([[fitc.pcov[a, b] for b in hyperprior] for a in hyperprior])
     assert rel(covc, cov) < 1e-3
+
+
+def test_mpmath_anchor():
+    """ the CUDA path against the 50-digit mpmath computation of logML, its gradient and the posterior mean
+    (tests/golden/mpmath_anchor_c2_n48.json, written by tests/test_oracle_mpmath_anchor.py): an anchor that does not
+    go through the oracle, LAPACK or float64 at all """
+    import json
+    from test_oracle_mpmath_anchor import problem
+    gold = json.loads((GOLD / 'mpmath_anchor_c2_n48.json').read_text())
+    X, y, Xs, (ell, sf, sn) = problem()
+    names = ['f0', 'f1', 'f2']
+    xs = lgp.unstructured_to_structured(X, names=names)
+    xp = lgp.unstructured_to_structured(Xs, names=names)
+    theta = torch.tensor([np.log(ell), np.log(sf), np.log(sn)], dtype=torch.float64, requires_grad=True)
+    main = torch.exp(theta[1]) ** 2 * lgp.Matern(nu=2.5, scale=torch.exp(theta[0]))
+    kern = main + torch.exp(theta[2]) ** 2 * lgp.White()
+    gp = lgp.GP(kern, checkpos=False, checksym=False).addx(xs, 'data')
+    ml = gp.marginal_likelihood({'data': y})
+    g, = torch.autograd.grad(ml, theta)
+    assert abs(float(ml.detach()) - gold['logml']) <= 1e-11 * abs(gold['logml'])
+    gg = np.array(gold['grad_minus_logml'])
+    np.testing.assert_allclose(-g.numpy(), gg, rtol=1e-9, atol=1e-9 * np.max(np.abs(gg)))
+    # posterior mean of the latent function at new points: the noise is White, absent between distinct points
+    with torch.no_grad():
+        gp2 = lgp.GP(sf ** 2 * lgp.Matern(nu=2.5, scale=ell) + sn ** 2 * lgp.White(), checkpos=False, checksym=False)
+        gp2 = gp2.addx(xs, 'data').addx(xp, 'pred')
+        mean, cov = gp2.predfromdata({'data': y}, 'pred', raw=True)
+    np.testing.assert_allclose(mean, gold['mean'], rtol=1e-9, atol=1e-11)
+
+
+def test_batch_in_flight_matches_sequential():
+    """ several evaluations in flight on one GPU (one thread + stream per slot) give the sequential results """
+    from lsqfitgp_b200 import _dist
+    rng = np.random.default_rng(77)
+    n = 900
+    X = rng.uniform(0, 10, (n, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(n)
+    xs = lgp.unstructured_to_structured(X, names=['f0', 'f1', 'f2'])
+
+    def fun(theta):
+        th = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+        k = torch.exp(th[1]) ** 2 * lgp.Matern(nu=2.5, scale=torch.exp(th[0])) + torch.exp(th[2]) ** 2 * lgp.White()
+        ml = lgp.GP(k, checkpos=False, checksym=False).addx(xs, 'data').marginal_likelihood({'data': y})
+        g, = torch.autograd.grad(ml, th)
+        return np.r_[float(ml.detach()), g.numpy()]
+    thetas = np.array([np.log(1.5), 0.0, np.log(0.1)]) + 0.2 * rng.standard_normal((9, 3))
+    dev = torch.device('cuda', torch.cuda.current_device())
+    seq = _dist.eval_batch_sharded(fun, thetas, device=dev)
+    par = _dist.eval_batch_sharded(fun, thetas, device=dev, in_flight=3)
+    np.testing.assert_allclose(par[:, 0], seq[:, 0], rtol=1e-13)
+    np.testing.assert_allclose(par[:, 1:], seq[:, 1:], rtol=1e-10, atol=1e-10 * np.abs(seq[:, 1:]).max())
