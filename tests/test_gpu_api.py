@@ -452,3 +452,63 @@ def test_batch_in_flight_matches_sequential():
     par = _dist.eval_batch_sharded(fun, thetas, device=dev, in_flight=3)
     np.testing.assert_allclose(par[:, 0], seq[:, 0], rtol=1e-13)
     np.testing.assert_allclose(par[:, 1:], seq[:, 1:], rtol=1e-10, atol=1e-10 * np.abs(seq[:, 1:]).max())
+
+
+def test_reference_gp_shell_semantics():
+    """ behaviour pinned by the reference's own tests/GP/test_GP.py (file:line cited per block), raw=True forms """
+    rng = np.random.default_rng(20)
+    # test_zero_covblock (:509-515): independent addcov keys have a zero cross block
+    a = rng.standard_normal((10, 10))
+    m = a.T @ a
+    gp = lgp.GP().addcov(m, 0).addcov(m, 1)
+    prior = gp.prior(raw=True)
+    assert np.array_equal(prior[0, 1], np.zeros_like(m)) and np.allclose(prior[0, 0], m, rtol=1e-15)
+    # test_addcov_checks (:517-530): non-symmetric / non-finite blocks are refused unless the checks are disabled
+    b = a.copy()
+    b[0, 0] = np.inf
+    with pytest.raises(ValueError):
+        lgp.GP().addcov(a, 0)
+    with pytest.raises(ValueError):
+        lgp.GP().addcov(b.T @ b, 0)
+    lgp.GP(checksym=False).addcov(a, 0)
+    lgp.GP(checkfinite=False).addcov(b.T @ b, 0)
+    # test_zero_givencov (:652-660): a zero data covariance changes nothing
+    x, y, z = rng.standard_normal((3, 20))
+    gp = lgp.GP(lgp.ExpQuad()).addx(x, 0).addx(y, 1)
+    m1, c1 = gp.predfromdata({0: z}, 1, {(0, 0): np.zeros((20, 20))}, raw=True)
+    m2, c2 = gp.predfromdata({0: z}, 1, raw=True)
+    np.testing.assert_array_equal(m1, m2)
+    np.testing.assert_array_equal(c1, c2)
+    # test_pred_all (:683-690): no key = all keys
+    ma, ca = gp.predfromdata({0: z}, raw=True)
+    mb, cb = gp.predfromdata({0: z}, [0, 1], raw=True)
+    assert set(ma) == {0, 1} and all(np.array_equal(ma[k], mb[k]) for k in ma)
+    assert all(np.array_equal(ca[k], cb[k]) for k in ca)
+    # test_pred_checks (:662-681)
+    with pytest.raises(ValueError):
+        gp.pred({0: z}, 1)
+    with pytest.raises(ValueError):
+        gp.predfromdata({0: z}, 1, raw=True, keepcorr=True)
+    with pytest.raises(ValueError):
+        gp.predfromdata({0: np.full_like(z, np.nan)}, 1, raw=True)
+    with pytest.raises(ValueError):
+        gp.predfromdata({0: z}, 1, {(0, 0): np.full((20, 20), np.nan)}, raw=True)
+    with pytest.raises(ValueError):
+        gp.predfromdata({0: z}, 1, {(0, 0): rng.standard_normal((20, 20))}, raw=True)
+    with pytest.raises(KeyError):
+        gp.predfromdata({2: z}, 1, raw=True)
+    with pytest.raises(ValueError):
+        gp.predfromdata({0: z[:-1]}, 1, raw=True)
+    # test_marginal_likelihood_checks (:692-705, without the gvar form)
+    with pytest.raises(ValueError):
+        gp.marginal_likelihood({0: np.full_like(z, np.nan)})
+    with pytest.raises(ValueError):
+        gp.marginal_likelihood({0: z}, {(0, 0): np.full((20, 20), np.nan)})
+    with pytest.raises(ValueError):
+        gp.marginal_likelihood({0: z}, {(0, 0): rng.standard_normal((20, 20))})
+    # test_marginal_likelihood_gvar (:707-715), matrix form: equals the oracle
+    c = rng.standard_normal((20, 20))
+    c = c.T @ c
+    ml = gp.marginal_likelihood({0: z}, {(0, 0): c})
+    Kxx = ogp.gram([(1.0, [dict(kind='expquad')])], x[None], x[None])
+    assert abs(ml - ogp.logml(Kxx, z, c)) <= 1e-12 * abs(ml)
