@@ -16,6 +16,12 @@ void lgp_host_exp_neg(const double *a, double *out, long n) {
 void lgp_host_exp_neg_fast(const double *a, double *out, long n) {
     for (long i = 0; i < n; i++) out[i] = lgp::fm_exp_neg_fast(a[i], lgp::EXP_TAB_HOST);
 }
+void lgp_host_div_recip(const double *a, const double *b, double *out, long n) {
+    for (long i = 0; i < n; i++) {
+        const double y = 1.0 / b[i];
+        out[i] = lgp::fm_div_recip_ok(a[i]) ? lgp::fm_div_recip(a[i], b[i], y) : a[i] / b[i];
+    }
+}
 void lgp_host_sqrt(const double *z, double *out, long n) {
     for (long i = 0; i < n; i++) {
         double y0 = trunc20(1.0 / sqrt(trunc20(z[i])));

@@ -18,11 +18,19 @@ def host():
         import subprocess
         subprocess.run(['make', '-C', str(ROOT / 'oracle')], check=True)
     lib = ctypes.CDLL(str(path))
+    lib.lgp_host_div_recip.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_long]
+    lib.lgp_host_div_recip.restype = None
+    call_div = lib.lgp_host_div_recip
     for name in ('lgp_host_exp_neg', 'lgp_host_exp_neg_fast', 'lgp_host_sqrt'):
         getattr(lib, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
         getattr(lib, name).restype = None
 
     def call(name, a):
+        if name == 'lgp_host_div_recip':
+            a, b = (np.ascontiguousarray(v, dtype=np.float64) for v in a)
+            out = np.empty_like(a)
+            call_div(a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size)
+            return out
         a = np.ascontiguousarray(a, dtype=np.float64)
         out = np.empty_like(a)
         getattr(lib, name)(a.ctypes.data, out.ctypes.data, a.size)
@@ -86,3 +94,23 @@ def test_true_error_against_mpmath(host):
     got = host('lgp_host_sqrt', z)
     err = [abs(mpmath.mpf(float(g)) - mpmath.sqrt(mpmath.mpf(float(x)))) / mpmath.mpf(float(np.spacing(g))) for g, x in zip(got, z)]
     assert max(err) < 1.0
+
+
+def test_division_by_reciprocal_is_correctly_rounded(host):
+    """ (x - loc) / scale of the Gram kernels: reciprocal + two exact-residual corrections == IEEE division, bit for bit
+    (random and adversarial divisors: significands 1, 1 + ulp, 2 - ulp, ...), with the library division outside the
+    proven range (tiny / huge / non-finite numerators) """
+    rng = np.random.default_rng(15)
+    N = 3_000_000
+    a = rng.standard_normal(N) * 10.0 ** rng.uniform(-30, 30, N)
+    b = (1 + rng.random(N)) * 2.0 ** rng.integers(-60, 60, N) * rng.choice([-1, 1], N)
+    assert np.array_equal(host('lgp_host_div_recip', (a, b)), a / b)
+    for sig in [1.0, np.nextafter(1.0, 2), np.nextafter(2.0, 1), 1.5, 1 + 2.0 ** -26, 2 - 2.0 ** -26, 4 / 3, 5 / 3, 1.9999999]:
+        a = (1 + rng.random(300000)) * 2.0 ** rng.integers(-5, 5, 300000)
+        a[:1000] = np.nextafter(np.linspace(1, 2, 1000), 3)
+        bb = np.full_like(a, sig * 8)
+        assert np.array_equal(host('lgp_host_div_recip', (a, bb)), a / bb)
+    a = np.array([0.0, 6.0, 1e-310, 1e305, np.inf, -np.inf, np.nan, 2.0 ** -600, 2.0 ** 600])
+    out = host('lgp_host_div_recip', (a, np.full_like(a, 3.0)))
+    ref = a / 3.0
+    assert all((o == r) or (o != o and r != r) for o, r in zip(out, ref))
