@@ -128,3 +128,27 @@ def test_gradient_against_finite_differences(state):
         e[k] = h
         fd = (_value_and_grad(state, THETA0 + e, grad=False) - _value_and_grad(state, THETA0 - e, grad=False)) / (2 * h)
         assert abs(fd - grad[k]) <= 1e-5 * np.max(np.abs(grad)), (k, fd, grad)
+
+
+def test_matern_real_order_full_size_sampled_rows():
+    """ Matern(nu = 1.3) at n = 20000 (K_nu evaluated in the kernel): sampled rows against the oracle's scipy.special.kv route
+    (2e-13: AMOS itself is ~1e-13 from exact, tests/test_bessel_cpu.py), exact symmetry of the general kernel's output """
+    import time
+    dev = torch.device('cuda:0')
+    X, _ = _data()
+    xd = torch.tensor(np.ascontiguousarray(X.T)).to(dev)
+    descs = [dict(kind=_lib.K_MATERN, term=0, dimmask=7, par0=1.3, scale_x=1.5, scale_y=1.5, amp=1.0),
+             dict(kind=_lib.K_WHITE, term=1, dimmask=7, amp=0.01)]
+    K = _ops.aligned_empty(N, N, dev)
+    _ops.gram_iso(descs, xd, xd, out=K, symmetric=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _ops.gram_iso(descs, xd, xd, out=K, symmetric=True)
+    torch.cuda.synchronize()
+    print(f'Matern(nu=1.3) Gram n={N}: {(time.perf_counter() - t0) * 1e3:.1f} ms')
+    rows = np.random.default_rng(2).choice(N, 24, replace=False)
+    terms = [(1.0, [dict(kind='matern', nu=1.3, scale=1.5)]), (0.01, [dict(kind='white')])]
+    Ko = ogp.gram(terms, X[rows].T.copy(), X.T.copy())
+    Kg = K[torch.as_tensor(rows, device=dev)].cpu().numpy()
+    assert np.max(np.abs(Kg - Ko) / np.abs(Ko)) < 2e-13
+    assert torch.equal(K[:2048, :2048], K[:2048, :2048].T)
