@@ -446,6 +446,7 @@ struct FastDesc {
     double scale, loc, par0, par1, amp, amp_white, amp_const;
     double coef[G_MAX_P];
     double coef2[G_MAX_P];  // 2 * coef (exact), precomputed on the host for the fast path
+    double mat[MATERN_NPAR];  // LGP_K_MATERN: host-computed constants of the order (bessel_k.cuh)
     double rscale;          // RN(1 / scale) for fm_div_recip
     int div_fast;           // scale inside the exponent range where fm_div_recip is exact
     unsigned char dims[LGP_MAX_DIMS];
@@ -469,6 +470,11 @@ __device__ __forceinline__ double fast_core(const FastDesc &d, double r2) {
         for (int k = d.p - 1; k >= 0; k--)
             poly = __dadd_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(poly, d.coef[k]), 2.0), x));
         return __dmul_rn(exp(-x), poly);
+    }
+    if (KIND == LGP_K_MATERN) {
+        double val, dr2;
+        matern_nu_core(d.mat, r2, false, val, dr2);
+        return val;
     }
     // Cauchy
     double pw = (d.par0 == 2.0) ? r2 : pow(r2, d.par0 / 2.0);
@@ -1003,7 +1009,9 @@ template <int KIND>
 __device__ __forceinline__ void fast_core_derivs(const FastDesc &d, double r2, double &val, double &dr2,
                                                  double &dpar1) {
     dpar1 = 0.0;
-    if (KIND == LGP_K_EXPQUAD) {
+    if (KIND == LGP_K_MATERN) {
+        matern_nu_core(d.mat, r2, true, val, dr2);
+    } else if (KIND == LGP_K_EXPQUAD) {
         val = exp(-0.5 * r2);
         dr2 = -0.5 * val;
     } else if (KIND == LGP_K_MATERNP) {
@@ -1252,7 +1260,9 @@ static bool build_fast(const lgp_factor_t *f, int nf, int ndim, FastDesc &d) {
     if (pos_white >= 0 && pos_const >= 0 && pos_white > pos_const) return false;
     const lgp_factor_t &m = f[main_i];
     if (m.scale_x != m.scale_y || m.loc_x != m.loc_y) return false;
-    if (m.kind != LGP_K_EXPQUAD && m.kind != LGP_K_MATERNP && m.kind != LGP_K_CAUCHY) return false;
+    if (m.kind != LGP_K_EXPQUAD && m.kind != LGP_K_MATERNP && m.kind != LGP_K_CAUCHY && m.kind != LGP_K_MATERN)
+        return false;
+    if (m.kind == LGP_K_MATERN && !matern_nu_setup(m.par0, d.mat)) return false;  // (general path reports the error)
     d.kind = m.kind;
     d.p = m.ipar;
     d.scale = m.scale_x;
@@ -1369,6 +1379,7 @@ int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors,
             }
             if (fd.kind == LGP_K_EXPQUAD) return launch_fast<LGP_K_EXPQUAD>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
             if (fd.kind == LGP_K_MATERNP) return launch_fast<LGP_K_MATERNP>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
+            if (fd.kind == LGP_K_MATERN) return launch_fast<LGP_K_MATERN>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
             return launch_fast<LGP_K_CAUCHY>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
         }
     }
@@ -1426,6 +1437,8 @@ int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfact
                 LGP_VJP_LAUNCH(LGP_K_MATERNP, 3);
             else if (fd.kind == LGP_K_MATERNP)
                 LGP_VJP_LAUNCH(LGP_K_MATERNP, -1);
+            else if (fd.kind == LGP_K_MATERN)
+                LGP_VJP_LAUNCH(LGP_K_MATERN, -1);
             else
                 LGP_VJP_LAUNCH(LGP_K_CAUCHY, -1);
 #undef LGP_VJP_LAUNCH
