@@ -255,6 +255,13 @@ int lgp_tile_trsm_right_bcast(lgp_stream_t stream, const double *L, int64_t ldl,
 #define LGP_MAX_FLAGS 16
 int lgp_flag_signal(lgp_stream_t stream, void *const *flag_ptrs, int n, uint64_t value);
 int lgp_flag_wait(lgp_stream_t stream, const uint64_t *flags, int n, uint64_t value, int64_t timeout_ms, int32_t *err);
+
+/* Copy a rows x cols block (src, lds) to n_dst (<= 8) destinations dst[d] + i*ld_dst + j at once: peer-mapped buffers
+ * (one NVLink store per destination) or, with multimem != 0, ONE NVSwitch multicast address (n_dst == 1).  Used to
+ * hand the factored diagonal tile and its inverted 128x128 blocks to the other GPUs of a process column without
+ * ncclBroadcast; order readers with lgp_flag_signal / lgp_flag_wait.  `dst` is a HOST array. */
+int lgp_copy2d_bcast(lgp_stream_t stream, const double *src, int64_t lds, int64_t rows, int64_t cols, int n_dst,
+                     void *const *dst, int64_t ld_dst, int multimem);
 /* b (t contiguous doubles) <- L^-1 b (trans=0) or L^-T b (trans=1) */
 int lgp_tile_trsv(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *b,
                   int trans);

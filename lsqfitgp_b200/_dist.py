@@ -377,6 +377,14 @@ class CudaTileOps:
                                                     B.stride(0), B.shape[0], len(dst_ptrs), arr, ld_dst,
                                                     int(bool(multimem))), 'lgp_tile_trsm_right_bcast')
 
+    def copy2d_bcast(self, src, dst_ptrs, ld_dst, multimem):
+        rows, cols = src.shape
+        if rows == 0 or cols == 0:
+            return
+        arr = (ctypes.c_void_p * len(dst_ptrs))(*dst_ptrs)
+        self._ck(self.lib.lgp_copy2d_bcast(self._sp(), self._p(src), src.stride(0), rows, cols, len(dst_ptrs), arr,
+                                           ld_dst, int(bool(multimem))), 'lgp_copy2d_bcast')
+
     def flag_signal(self, ptrs, value):
         arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
         self._ck(self.lib.lgp_flag_signal(self._sp(), arr, len(ptrs), int(value)), 'lgp_flag_signal')
@@ -416,8 +424,9 @@ def peer_reserve(n, tile, device, *, grid=None, group=None):
     Pr, Pc = grid if grid is not None else default_grid(world)
     lay = Layout(n, tile, Pr, Pc, rank)
     slab_cap = max(max(lay.panel_count(0, r) for r in range(Pr)), 1) * lay.T * lay.T
+    diag_cap = lay.T * lay.T + (lay.T // 128) * 128 * 128 if Pr > 1 else 0
     try:
-        CudaTileOps(device).peer_setup(2 * Pr * slab_cap, group)
+        CudaTileOps(device).peer_setup(2 * Pr * slab_cap + 2 * diag_cap, group)
         return True
     except Exception:
         return False
@@ -474,7 +483,8 @@ class DistChol:
 
         # ---- peer-mapped slab buffers for the fused TRSM -> broadcast path (allocation / rendezvous: not timed)
         self._slab_cap = max(max(lay.panel_count(0, r) for r in range(Pr)), 1) * lay.T * lay.T
-        self._pb = self._peer_init(2 * Pr * self._slab_cap)
+        self._diag_cap = lay.T * lay.T + (lay.T // 128) * 128 * 128 if Pr > 1 else 0
+        self._pb = self._peer_init(2 * Pr * self._slab_cap + 2 * self._diag_cap)
         self._mark('peer_setup')
 
         # ---- factorisation (device-timed on the main stream, which joins the panel stream at the end)
@@ -527,8 +537,11 @@ class DistChol:
             # slabs live in the symmetric buffer: the panel TRSM stores its result straight into the slab of every GPU
             soff = lambda s_, r_: (s_ * Pr + r_) * slab_cap
             slab = [[pb.data[soff(s_, r_):soff(s_, r_) + slab_cap] for r_ in range(Pr)] for s_ in range(2)]
-            READY, DONE = 0, 16  # counter indices: READY + process row (slab landed), DONE + rank (update finished)
-            perr = self._peer_err
+            READY, READYD, DONE = 0, 8, 16  # counters: READY + process row (slab landed), READYD (diagonal tile landed),
+            perr = self._peer_err           # DONE + rank (trailing update finished)
+            doff = lambda s_: 2 * Pr * slab_cap + s_ * self._diag_cap
+            if Pr > 1:
+                diagbuf = [pb.data[doff(s_):doff(s_) + self._diag_cap] for s_ in range(2)]
         col_ready = {0: None}
         buf_free = [None, None]
         for k in range(NT):
@@ -558,10 +571,27 @@ class DistChol:
                 if Pr > 1 and any(lay.panel_count(k, r) for r in range(Pr)):
                     # the other process rows of this process column need L_kk for their share of the TRSM
                     db = diagbuf[set_]
-                    if own_diag:
-                        ops.copy2d(Lkk, db[:TT].view(T, T))
-                        db[TT:].copy_(invd_k)
-                    self._bcast(db, lay.rank_of(prow, pcol))
+                    if pb is not None:
+                        # peer memory: the owner stores [L_kk | inverted diagonal blocks] into the buffer of every GPU of
+                        # its process column (multicast: of every GPU) and releases READYD; no NCCL in the factor loop
+                        if in_col:
+                            if own_diag:
+                                if k >= 2:  # buffer set of step k - 2: all its readers are done
+                                    ops.flag_wait(pb.flag_addr(self.rank, DONE), self.world, k - 1, self.PEER_TIMEOUT_MS,
+                                                  perr)
+                                col_ranks = [lay.rank_of(r, pcol) for r in range(Pr)]
+                                d0 = [pb.data_addr('mc', doff(set_))] if self._multimem else \
+                                    [pb.data_addr(q, doff(set_)) for q in col_ranks]
+                                ops.copy2d_bcast(Lkk, d0, T, self._multimem)
+                                ops.copy2d_bcast(invd_k.view(1, -1), [a + 8 * TT for a in d0], nb * 128 * 128,
+                                                 self._multimem)
+                                ops.flag_signal([pb.flag_addr(q, READYD) for q in col_ranks], k + 1)
+                            ops.flag_wait(pb.flag_addr(self.rank, READYD), 1, k + 1, self.PEER_TIMEOUT_MS, perr)
+                    else:
+                        if own_diag:
+                            ops.copy2d(Lkk, db[:TT].view(T, T))
+                            db[TT:].copy_(invd_k)
+                        self._bcast(db, lay.rank_of(prow, pcol))
                     Lkk, invd_k = db[:TT].view(T, T), db[TT:]
                 cnt = lay.panel_count(k)
                 if pb is not None:

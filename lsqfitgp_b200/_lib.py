@@ -95,6 +95,7 @@ SIGNATURES = {
     'lgp_tile_trsm_right': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64]),
     'lgp_tile_trsm_right_bcast': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _int, ctypes.POINTER(_vp), _i64,
                                          _int]),
+    'lgp_copy2d_bcast': (_int, [_vp, _vp, _i64, _i64, _i64, _int, ctypes.POINTER(_vp), _i64, _int]),
     'lgp_flag_signal': (_int, [_vp, ctypes.POINTER(_vp), _int, ctypes.c_uint64]),
     'lgp_flag_wait': (_int, [_vp, _vp, _int, ctypes.c_uint64, _i64, _vp]),
     'lgp_tile_trsv': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _int]),

@@ -174,6 +174,20 @@ __global__ void copy2d_kernel(const double *__restrict__ src, int64_t lds, doubl
         dst[r * ldd + 2 * c2] = src[r * lds + 2 * c2];
 }
 
+// copy to several destinations at once (peer-mapped buffers or one multicast address): see GemmMirror
+__global__ void copy2d_bcast_kernel(const double *__restrict__ src, int64_t lds, GemmMirror mir, int64_t rows, int cols) {
+    int c2 = blockIdx.x * blockDim.x + threadIdx.x;  // pairs of columns
+    int64_t r = blockIdx.y + (int64_t)blockIdx.z * 65535;
+    if (r >= rows || 2 * c2 >= cols) return;
+    const int64_t off = r * mir.ld + 2 * c2;
+    if (2 * c2 + 1 < cols) {
+        const double2 v = *reinterpret_cast<const double2 *>(src + r * lds + 2 * c2);
+        gemm_mirror_store2(mir, off, v.x, v.y);
+    } else {
+        gemm_mirror_store(mir, off, src[r * lds + 2 * c2]);
+    }
+}
+
 }  // namespace lgp
 
 using namespace lgp;
@@ -280,6 +294,28 @@ int lgp_copy2d(lgp_stream_t stream, const double *src, int64_t lds, double *dst,
     dim3 grid((unsigned)((cols / 2 + 1 + 127) / 128), (unsigned)(rows > 65535 ? 65535 : rows),
               (unsigned)((rows + 65534) / 65535));
     copy2d_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, (int)cols);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+int lgp_copy2d_bcast(lgp_stream_t stream, const double *src, int64_t lds, int64_t rows, int64_t cols, int n_dst,
+                     void *const *dst, int64_t ld_dst, int multimem) {
+    if (rows < 0 || cols < 0 || !src || n_dst < 1 || n_dst > GEMM_MAX_MIRRORS || !dst || ld_dst < cols ||
+        (multimem && n_dst != 1))
+        return LGP_ERR_BADARG;
+    if (rows == 0 || cols == 0) return LGP_OK;
+    if ((lds & 1) || (ld_dst & 1) || (reinterpret_cast<uintptr_t>(src) & 15)) return LGP_ERR_ALIGN;
+    GemmMirror mir;
+    mir.n = n_dst;
+    mir.multimem = multimem ? 1 : 0;
+    mir.ld = ld_dst;
+    for (int i = 0; i < n_dst; i++) {
+        if (!dst[i] || (reinterpret_cast<uintptr_t>(dst[i]) & 15)) return LGP_ERR_ALIGN;
+        mir.dst[i] = (double *)dst[i];
+    }
+    dim3 grid((unsigned)((cols / 2 + 1 + 127) / 128), (unsigned)(rows > 65535 ? 65535 : rows),
+              (unsigned)((rows + 65534) / 65535));
+    copy2d_bcast_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, lds, mir, rows, (int)cols);
     LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
 }
