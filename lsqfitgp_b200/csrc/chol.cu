@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm_dmma.cuh"
 #include "internal.h"
+#include "chol_leaf2.cuh"
 
 namespace lgp {
 
@@ -371,6 +372,29 @@ __global__ void finalize_info_kernel(int32_t *info, int n) {
 // ------------------------------------------------------------------------------------------------
 // 4. host-side recursion (all sizes in 128-blocks of the padded matrix)
 // ------------------------------------------------------------------------------------------------
+// Leaf selection: version 1 (register-resident, unblocked; above) is the product path.  Version 2 (chol_leaf2.cuh, blocked
+// 4 x 32) is bit-for-bit as accurate but measured no faster (67 us both; its phase breakdown is in DESIGN.md section 3):
+// kept selectable with LGP_LEAF=2 for kernel experiments only.
+static int leaf_version() {
+    static const int v = [] {
+        const char *e = getenv("LGP_LEAF");
+        return (e && e[0] == '2') ? 2 : 1;
+    }();
+    return v;
+}
+static cudaError_t leaf_set_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(potrf_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM_BYTES);
+}
+static void leaf_launch(cudaStream_t st, double *Wblk, int64_t ld, double *invd, double *dvec, int32_t *info, int j0,
+                        int version = 0) {
+    if ((version ? version : leaf_version()) == 2)
+        potrf_leaf2_kernel<<<1, L2_THREADS, L2_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
+    else
+        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
+}
+
 struct CholCtx {
     cudaStream_t st;
     double *W;
@@ -436,9 +460,7 @@ static void trsm_right_rec(CholCtx &c, int rb, int rows, int jb, int nb) {
 static void potrf_rec(CholCtx &c, int jb, int nb) {
     if (c.rc) return;
     if (nb == 1) {
-        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, c.st>>>(Wp(c, jb, jb), c.ldw,
-                                                                      c.invd + (int64_t)jb * NB * NB, c.dvec, c.info,
-                                                                      c.j0base + jb * NB);
+        leaf_launch(c.st, Wp(c, jb, jb), c.ldw, c.invd + (int64_t)jb * NB * NB, c.dvec, c.info, c.j0base + jb * NB);
         count_launch();
         if (cudaGetLastError() != cudaSuccess) c.rc = LGP_ERR_CUDA;
         return;
@@ -898,9 +920,7 @@ int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const dou
     cudaStream_t st = (cudaStream_t)stream;
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES) !=
-            cudaSuccess)
-            return LGP_ERR_CUDA;
+        if (leaf_set_attrs() != cudaSuccess) return LGP_ERR_CUDA;
         attr = true;
     }
     if (epsrel < 0) epsrel = (double)n * 2.220446049250313e-16;
@@ -929,12 +949,15 @@ int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const dou
 // debug/benchmark hook (not in the public header): run the 128x128 leaf `reps` times back to back
 int lgp_debug_leaf(lgp_stream_t stream, double *Wblk, int64_t ld, double *invd, double *dvec, int32_t *info, int reps,
                    int variant) {
-    (void)variant;
-    cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
-    for (int i = 0; i < reps; i++)
-        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, (cudaStream_t)stream>>>(Wblk, ld, invd, dvec, info, 0);
+    if (leaf_set_attrs() != cudaSuccess) return LGP_ERR_CUDA;
+    for (int i = 0; i < reps; i++) leaf_launch((cudaStream_t)stream, Wblk, ld, invd, dvec, info, 0, variant);
     LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
+}
+
+// debug hook: phase timestamps (SM clock cycles) of the last leaf-2 launch
+int lgp_debug_leaf2_clocks(long long *out32) {
+    return cudaMemcpyFromSymbol(out32, l2_dbg, 32 * sizeof(long long)) == cudaSuccess ? LGP_OK : LGP_ERR_CUDA;
 }
 
 int lgp_chol_solve(lgp_stream_t stream, const double *W, int64_t ldw, const double *aux, int64_t n64, double *B,
@@ -1036,9 +1059,7 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
 static int leaf_attr() {
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES) !=
-            cudaSuccess)
-            return LGP_ERR_CUDA;
+        if (leaf_set_attrs() != cudaSuccess) return LGP_ERR_CUDA;
         attr = true;
     }
     return LGP_OK;
