@@ -17,6 +17,7 @@ torch tensors that require grad make `marginal_likelihood` return a differentiab
 """
 
 import math
+import threading
 
 import numpy
 import torch
@@ -181,6 +182,21 @@ class _NegLogDensityFn(torch.autograd.Function):
         return gK, gr, None
 
 
+_SIDE_STREAMS = {}
+_SIDE_LOCK = threading.Lock()
+
+
+def _side_stream_for(main):
+    """ one persistent side stream per caller stream: its allocator pool keeps the inverse buffers warm from one
+    evaluation to the next (a fresh stream per call would allocate 2 n^2 doubles in a new pool every time) """
+    key = (main.device_index, main.cuda_stream)
+    with _SIDE_LOCK:
+        side = _SIDE_STREAMS.get(key)
+        if side is None:
+            side = _SIDE_STREAMS[key] = torch.cuda.Stream(torch.device('cuda', main.device_index))
+        return side
+
+
 class _FusedNegLogMLFn(torch.autograd.Function):
     """ Gram -> Chol -> value in one node for the common case (one set of points, kernel-only covariance):
     the backward pass feeds the lower triangle of K^-1 and b = K^-1 r straight into the symmetric Gram-VJP
@@ -192,6 +208,16 @@ class _FusedNegLogMLFn(torch.autograd.Function):
         K = kern._gram_device(xd, xd, labels, symmetric=True)
         dec = _linalg.Chol(K, **kw)
         del K
+        ctx.low = ctx.side = None
+        if any(ctx.needs_input_grad[5:]):
+            # the gradient will need K^-1: start TRTRI + LAUUM on a side stream right behind the factorisation, so that the
+            # latency-bound triangular solves below (and whatever the caller does before backward) overlap its GEMMs
+            main = torch.cuda.current_stream()
+            side = _side_stream_for(main)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ctx.low = dec.inverse_lower()
+            ctx.side = side
         ldq, a = dec.logdet_quad(r)
         ctx.kern, ctx.xd, ctx.labels, ctx.dec, ctx.a = kern, xd, labels, dec, a
         half = torch.tensor(0.5, dtype=f64, device=xd.device)
@@ -205,7 +231,14 @@ class _FusedNegLogMLFn(torch.autograd.Function):
         hyper = kern._hyperparams()
         grads = []
         if hyper:
-            low = dec.inverse_lower()
+            if ctx.low is not None:
+                low = ctx.low
+                cur = torch.cuda.current_stream()
+                cur.wait_stream(ctx.side)
+                low.record_stream(cur)   # allocated on the side stream's pool, read here
+                ctx.low = None
+            else:
+                low = dec.inverse_lower()
             descs, index = kern._descriptor(labels)
             vjp = (0.5 * _ops.gram_iso_vjp(descs, xd, low, b)).cpu()
             del low
