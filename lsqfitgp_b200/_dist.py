@@ -35,6 +35,20 @@ def shard_indices(nitems, rank, world):
     return list(range(rank, nitems, world))
 
 
+_WORKER_STREAMS = {}
+
+
+def _worker_stream(device, slot):
+    """ persistent stream of in-flight slot `slot` on `device`: the caching allocator keeps one pool per stream, so
+    reusing the streams keeps the (large) factor / inverse buffers of a slot warm from one batch to the next """
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), slot)
+    st = _WORKER_STREAMS.get(key)
+    if st is None:
+        st = _WORKER_STREAMS[key] = torch.cuda.Stream(dev)
+    return st
+
+
 def eval_concurrent(fun, items, in_flight, device=None):
     """[fun(item) for item in items] with up to `in_flight` evaluations in flight on one GPU: one host thread and one
     CUDA stream per slot (slot c takes items c, c + in_flight, ...).  Independent evaluations overlap on the device: the
@@ -53,7 +67,7 @@ def eval_concurrent(fun, items, in_flight, device=None):
     def worker(slot):
         try:
             if cuda:
-                stream = torch.cuda.Stream(device)
+                stream = _worker_stream(device, slot)
                 with torch.cuda.device(device), torch.cuda.stream(stream):
                     for i in range(slot, len(items), in_flight):
                         out[i] = fun(items[i])
