@@ -21,6 +21,7 @@ ERRORS = {-1: 'bad argument', -2: 'misaligned pointer or odd leading dimension',
 
 # kernel kinds (lgp_b200.h)
 K_EXPQUAD, K_MATERNP, K_CAUCHY, K_WHITE, K_CONSTANT, K_MATERN = range(6)
+GRAM_SYMMETRIC, GRAM_GENERAL, GRAM_LIBM = 1, 2, 4  # LGP_GRAM_* flags of lgp_gram_iso
 MAX_FACTORS = 8
 MAX_DIMS = 32
 

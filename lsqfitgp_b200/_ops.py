@@ -74,8 +74,9 @@ def make_factors(descs):
     return arr
 
 
-def gram_iso(descs, x, y, out=None, symmetric=False):
-    """ x: (ndim, n) float64 device tensor (one row per field), y: (ndim, m). Returns (n, m). """
+def gram_iso(descs, x, y, out=None, symmetric=False, flags=0):
+    """ x: (ndim, n) float64 device tensor (one row per field), y: (ndim, m). Returns (n, m).
+    `flags`: extra LGP_GRAM_* bits (_lib.GRAM_GENERAL, _lib.GRAM_LIBM: A/B checks of the fast paths). """
     lib = _lib.load()
     ndim, n = x.shape
     m = y.shape[1]
@@ -86,7 +87,7 @@ def gram_iso(descs, x, y, out=None, symmetric=False):
         out = aligned_empty(n, m, x.device)
     facs = make_factors(descs)
     check(lib.lgp_gram_iso(stream_ptr(), facs, len(descs), ndim, ptr(x), x.stride(0) if ndim else 0, n, ptr(y),
-                           y.stride(0) if ndim else 0, m, ptr(out), out.stride(0), 1 if symmetric else 0),
+                           y.stride(0) if ndim else 0, m, ptr(out), out.stride(0), (1 if symmetric else 0) | int(flags)),
           'lgp_gram_iso')
     return out
 

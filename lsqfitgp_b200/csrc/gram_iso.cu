@@ -447,6 +447,8 @@ struct FastDesc {
     double coef[G_MAX_P];
     double coef2[G_MAX_P];  // 2 * coef (exact), precomputed on the host for the fast path
     double mat[MATERN_NPAR];  // LGP_K_MATERN: host-computed constants of the order (bessel_k.cuh)
+    double rpar1, cexp, r2max;  // rational quadratic fast path: RN(1/beta), -beta/2, largest r2 it accepts
+    int cauchy_fast;
     double rscale;          // RN(1 / scale) for fm_div_recip
     int div_fast;           // scale inside the exponent range where fm_div_recip is exact
     unsigned char dims[LGP_MAX_DIMS];
@@ -626,8 +628,14 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_kernel(const __grid_co
 // words, which order like the non-negative doubles) and redoes out-of-range entries on the slow path.
 template <int KIND, int P>
 __device__ __forceinline__ double fast2_core(double r2, double nu2, double par0, double c0, double c1, double c2,
-                                             const ExpTab *tab) {
+                                             const ExpTab *tab, const LogTab *ltab) {
     if (KIND == LGP_K_EXPQUAD) return fm_exp_neg_fast(__dmul_rn(-0.5, r2), tab);
+    if (KIND == LGP_K_CAUCHY) {
+        // rational quadratic (alpha = 2): (1 + r2/beta)^(-beta/2) (_basic.py:339-343); here nu2 = beta, par0 = RN(1/beta),
+        // c0 = -beta/2.  Division and sum rounded as in the reference, the power as exp(c0 log x) with the short log / exp
+        const double x = __dadd_rn(1.0, fm_div_recip(r2, nu2, par0));
+        return fm_exp_neg_fast(__dmul_rn(c0, fm_log_ge1_fast(x, ltab)), tab);
+    }
     // Maternp: x = sqrt((2p+1) r2 + par0); exp(-x) * poly_p(2x)   (_matern.py:48-49, _bessel.py:103-110)
     const double z = __dadd_rn(__dmul_rn(nu2, r2), par0);
     const double x = fm_sqrt_fast(z);
@@ -653,6 +661,8 @@ template <int KIND>
 __device__ __forceinline__ bool fast2_out_of_range(double r2, double nu2, double par0, bool white) {
     const unsigned hr = (unsigned)__double2hiint(r2);
     if (KIND == LGP_K_EXPQUAD) return (hr - 1u) > (0x40962000u - 1u);
+    if (KIND == LGP_K_CAUCHY)  // nu2 = largest accepted r2 (|exponent| <= 200); below 2^-500 (and r2 == 0): library path
+        return (hr - 0x20b00000u) > ((unsigned)__double2hiint(nu2) - 0x20b00000u);
     const unsigned hz = (unsigned)__double2hiint(__dadd_rn(__dmul_rn(nu2, r2), par0));
     return ((hz - 0x03f00000u) > (0x411e9840u - 0x03f00000u)) || (white && hr == 0u);
 }
@@ -683,7 +693,8 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
     // transpose buffer T[64][65] in symmetric mode
     const int nd = d.nd;
     ExpTab *tab = reinterpret_cast<ExpTab *>(fsm);
-    double *su = fsm + 128, *sv = su + nd * FT;
+    const LogTab *ltab = reinterpret_cast<const LogTab *>(fsm + 128);  // rational quadratic only
+    double *su = fsm + 128 + (KIND == LGP_K_CAUCHY ? 256 : 0), *sv = su + nd * FT;
     double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
     double *T = rv + (d.white_raw ? nd * FT : 0);
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -700,6 +711,7 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
     }
     const int64_t i0 = (int64_t)tm * FT, j0 = (int64_t)tn * FT;
     if (tid < 64) tab[tid] = EXP_TAB_DEV[tid];
+    if (KIND == LGP_K_CAUCHY && tid >= 64 && tid < 128) reinterpret_cast<LogTab *>(fsm + 128)[tid - 64] = LOG_TAB_DEV[tid - 64];
     for (int idx = tid; idx < nd * FT; idx += G_THREADS) {
         const int s = idx / FT, r = idx % FT;
         const int64_t i = i0 + r, j = j0 + r;
@@ -714,8 +726,12 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
     }
     __syncthreads();
 
-    const double nu2 = (double)(2 * P + 1), par0 = d.par0, amp = d.amp;
-    const double c0 = d.coef2[0], c1 = d.coef2[1], c2 = d.coef2[2];
+    // core parameters (Maternp: 2p+1, offset, doubled Horner ratios; rational quadratic: beta, 1/beta, -beta/2) and the
+    // first argument of the range test (rational quadratic: the largest accepted r2)
+    const double nu2 = KIND == LGP_K_CAUCHY ? d.par1 : (double)(2 * P + 1);
+    const double par0 = KIND == LGP_K_CAUCHY ? d.rpar1 : d.par0, amp = d.amp;
+    const double c0 = KIND == LGP_K_CAUCHY ? d.cexp : d.coef2[0], c1 = d.coef2[1], c2 = d.coef2[2];
+    const double rng0 = KIND == LGP_K_CAUCHY ? d.r2max : nu2;
     const double *wu = d.white_raw ? ru : su, *wv = d.white_raw ? rv : sv;
     const bool white = d.has_white != 0;
     const bool mirror = SYM && tm != tn;
@@ -757,18 +773,18 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
                 const unsigned hr = (unsigned)__double2hiint(r2[a][c]);
                 hmin = min(hmin, hr);
                 hmax = max(hmax, hr);
-                val[a][c] = __dmul_rn(amp, fast2_core<KIND, P>(r2[a][c], nu2, par0, c0, c1, c2, tab));
+                val[a][c] = __dmul_rn(amp, fast2_core<KIND, P>(r2[a][c], nu2, par0, c0, c1, c2, tab, ltab));
             }
         // the range test is monotone in r2: test the two extremes (the high word rounds r2 down, which only makes the
         // test stricter at the low end; at the high end the bounds are far inside the true limits)
-        if (fast2_out_of_range<KIND>(__hiloint2double((int)hmin, 0), nu2, par0, white) ||
-            fast2_out_of_range<KIND>(__hiloint2double((int)hmax, 0xffffffff), nu2, par0, white)) {
+        if (fast2_out_of_range<KIND>(__hiloint2double((int)hmin, 0), rng0, par0, white) ||
+            fast2_out_of_range<KIND>(__hiloint2double((int)hmax, 0xffffffff), rng0, par0, white)) {
             // some entry of this thread left the fast range: redo exactly those with the library path
 #pragma unroll
             for (int a = 0; a < 2; a++)
 #pragma unroll
                 for (int c = 0; c < 4; c++)
-                    if (fast2_out_of_range<KIND>(r2[a][c], nu2, par0, white))
+                    if (fast2_out_of_range<KIND>(r2[a][c], rng0, par0, white))
                         val[a][c] = fast2_slow_entry<KIND>(d, r2[a][c], wu, wv, ty + 16 * (a0 + a),
                                                            2 * tx + 32 * (c >> 1) + (c & 1));
         }
@@ -861,7 +877,8 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
     extern __shared__ __align__(16) double fsm[];
     const int nd = d.nd;
     ExpTab *tab = reinterpret_cast<ExpTab *>(fsm);
-    double *su = fsm + 128, *sv = su + nd * FT;
+    const LogTab *ltab = reinterpret_cast<const LogTab *>(fsm + 128);  // rational quadratic only
+    double *su = fsm + 128 + (KIND == LGP_K_CAUCHY ? 256 : 0), *sv = su + nd * FT;
     double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
     double *D = rv + (d.white_raw ? nd * FT : 0);  // D[row][col], stride F2_TS
     double *T = D + FT * F2_TS;                    // T[col][row]
@@ -873,6 +890,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
     const int tn = (int)(b - (long long)tm * (tm + 1) / 2);
     const int64_t i0 = (int64_t)tm * FT, j0 = (int64_t)tn * FT;
     if (tid < 64) tab[tid] = EXP_TAB_DEV[tid];
+    if (KIND == LGP_K_CAUCHY && tid >= 64 && tid < 128) reinterpret_cast<LogTab *>(fsm + 128)[tid - 64] = LOG_TAB_DEV[tid - 64];
     for (int idx = tid; idx < nd * FT; idx += G_THREADS) {
         const int s = idx / FT, r = idx % FT;
         const int64_t i = i0 + r, j = j0 + r;
@@ -887,8 +905,12 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
     }
     __syncthreads();
 
-    const double nu2 = (double)(2 * P + 1), par0 = d.par0, amp = d.amp;
-    const double c0 = d.coef2[0], c1 = d.coef2[1], c2 = d.coef2[2];
+    // core parameters (Maternp: 2p+1, offset, doubled Horner ratios; rational quadratic: beta, 1/beta, -beta/2) and the
+    // first argument of the range test (rational quadratic: the largest accepted r2)
+    const double nu2 = KIND == LGP_K_CAUCHY ? d.par1 : (double)(2 * P + 1);
+    const double par0 = KIND == LGP_K_CAUCHY ? d.rpar1 : d.par0, amp = d.amp;
+    const double c0 = KIND == LGP_K_CAUCHY ? d.cexp : d.coef2[0], c1 = d.coef2[1], c2 = d.coef2[2];
+    const double rng0 = KIND == LGP_K_CAUCHY ? d.r2max : nu2;
     const double *wu = d.white_raw ? ru : su, *wv = d.white_raw ? rv : sv;
     const bool white = d.has_white != 0;
     const bool mirror = tm != tn;
@@ -928,15 +950,15 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
                 const unsigned hr = (unsigned)__double2hiint(r2[a][c]);
                 hmin = min(hmin, hr);
                 hmax = max(hmax, hr);
-                val[a][c] = __dmul_rn(amp, fast2_core<KIND, P>(r2[a][c], nu2, par0, c0, c1, c2, tab));
+                val[a][c] = __dmul_rn(amp, fast2_core<KIND, P>(r2[a][c], nu2, par0, c0, c1, c2, tab, ltab));
             }
-        if (fast2_out_of_range<KIND>(__hiloint2double((int)hmin, 0), nu2, par0, white) ||
-            fast2_out_of_range<KIND>(__hiloint2double((int)hmax, 0xffffffff), nu2, par0, white)) {
+        if (fast2_out_of_range<KIND>(__hiloint2double((int)hmin, 0), rng0, par0, white) ||
+            fast2_out_of_range<KIND>(__hiloint2double((int)hmax, 0xffffffff), rng0, par0, white)) {
 #pragma unroll
             for (int a = 0; a < 2; a++)
 #pragma unroll
                 for (int c = 0; c < 4; c++)
-                    if (fast2_out_of_range<KIND>(r2[a][c], nu2, par0, white))
+                    if (fast2_out_of_range<KIND>(r2[a][c], rng0, par0, white))
                         val[a][c] = fast2_slow_entry<KIND>(d, r2[a][c], wu, wv, ty + 16 * (a0 + a),
                                                            2 * tx + 32 * (c >> 1) + (c & 1));
         }
@@ -1267,6 +1289,14 @@ static bool build_fast(const lgp_factor_t *f, int nf, int ndim, FastDesc &d) {
     d.p = m.ipar;
     d.scale = m.scale_x;
     d.rscale = 1.0 / m.scale_x;
+    if (m.kind == LGP_K_CAUCHY && m.par0 == 2.0 && m.par1 >= 0x1p-100 && m.par1 <= 0x1p100) {
+        d.cauchy_fast = 1;
+        d.rpar1 = 1.0 / m.par1;
+        d.cexp = -0.5 * m.par1;
+        // (beta/2) log(1 + r2/beta) <= 200 keeps the error of exp(c log x) below 1e-13; also r2 <= 2^500 for the division
+        const double lim = 400.0 / m.par1;
+        d.r2max = lim < 700.0 ? fmin(m.par1 * expm1(lim), 0x1p500) : 0x1p500;
+    }
     d.div_fast = (fabs(m.scale_x) >= 0x1p-200 && fabs(m.scale_x) <= 0x1p200) ? 1 : 0;
     d.loc = m.loc_x;
     d.par0 = m.par0;
@@ -1315,7 +1345,8 @@ static int launch_fast(cudaStream_t st, const FastDesc &d, const double *x, int6
 template <int KIND, int P>
 static int launch_fast2(cudaStream_t st, const FastDesc &d, const double *x, int64_t ldx, int64_t n, const double *y,
                         int64_t ldy, int64_t m, double *K, int64_t ldk, bool sym) {
-    size_t smem = 1024 + (size_t)(2 + (d.white_raw ? 2 : 0)) * d.nd * FT * sizeof(double) + (sym ? FT * F2_TS * 8 : 0);
+    size_t smem = 1024 + (KIND == LGP_K_CAUCHY ? 2048 : 0) + (size_t)(2 + (d.white_raw ? 2 : 0)) * d.nd * FT * sizeof(double) +
+                  (sym ? FT * F2_TS * 8 : 0);
     int64_t tm = (n + FT - 1) / FT, tn = (m + FT - 1) / FT;
     int64_t grid = sym ? tm * (tm + 1) / 2 : tm * tn;
     if (grid > 2147483647LL) return LGP_ERR_UNSUPPORTED;
@@ -1376,6 +1407,8 @@ int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors,
                     return launch_fast2<LGP_K_MATERNP, 2>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
                 if (fd.kind == LGP_K_MATERNP && fd.p == 3)
                     return launch_fast2<LGP_K_MATERNP, 3>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
+                if (fd.kind == LGP_K_CAUCHY && fd.cauchy_fast)
+                    return launch_fast2<LGP_K_CAUCHY, 0>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
             }
             if (fd.kind == LGP_K_EXPQUAD) return launch_fast<LGP_K_EXPQUAD>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
             if (fd.kind == LGP_K_MATERNP) return launch_fast<LGP_K_MATERNP>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);

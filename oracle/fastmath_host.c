@@ -22,6 +22,18 @@ void lgp_host_div_recip(const double *a, const double *b, double *out, long n) {
         out[i] = lgp::fm_div_recip_ok(a[i]) ? lgp::fm_div_recip(a[i], b[i], y) : a[i] / b[i];
     }
 }
+void lgp_host_log_ge1(const double *x, double *out, long n) {
+    for (long i = 0; i < n; i++) out[i] = lgp::fm_log_ge1_fast(x[i], lgp::LOG_TAB_HOST);
+}
+/* rational quadratic core as the Gram fast path evaluates it: (1 + r2/beta)^(-beta/2) */
+void lgp_host_ratquad(double beta, const double *r2, double *out, long n) {
+    const double rb = 1.0 / beta, cexp = -0.5 * beta;
+    for (long i = 0; i < n; i++) {
+        const double t = lgp::fm_div_recip_ok(r2[i]) ? lgp::fm_div_recip(r2[i], beta, rb) : r2[i] / beta;
+        const double y = cexp * lgp::fm_log_ge1_fast(1.0 + t, lgp::LOG_TAB_HOST);
+        out[i] = lgp::fm_exp_neg_fast(y, lgp::EXP_TAB_HOST);
+    }
+}
 void lgp_host_sqrt(const double *z, double *out, long n) {
     for (long i = 0; i < n; i++) {
         double y0 = trunc20(1.0 / sqrt(trunc20(z[i])));

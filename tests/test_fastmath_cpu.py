@@ -114,3 +114,29 @@ def test_division_by_reciprocal_is_correctly_rounded(host):
     out = host('lgp_host_div_recip', (a, np.full_like(a, 3.0)))
     ref = a / 3.0
     assert all((o == r) or (o != o and r != r) for o, r in zip(out, ref))
+
+
+def test_log_and_rational_quadratic_core():
+    """ short log of the rational-quadratic Gram path: absolute error ~1 ulp of the result (what exp(c log x) needs);
+    the core (1 + r2/beta)^(-beta/2) within 2e-14 of numpy's pow where the kernel uses it (|exponent| <= 200) """
+    import ctypes as ct
+    lib = ct.CDLL(str(ROOT / 'oracle' / 'libfastmath_host.so'))
+    lib.lgp_host_log_ge1.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_long]
+    lib.lgp_host_ratquad.argtypes = [ct.c_double, ct.c_void_p, ct.c_void_p, ct.c_long]
+    rng = np.random.default_rng(16)
+    x = np.concatenate([1 + 10.0 ** rng.uniform(-17, 0, 200000), 10.0 ** rng.uniform(0, 150, 200000),
+                        [1.0, 2.0, 1.0078125, np.nextafter(2.0, 1), 2.0 ** 500]])
+    out = np.empty_like(x)
+    lib.lgp_host_log_ge1(x.ctypes.data, out.ctypes.data, x.size)
+    ref = np.log(x)
+    assert np.all(np.abs(out - ref) <= np.maximum(1.5 * np.spacing(ref), 4e-18))   # absolute: ~1 ulp, 4e-18 near x = 1
+    assert abs(out[-5]) < 1e-17      # log(1)
+    for beta in [0.3, 1.0, 3.0, 10.0, 100.0]:
+        r2max = min(beta * np.expm1(400.0 / beta), 2.0 ** 500) if 400.0 / beta < 700 else 2.0 ** 500
+        r2 = np.concatenate([10.0 ** rng.uniform(-12, min(np.log10(r2max), 12), 200000), [0.0, r2max]])
+        o = np.empty_like(r2)
+        lib.lgp_host_ratquad(beta, r2.ctypes.data, o.ctypes.data, r2.size)
+        refv = (1 + r2 / beta) ** (-beta / 2)
+        assert np.max(np.abs(o - refv) / refv) < 6e-14, beta
+        ok = refv > 1e-20
+        assert np.max(np.abs(o[ok] - refv[ok]) / refv[ok]) < 2e-14, beta

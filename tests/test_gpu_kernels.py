@@ -287,3 +287,31 @@ def test_gram_jvp_matches_finite_differences_and_vjp():
     B = _ops.as_aligned(torch.tensor(D).to(dev()))
     np.testing.assert_allclose(float(_ops.frob_dot(A, B)[0]), (G * D).sum(), rtol=1e-12)
     np.testing.assert_allclose(float(_ops.frob_dot(A[:50, :33], B[:50, :33])[0]), (G[:50, :33] * D[:50, :33]).sum(), rtol=1e-12)
+
+
+@pytest.mark.parametrize('beta', [0.4, 3.0, 25.0])
+def test_gram_rational_quadratic_fast_path(beta):
+    """ Cauchy(alpha=2) = rational quadratic through the short log/exp fast path (symmetric v3 and rectangular v2 kernels),
+    with White and Constant terms, duplicated and far points, against the oracle (numpy pow), 1e-13 """
+    rng = np.random.default_rng(31)
+    n, m, d = 333, 257, 3
+    x = rng.uniform(0, 10, (d, n))
+    x[:, 7] = x[:, 3]
+    x[:, 11] = x[:, 12] + 1e6      # far point: tiny but nonzero covariance
+    y = rng.uniform(0, 10, (d, m))
+    xd, yd = torch.tensor(x).to(dev()), torch.tensor(y).to(dev())
+    descs = [dict(kind=_lib.K_CAUCHY, term=0, dimmask=7, par0=2.0, par1=beta, scale_x=1.7, scale_y=1.7, amp=1.3),
+             dict(kind=_lib.K_WHITE, term=1, dimmask=7, amp=0.01),
+             dict(kind=_lib.K_CONSTANT, term=2, dimmask=0, amp=0.25)]
+    terms = [(1.3, [dict(kind='cauchy', alpha=2, beta=beta, scale=1.7)]), (0.01, [dict(kind='white')]),
+             (0.25, [dict(kind='constant')])]
+    for (a, ad, b, bd, sym) in [(x, xd, x, xd, True), (x, xd, y, yd, False)]:
+        Kg = _ops.gram_iso(descs, ad, bd, symmetric=sym).cpu().numpy()
+        Kr = ogp.gram(terms, a, b)
+        assert np.max(np.abs(Kg - Kr) / np.abs(Kr)) < 1e-13
+        if sym:
+            assert np.array_equal(Kg, Kg.T)
+    # the library-path kernel (LGP_GRAM_LIBM) agrees to rounding
+    K1 = _ops.gram_iso(descs[:1], xd, xd, symmetric=True)
+    K2 = _ops.gram_iso(descs[:1], xd, xd, symmetric=True, flags=_lib.GRAM_LIBM) if hasattr(_lib, 'GRAM_LIBM') else K1
+    assert float(((K1 - K2).abs() / K2).max()) < 1e-13

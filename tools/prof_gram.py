@@ -10,6 +10,9 @@ x = torch.rand(3, n, dtype=torch.float64, device=dev) * 10
 if kind == 'matern52':
     descs = [dict(kind=_lib.K_MATERNP, term=0, dimmask=7, ipar=2, par0=0.0, scale_x=1.5, scale_y=1.5, amp=1.0),
              dict(kind=_lib.K_WHITE, term=1, dimmask=7, amp=0.01)]
+elif kind == 'ratquad':
+    descs = [dict(kind=_lib.K_CAUCHY, term=0, dimmask=7, par0=2.0, par1=3.0, scale_x=1.5, scale_y=1.5, amp=1.0),
+             dict(kind=_lib.K_WHITE, term=1, dimmask=7, amp=0.01)]
 else:
     descs = [dict(kind=_lib.K_EXPQUAD, term=0, dimmask=7, scale_x=1.5, scale_y=1.5, amp=1.0),
              dict(kind=_lib.K_WHITE, term=1, dimmask=7, amp=0.01)]
