@@ -12,7 +12,13 @@
  *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it and never synchronise
  *   - return value: 0 = launched ok; <0 = argument/launch error (LGP_ERR_*).  Numerical failure of the
  *     factorisation is reported in the device-side `info` word (LAPACK convention, 1-based pivot index)
- *   - no allocation happens inside the library
+ *   - no device memory is allocated inside the library (it creates a few CUDA streams and events on first use: one
+ *     high-priority panel stream per caller stream, side streams for the inverse recursion)
+ *   - thread safety: entry points may be called concurrently from several host threads on different streams
+ *
+ * Environment switches, for kernel experiments only (the product path needs none): LGP_TRACE (per-panel timeline of the
+ * factorisation, synchronises), LGP_PANEL_BLOCKS (panel width in 128-blocks, default 4), LGP_GRAM_V3=0 (symmetric Gram
+ * through the version-2 kernel), LGP_LEAF=2 (blocked 128x128 leaf of chol_leaf2.cuh).
  */
 #ifndef LGP_B200_H
 #define LGP_B200_H
