@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_kernel(const __grid_co
                                                                  int tiles_n) {
     extern __shared__ __align__(16) double fsm[];
     // layout: su[nd][64], sv[nd][64], (raw copies for White when the main factor rescales) ru[nd][64], rv[nd][64],
-    // then the transpose buffer T[64][65] in symmetric mode
+    // then the transpose buffer T[64][65] (version 1 kernel) in symmetric mode
     const int nd = d.nd;
     double *su = fsm, *sv = fsm + nd * FT;
     double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
                                                                   int tiles_n) {
     extern __shared__ __align__(16) double fsm[];
     // layout: exp table (64 x 16 B), su[nd][64], sv[nd][64], raw copies ru, rv (White with a rescaled main factor),
-    // transpose buffer T[64][65] in symmetric mode
+    // transpose buffer T[64][66] in symmetric mode
     const int nd = d.nd;
     ExpTab *tab = reinterpret_cast<ExpTab *>(fsm);
     const LogTab *ltab = reinterpret_cast<const LogTab *>(fsm + 128);  // rational quadratic only
