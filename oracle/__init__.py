@@ -21,8 +21,11 @@ Pinning status (see tests/test_oracle_*.py, tests/golden/):
   * Matern/Maternp cores: pinned by tests/test_special.py:68-97 restated (mpmath / scipy kv).
   * BART: the fast path is pinned against a restatement of the reference's independent recursive
     implementation `_correlation_old` (tests/kernels/test_bart.py:332-353) and the property tests.
-  * Reference source executed through a NumPy-backed jax shim (oracle/jaxshim) where that was possible:
-    see tests/golden/README.md for which golden files come from the reference's own code.
-  * logML / posterior values of the BASELINE configs: the reference holds no golden numbers
-    ("parity unpinned" for those scalars beyond the component-level pins above and an mpmath anchor).
+  * THE REFERENCE'S OWN SOURCE, executed under a numpy stand-in for the jax API (oracle/refshim.py): lgp.GP
+    .marginal_likelihood / .predfromdata(raw=True), every supported kernel class, _linalg.Chol (value, forward gradient,
+    Fisher matrix, solves) and BART (preprocessing, correlation) produce tests/golden/reference_vectors.npz
+    (tests/golden/gen_reference_vectors.py).  The restatement reproduces those vectors to 0-2 ulp on Gram blocks, exactly
+    on eps, to 1e-13 on logML (tests/test_reference_vectors.py); logML / posterior values of the BASELINE configs are
+    therefore pinned to the reference's code, though not to the JAX runtime (XLA's own rounding is not reproduced; LAPACK
+    is scipy's).  A 50-digit mpmath anchor (tests/test_oracle_mpmath_anchor.py) is the implementation-independent check.
 """

@@ -1,0 +1,234 @@
+"""Parity against golden vectors produced by executing the REFERENCE'S OWN SOURCE under the numpy stand-in for jax
+(oracle/refshim.py, tests/golden/gen_reference_vectors.py -> tests/golden/reference_vectors.npz):
+lgp.GP.marginal_likelihood / predfromdata(raw=True), every supported kernel's Gram block, _linalg.Chol with value,
+forward gradient and Fisher matrix, BART preprocessing and correlation.
+
+  * not gpu: the oracle restatement against the file (pins the oracle to the reference's code, not to a re-reading of it),
+    and, where /root/reference exists, a regeneration in memory that must reproduce the committed file bit for bit;
+  * gpu: the CUDA path (public API and C ABI) against the same file.  Tolerances of BASELINE.json north_star: Gram 1e-13
+    relative (2e-13 for Matern of non-half-integer order: AMOS's own accuracy, tests/test_bessel_cpu.py), logML and
+    posterior mean 1e-9."""
+import pathlib
+
+import numpy as np
+import pytest
+
+from oracle import gp as ogp, decomp as odecomp, bart as obart
+
+GOLD = pathlib.Path(__file__).resolve().parent / 'golden' / 'reference_vectors.npz'
+NAMES = ['f0', 'f1', 'f2']
+
+
+@pytest.fixture(scope='module')
+def vec():
+    return dict(np.load(GOLD))
+
+
+# kernel name -> oracle terms
+GRAM_TERMS = {
+    'expquad': [(1.0, [dict(kind='expquad', scale=1.5)])],
+    'expquad_loc': [(3.0, [dict(kind='expquad', scale=0.3, loc=1.0)])],
+    'maternp0': [(1.0, [dict(kind='constant'), dict(kind='maternp', p=0, scale=2.0)])],
+    'maternp1': [(1.0, [dict(kind='maternp', p=1, scale=2.0)])],
+    'maternp2': [(1.0, [dict(kind='maternp', p=2, scale=2.0)])],
+    'maternp3': [(1.0, [dict(kind='maternp', p=3, scale=2.0)])],
+    'matern05': [(1.0, [dict(kind='matern', nu=0.5, scale=2.0)])],
+    'matern25': [(1.0, [dict(kind='matern', nu=2.5, scale=2.0)])],
+    'matern03': [(1.0, [dict(kind='matern', nu=0.3, scale=2.0)])],
+    'matern13': [(1.0, [dict(kind='matern', nu=1.3, scale=2.0)])],
+    'matern42': [(1.0, [dict(kind='matern', nu=4.2, scale=2.0)])],
+    'ratquad': [(1.0, [dict(kind='cauchy', alpha=2, beta=3.0, scale=1.5)])],
+    'cauchy13': [(1.0, [dict(kind='cauchy', alpha=1.3, beta=0.7, scale=4.0)])],
+    'white_sum': [(2.0, [dict(kind='expquad', scale=1.5)]), (0.01, [dict(kind='white')]), (0.25, [dict(kind='constant')])],
+    'product': [(2.0, [dict(kind='cauchy', alpha=2, beta=3.0, dims=[0]), dict(kind='expquad', scale=0.7, dims=[1])])],
+}
+GP_TERMS = {
+    'c2': [(1.0, [dict(kind='matern', nu=2.5, scale=1.5)]), (0.01, [dict(kind='white')])],
+    'c2nu13': [(1.3, [dict(kind='matern', nu=1.3, scale=1.5)]), (0.01, [dict(kind='white')])],
+    'c3': [(1.44, [dict(kind='expquad', scale=2.0)]), (0.01, [dict(kind='white')])],
+    'rq': [(0.8, [dict(kind='cauchy', alpha=2, beta=3.0, scale=1.5)]), (0.01, [dict(kind='white')])],
+}
+BART_VARIANTS = {
+    'd0': dict(maxd=0), 'd1': dict(maxd=1), 'd2': dict(maxd=2), 'd4r2': dict(maxd=4, reset=2),
+    'd2g': dict(maxd=2, gamma=0.3, intercept=False), 'd10': dict(maxd=10, reset=[2, 4, 6, 8], gamma=1),
+    'd6w': dict(maxd=6, reset=[2, 4], weights=np.array([1., 0., 2., 3., 0.5])),
+}
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    den = np.abs(b).clip(1e-300)
+    return float(np.max(np.abs(a - b) / den))
+
+
+# ------------------------------------------------------------------------------------------------ CPU tier
+def test_committed_file_is_what_the_reference_produces():
+    from oracle import refshim
+    if not refshim.REF_SRC.exists():
+        pytest.skip('reference tree not present (GPU box)')
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('gen_reference_vectors', GOLD.parent / 'gen_reference_vectors.py')
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    fresh = gen.generate()
+    stored = dict(np.load(GOLD))
+    assert set(fresh) == set(stored)
+    for k in stored:
+        assert np.array_equal(np.asarray(fresh[k]), stored[k], equal_nan=True), k
+
+
+def test_oracle_gram_matches_reference(vec):
+    A, B = vec['gram_A'].T.copy(), vec['gram_B'].T.copy()
+    for name, terms in GRAM_TERMS.items():
+        K = ogp.gram(terms, A, B)
+        assert relerr(K, vec['gram_' + name]) <= 1e-15, name       # same formulas, same libm: identical or a few ulp
+
+
+def test_oracle_gp_matches_reference(vec):
+    rng = np.random.default_rng(1001)
+    x = np.sort(rng.uniform(0, 100, 1000))
+    y = np.sin(x / 3) + 0.1 * rng.standard_normal(1000)
+    xp = np.linspace(-5, 105, 500)
+    terms = [(1.0, [dict(kind='expquad', scale=3)])]
+    Kxx, Kxs, Kss = ogp.gram(terms, x[None], x[None]), ogp.gram(terms, x[None], xp[None]), ogp.gram(terms, xp[None], xp[None])
+    ycov = 0.01 * np.eye(1000)
+    assert abs(ogp.logml(Kxx, y, ycov) - vec['c1_logml']) <= 1e-13 * abs(vec['c1_logml'])
+    m, c = ogp.pred(Kxx, Kxs, Kss, y, ycov)
+    assert relerr(m, vec['c1_mean']) <= 1e-12
+    assert np.max(np.abs(np.diag(c) - vec['c1_cov_diag'])) <= 1e-13
+    X, y2, Xs = vec['c2_X'], vec['c2_y'], vec['c2_Xs']
+    for tag, terms in GP_TERMS.items():
+        K = ogp.gram(terms, X.T.copy(), X.T.copy())
+        assert relerr(K[:5], vec[tag + '_prior_rows']) <= 4e-16, tag
+        assert abs(ogp.logml(K, y2) - vec[tag + '_logml']) <= 1e-13 * abs(vec[tag + '_logml']), tag
+        Kxs = ogp.gram(terms, X.T.copy(), Xs.T.copy())      # (the White term lives on every key of the GP)
+        Kss = ogp.gram(terms, Xs.T.copy(), Xs.T.copy())
+        m, c = ogp.pred(K, Kxs, Kss, y2)
+        assert np.max(np.abs(m - vec[tag + '_mean'])) <= 1e-12 * np.max(np.abs(vec[tag + '_mean'])), tag
+        assert np.max(np.abs(c - vec[tag + '_cov'])) <= 1e-12, tag
+
+
+@pytest.mark.parametrize('nn', [10, 64])
+def test_oracle_chol_matches_reference(vec, nn):
+    g = lambda k: vec[f'chol{nn}_{k}']
+    dec = odecomp.Chol(g('K'))
+    assert dec.eps == float(g('eps'))
+    val, _, gradfwd, fisher, _ = dec.minus_log_normal_density(g('r'), dK=g('dK'), dr=g('dr'), value=True, gradfwd=True,
+                                                             fisher=True)
+    assert abs(val - float(g('value'))) <= 1e-14 * abs(float(g('value')))
+    np.testing.assert_allclose(gradfwd, g('gradfwd'), rtol=1e-12)
+    np.testing.assert_allclose(fisher, g('fisher'), rtol=1e-12)
+    np.testing.assert_allclose(dec.ginv_linear(g('A')), g('ginv_linear'), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(dec.ginv_quad(g('A')), g('ginv_quad'), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(dec.pinv_bilinear(g('A'), g('r')), g('pinv_bilinear'), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(dec.correlate(g('r')), g('correlate'), rtol=1e-13)
+    np.testing.assert_allclose(dec.pinv_correlate(g('r')), g('pinv_correlate'), rtol=1e-12)
+
+
+def test_oracle_bart_matches_reference(vec):
+    length, splits = obart.splits_from_coord(vec['bart_X'])
+    assert np.array_equal(length, vec['bart_length']) and np.array_equal(splits, vec['bart_splits'])
+    idx = obart.indices_from_coord(vec['bart_X'], (length, splits))
+    assert np.array_equal(idx, vec['bart_idx'])
+    for name, kw in BART_VARIANTS.items():
+        c = obart.gram(length, idx, idx, **kw)
+        ref = vec['bart_corr_' + name]
+        assert np.max(np.abs(c - ref) / np.spacing(np.abs(ref))) <= 32, name   # the reference's own bar between its two paths
+
+
+# ------------------------------------------------------------------------------------------------ GPU tier
+def _structured(lgp, X):
+    return lgp.unstructured_to_structured(np.ascontiguousarray(X), names=NAMES)
+
+
+@pytest.mark.gpu
+def test_cuda_gram_matches_reference(vec):
+    import lsqfitgp_b200 as lgp
+    A, B = vec['gram_A'], vec['gram_B']
+    xa, xb = _structured(lgp, A), _structured(lgp, B)
+    kernels = {
+        'expquad': lgp.ExpQuad(scale=1.5),
+        'expquad_loc': 3.0 * lgp.ExpQuad(scale=0.3, loc=1.0),
+        'maternp0': lgp.Constant() * lgp.Maternp(p=0, scale=2.0),
+        'maternp1': lgp.Maternp(p=1, scale=2.0),
+        'maternp2': lgp.Maternp(p=2, scale=2.0),
+        'maternp3': lgp.Maternp(p=3, scale=2.0),
+        'matern05': lgp.Matern(nu=0.5, scale=2.0),
+        'matern25': lgp.Matern(nu=2.5, scale=2.0),
+        'matern03': lgp.Matern(nu=0.3, scale=2.0),
+        'matern13': lgp.Matern(nu=1.3, scale=2.0),
+        'matern42': lgp.Matern(nu=4.2, scale=2.0),
+        'ratquad': lgp.Cauchy(alpha=2, beta=3.0, scale=1.5),
+        'cauchy13': lgp.Cauchy(alpha=1.3, beta=0.7, scale=4.0),
+        'white_sum': 2.0 * lgp.ExpQuad(scale=1.5) + 0.01 * lgp.White() + 0.25,
+        'product': lgp.Cauchy(alpha=2, beta=3.0, dim='f0') * (2.0 * lgp.ExpQuad(scale=0.7, dim='f1')),
+    }
+    for name, k in kernels.items():
+        K = k(xa.reshape(-1, 1), xb.reshape(1, -1))
+        tol = 2e-13 if name in ('matern03', 'matern13', 'matern42') else 1e-13
+        assert relerr(K, vec['gram_' + name]) <= tol, name
+
+
+@pytest.mark.gpu
+def test_cuda_gp_matches_reference(vec):
+    import lsqfitgp_b200 as lgp
+    rng = np.random.default_rng(1001)
+    x = np.sort(rng.uniform(0, 100, 1000))
+    y = np.sin(x / 3) + 0.1 * rng.standard_normal(1000)
+    xp = np.linspace(-5, 105, 500)
+    gp = lgp.GP(lgp.ExpQuad(scale=3), checkpos=False).addx(x, 'data').addx(xp, 'pred')
+    ycov = {('data', 'data'): 0.01 * np.eye(1000)}
+    ml = gp.marginal_likelihood({'data': y}, ycov)
+    assert abs(ml - vec['c1_logml']) <= 1e-9 * abs(vec['c1_logml'])
+    m, c = gp.predfromdata({'data': y}, 'pred', ycov, raw=True)
+    assert relerr(m, vec['c1_mean']) <= 1e-9
+    assert np.max(np.abs(np.diag(c) - vec['c1_cov_diag'])) <= 1e-9
+    assert np.max(np.abs(c[::25, ::25] - vec['c1_cov_sub'])) <= 1e-9
+    X, y2, Xs = vec['c2_X'], vec['c2_y'], vec['c2_Xs']
+    kernels = {'c2': 1.0 ** 2 * lgp.Matern(nu=2.5, scale=1.5) + 0.1 ** 2 * lgp.White(),
+               'c2nu13': 1.3 * lgp.Matern(nu=1.3, scale=1.5) + 0.1 ** 2 * lgp.White(),
+               'c3': 1.2 ** 2 * lgp.ExpQuad(scale=2.0) + 0.1 ** 2 * lgp.White(),
+               'rq': 0.8 * lgp.Cauchy(alpha=2, beta=3.0, scale=1.5) + 0.1 ** 2 * lgp.White()}
+    for tag, kern in kernels.items():
+        gp = lgp.GP(kern, checkpos=False).addx(_structured(lgp, X), 'data').addx(_structured(lgp, Xs), 'pred')
+        ml = gp.marginal_likelihood({'data': y2})
+        assert abs(ml - vec[tag + '_logml']) <= 1e-9 * abs(vec[tag + '_logml']), tag
+        m, c = gp.predfromdata({'data': y2}, 'pred', raw=True)
+        assert np.max(np.abs(m - vec[tag + '_mean'])) <= 1e-9 * np.max(np.abs(vec[tag + '_mean'])), tag
+        assert np.max(np.abs(c - vec[tag + '_cov'])) <= 1e-9, tag
+        tol = 2e-13 if tag == 'c2nu13' else 1e-13
+        assert relerr(gp.prior('data', raw=True)[:5], vec[tag + '_prior_rows']) <= tol, tag
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nn', [10, 64])
+def test_cuda_chol_matches_reference(vec, nn):
+    import lsqfitgp_b200 as lgp
+    g = lambda k: vec[f'chol{nn}_{k}']
+    dec = lgp._linalg.Chol(g('K'))
+    assert abs(dec.eps - float(g('eps'))) <= 1e-13 * float(g('eps'))
+    val, _, gradfwd, fisher, _ = dec.minus_log_normal_density(g('r'), dK=g('dK'), dr=g('dr'), value=True, gradfwd=True,
+                                                             fisher=True)
+    assert abs(val - float(g('value'))) <= 1e-9 * abs(float(g('value')))
+    np.testing.assert_allclose(gradfwd, g('gradfwd'), rtol=1e-9, atol=1e-9 * np.abs(g('gradfwd')).max())
+    np.testing.assert_allclose(fisher, g('fisher'), rtol=1e-9, atol=1e-9 * np.abs(g('fisher')).max())
+    np.testing.assert_allclose(dec.ginv_linear(g('A')), g('ginv_linear'), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(dec.ginv_quad(g('A')), g('ginv_quad'), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(dec.pinv_bilinear(g('A'), g('r')), g('pinv_bilinear'), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(dec.correlate(g('r')), g('correlate'), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(dec.pinv_correlate(g('r')), g('pinv_correlate'), rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cuda_bart_matches_reference(vec):
+    import lsqfitgp_b200 as lgp
+    X4 = vec['bart_X']
+    length, splits = lgp.BART.splits_from_coord(X4)
+    assert np.array_equal(length, vec['bart_length']) and np.array_equal(splits, vec['bart_splits'])
+    idx = lgp.BART.indices_from_coord(X4, (length, splits))
+    assert np.array_equal(idx, vec['bart_idx'])
+    xi = lgp.unstructured_to_structured(idx.astype(np.int32), names=[f'c{i}' for i in range(5)])
+    for name, kw in BART_VARIANTS.items():
+        kb = lgp.BART(splits=(length, splits), indices=True, **kw)
+        K = lgp.GP(kb, checkpos=False, checksym=False).addx(xi, 't').prior('t', raw=True)
+        assert relerr(K, vec['bart_corr_' + name]) <= 1e-13, name
