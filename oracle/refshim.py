@@ -200,11 +200,27 @@ def install():
         else (lambda f: _CustomJVP(f, nondiff_argnums))
     jax.custom_vjp = jax.custom_jvp
     jax.ensure_compile_time_eval = contextlib.nullcontext
-    for name in ('vjp', 'jvp', 'jacfwd', 'jacrev', 'grad', 'value_and_grad', 'vmap', 'linearize'):
+    for name in ('vjp', 'jvp', 'jacfwd', 'jacrev', 'grad', 'value_and_grad', 'linearize'):
         setattr(jax, name, _not_available(name))
+
+    def vmap(f, in_axes=0, out_axes=0):
+        """ jax.vmap by an explicit loop over the mapped axis (array arguments and a single array output) """
+        def g(*args):
+            axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+            n = next(numpy.shape(a)[ax] for a, ax in zip(args, axes) if ax is not None)
+            outs = [f(*[a if ax is None else numpy.take(numpy.asarray(a), i, axis=ax) for a, ax in zip(args, axes)])
+                    for i in range(n)]
+            return numpy.stack([numpy.asarray(o) for o in outs], axis=out_axes).view(Array)
+        return g
+    jax.vmap = vmap
     jax.pure_callback = lambda callback, result_shape, *args, **kw: _wrap(callback(*args))
     jax.ShapeDtypeStruct = lambda shape, dtype: types.SimpleNamespace(shape=shape, dtype=dtype)
-    jax.eval_shape = lambda f, *a, **k: _wrap(f(*a, **k))  # (only .shape / .dtype of the result are used)
+    def eval_shape(f, *a, **k):
+        """ abstract evaluation: inputs may be shape/dtype mock-ups; only .shape / .dtype of the result are used """
+        conc = [numpy.zeros(x.shape, x.dtype).view(Array)
+                if (hasattr(x, 'shape') and hasattr(x, 'dtype') and not isinstance(x, numpy.ndarray)) else x for x in a]
+        return _wrap(f(*conc, **k))
+    jax.eval_shape = eval_shape
     errors = types.ModuleType('jax.errors')
 
     class ConcretizationTypeError(Exception):

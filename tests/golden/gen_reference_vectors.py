@@ -137,6 +137,25 @@ def generate():
     for name, kw in variants.items():
         out['bart_corr_' + name] = np.asarray(bartm.BART.correlation(np.asarray(length), idx[:, None, :], idx[None, :, :],
                                                                      altinput=True, **kw))
+    # ---- config C4 recipe (bayestree.bart, reference bayestree/_bart.py:187-227): lambda^2 BART + sigma^2 I + k^2 through
+    # addx / addcov / addtransf of the reference's GP, epsrel = 0
+    rng = np.random.default_rng(4005)
+    nr = 40
+    X5 = np.concatenate([rng.standard_normal((nr, 4)), rng.integers(0, 2, (nr, 1)).astype(float)], axis=1)
+    sp = bartm.BART.splits_from_coord(X5)
+    idx5 = np.asarray(bartm.BART.indices_from_coord(X5, sp))
+    xi = np.zeros(nr, dtype=[(f'c{i}', 'i4') for i in range(5)])
+    for i in range(5):
+        xi[f'c{i}'] = idx5[:, i]
+    y5 = rng.standard_normal(nr)
+    lam, sig, kk = 1.3, 0.5, 0.7
+    kb = bartm.BART(splits=sp, indices=True, maxd=10, reset=[2, 4, 6, 8])
+    gp = (GP(lam ** 2 * kb, checkpos=False, checksym=False, epsrel=0)
+          .addx(xi, 'trainmean').addcov(sig ** 2 * np.eye(nr), 'trainnoise').addcov(kk ** 2, 'mean')
+          .addtransf({'trainmean': 1, 'trainnoise': 1, 'mean': 1}, 'train'))
+    out['c4_X'], out['c4_y'] = X5, y5
+    out['c4_logml'] = float(gp.marginal_likelihood({'train': y5}))
+    out['c4_prior'] = np.asarray(gp.prior('train', raw=True))
     return out
 
 

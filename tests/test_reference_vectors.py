@@ -136,6 +136,15 @@ def test_oracle_bart_matches_reference(vec):
         assert np.max(np.abs(c - ref) / np.spacing(np.abs(ref))) <= 32, name   # the reference's own bar between its two paths
 
 
+def test_oracle_bart_recipe_matches_reference(vec):
+    X5, y5 = vec['c4_X'], vec['c4_y']
+    length, splits = obart.splits_from_coord(X5)
+    idx = obart.indices_from_coord(X5, (length, splits))
+    K = 1.3 ** 2 * obart.gram(length, idx, idx, maxd=10, reset=[2, 4, 6, 8]) + 0.25 * np.eye(len(y5)) + 0.49
+    assert relerr(K, vec['c4_prior']) <= 1e-14
+    assert abs(ogp.logml(K, y5, epsrel=0) - vec['c4_logml']) <= 1e-13 * abs(vec['c4_logml'])
+
+
 # ------------------------------------------------------------------------------------------------ GPU tier
 def _structured(lgp, X):
     return lgp.unstructured_to_structured(np.ascontiguousarray(X), names=NAMES)
@@ -232,3 +241,21 @@ def test_cuda_bart_matches_reference(vec):
         kb = lgp.BART(splits=(length, splits), indices=True, **kw)
         K = lgp.GP(kb, checkpos=False, checksym=False).addx(xi, 't').prior('t', raw=True)
         assert relerr(K, vec['bart_corr_' + name]) <= 1e-13, name
+
+
+@pytest.mark.gpu
+def test_cuda_bart_recipe_matches_reference(vec):
+    """ config C4 recipe through the public API exactly as the reference's bayestree.bart builds it """
+    import lsqfitgp_b200 as lgp
+    X5, y5 = vec['c4_X'], vec['c4_y']
+    n = len(y5)
+    sp = lgp.BART.splits_from_coord(X5)
+    idx = lgp.BART.indices_from_coord(X5, sp)
+    xi = lgp.unstructured_to_structured(idx.astype(np.int32), names=[f'c{i}' for i in range(5)])
+    kb = lgp.BART(splits=sp, indices=True, maxd=10, reset=[2, 4, 6, 8])
+    gp = (lgp.GP(1.3 ** 2 * kb, checkpos=False, checksym=False, epsrel=0)
+          .addx(xi, 'trainmean').addcov(0.5 ** 2 * np.eye(n), 'trainnoise').addcov(0.7 ** 2, 'mean')
+          .addtransf({'trainmean': 1, 'trainnoise': 1, 'mean': 1}, 'train'))
+    assert relerr(gp.prior('train', raw=True), vec['c4_prior']) <= 1e-13
+    ml = gp.marginal_likelihood({'train': y5})
+    assert abs(ml - vec['c4_logml']) <= 1e-9 * abs(vec['c4_logml'])
