@@ -116,6 +116,14 @@ def generate():
         out[f'chol{nn}_value'] = float(val)
         out[f'chol{nn}_gradfwd'] = np.asarray(gradfwd)
         out[f'chol{nn}_fisher'] = np.asarray(fisher)
+        # reverse-mode assembly (_decomp.py:505-512) and Fisher-vector product (:560-582) with explicit callbacks
+        vecv = rng.standard_normal(2)
+        _, gradrev, _, _, fishvec = dec.minus_log_normal_density(
+            r, dK_vjp=lambda G: np.einsum('ij,ijk->k', np.asarray(G), dK), dr_vjp=lambda g: np.asarray(g) @ dr,
+            dK_jvp_vec=dK @ vecv, dr_jvp_vec=dr @ vecv, gradrev=True, fishvec=True)
+        out[f'chol{nn}_vec'] = vecv
+        out[f'chol{nn}_gradrev'] = np.asarray(gradrev)
+        out[f'chol{nn}_fishvec'] = np.asarray(fishvec)
         out[f'chol{nn}_ginv_linear'] = np.asarray(dec.ginv_linear(Amat))
         out[f'chol{nn}_ginv_quad'] = np.asarray(dec.ginv_quad(Amat))
         out[f'chol{nn}_pinv_bilinear'] = np.asarray(dec.pinv_bilinear(Amat, r))

@@ -118,6 +118,14 @@ def test_oracle_chol_matches_reference(vec, nn):
     assert abs(val - float(g('value'))) <= 1e-14 * abs(float(g('value')))
     np.testing.assert_allclose(gradfwd, g('gradfwd'), rtol=1e-12)
     np.testing.assert_allclose(fisher, g('fisher'), rtol=1e-12)
+    dK, dr, v = g('dK'), g('dr'), g('vec')
+    _, gradrev, _, _, fishvec = dec.minus_log_normal_density(
+        g('r'), dK_vjp=lambda G: np.einsum('ij,ijk->k', G, dK), dr_vjp=lambda x: x @ dr, dK_jvp_vec=dK @ v, dr_jvp_vec=dr @ v,
+        gradrev=True, fishvec=True)
+    np.testing.assert_allclose(gradrev, g('gradrev'), rtol=1e-12)
+    np.testing.assert_allclose(fishvec, g('fishvec'), rtol=1e-12)
+    np.testing.assert_allclose(gradrev, g('gradfwd'), rtol=1e-9)      # the two modes agree (reference test :241-261)
+    np.testing.assert_allclose(fishvec, g('fisher') @ v, rtol=1e-9)
     np.testing.assert_allclose(dec.ginv_linear(g('A')), g('ginv_linear'), rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(dec.ginv_quad(g('A')), g('ginv_quad'), rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(dec.pinv_bilinear(g('A'), g('r')), g('pinv_bilinear'), rtol=1e-12, atol=1e-15)
@@ -221,6 +229,12 @@ def test_cuda_chol_matches_reference(vec, nn):
     assert abs(val - float(g('value'))) <= 1e-9 * abs(float(g('value')))
     np.testing.assert_allclose(gradfwd, g('gradfwd'), rtol=1e-9, atol=1e-9 * np.abs(g('gradfwd')).max())
     np.testing.assert_allclose(fisher, g('fisher'), rtol=1e-9, atol=1e-9 * np.abs(g('fisher')).max())
+    dK, dr, v = g('dK'), g('dr'), g('vec')
+    _, gradrev, _, _, fishvec = dec.minus_log_normal_density(
+        g('r'), dK_vjp=lambda G: np.einsum('ij,ijk->k', np.asarray(G), dK), dr_vjp=lambda x: np.asarray(x) @ dr,
+        dK_jvp_vec=dK @ v, dr_jvp_vec=dr @ v, gradrev=True, fishvec=True)
+    np.testing.assert_allclose(gradrev, g('gradrev'), rtol=1e-9, atol=1e-9 * np.abs(g('gradrev')).max())
+    np.testing.assert_allclose(fishvec, g('fishvec'), rtol=1e-9, atol=1e-9 * np.abs(g('fishvec')).max())
     np.testing.assert_allclose(dec.ginv_linear(g('A')), g('ginv_linear'), rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(dec.ginv_quad(g('A')), g('ginv_quad'), rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(dec.pinv_bilinear(g('A'), g('r')), g('pinv_bilinear'), rtol=1e-9, atol=1e-12)
