@@ -145,6 +145,28 @@ def generate():
     for name, kw in variants.items():
         out['bart_corr_' + name] = np.asarray(bartm.BART.correlation(np.asarray(length), idx[:, None, :], idx[None, :, :],
                                                                      altinput=True, **kw))
+    # ---- multi-key GP: two sets of points, a linear transformation of both, data on the transformed key and on one set;
+    # predfromdata on several keys, predfromfit with a given covariance, prior blocks (_GP/_elements.py, _compute.py)
+    rng = np.random.default_rng(77)
+    xa_, xb_ = np.sort(rng.uniform(0, 10, 25)), np.sort(rng.uniform(0, 10, 18))
+    Ta, Tb = rng.standard_normal((7, 25)), rng.standard_normal((7, 18))
+    yc, ya = rng.standard_normal(7), rng.standard_normal(25)
+    R = rng.standard_normal((7, 7))
+    ccov = R @ R.T / 7 + 0.1 * np.eye(7)
+    gp = (GP(1.5 * basic.ExpQuad(scale=2.0) + 0.05 * matern.Maternp(p=1, scale=0.7), checkpos=False)
+          .addx(xa_, 'a').addx(xb_, 'b').addtransf({'a': Ta, 'b': Tb}, 'c'))
+    out['mk_xa'], out['mk_xb'], out['mk_Ta'], out['mk_Tb'] = xa_, xb_, Ta, Tb
+    out['mk_yc'], out['mk_ya'], out['mk_ccov'] = yc, ya, ccov
+    pr = gp.prior(['a', 'c'], raw=True)
+    out['mk_prior_ac'], out['mk_prior_cc'] = np.asarray(pr['a', 'c']), np.asarray(pr['c', 'c'])
+    out['mk_logml'] = float(gp.marginal_likelihood({'c': yc, 'a': ya}, {('c', 'c'): ccov, ('a', 'a'): 0.01 * np.eye(25),
+                                                                         ('c', 'a'): np.zeros((7, 25)), ('a', 'c'): np.zeros((25, 7))}))
+    m, c = gp.predfromdata({'c': yc}, ['a', 'b'], {('c', 'c'): ccov}, raw=True)
+    out['mk_mean_a'], out['mk_mean_b'] = np.asarray(m['a']), np.asarray(m['b'])
+    out['mk_cov_ab'], out['mk_cov_bb'] = np.asarray(c['a', 'b']), np.asarray(c['b', 'b'])
+    m, c = gp.predfromfit({'c': yc}, 'b', {('c', 'c'): ccov}, raw=True)
+    out['mk_fit_mean_b'], out['mk_fit_cov_bb'] = np.asarray(m), np.asarray(c)
+
     # ---- config C4 recipe (bayestree.bart, reference bayestree/_bart.py:187-227): lambda^2 BART + sigma^2 I + k^2 through
     # addx / addcov / addtransf of the reference's GP, epsrel = 0
     rng = np.random.default_rng(4005)

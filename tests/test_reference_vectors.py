@@ -273,3 +273,27 @@ def test_cuda_bart_recipe_matches_reference(vec):
     assert relerr(gp.prior('train', raw=True), vec['c4_prior']) <= 1e-13
     ml = gp.marginal_likelihood({'train': y5})
     assert abs(ml - vec['c4_logml']) <= 1e-9 * abs(vec['c4_logml'])
+
+
+@pytest.mark.gpu
+def test_cuda_multikey_gp_matches_reference(vec):
+    """ several keys, addtransf, data on two keys with given covariances, predfromdata on a list of keys, predfromfit:
+    the reference's GP orchestration (_GP/_elements.py:248-649, _compute.py:138-322) against this one """
+    import lsqfitgp_b200 as lgp
+    g = lambda k: vec['mk_' + k]
+    gp = (lgp.GP(1.5 * lgp.ExpQuad(scale=2.0) + 0.05 * lgp.Maternp(p=1, scale=0.7), checkpos=False)
+          .addx(g('xa'), 'a').addx(g('xb'), 'b').addtransf({'a': g('Ta'), 'b': g('Tb')}, 'c'))
+    pr = gp.prior(['a', 'c'], raw=True)
+    np.testing.assert_allclose(pr['a', 'c'], g('prior_ac'), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(pr['c', 'c'], g('prior_cc'), rtol=1e-12, atol=1e-12)
+    ml = gp.marginal_likelihood({'c': g('yc'), 'a': g('ya')}, {('c', 'c'): g('ccov'), ('a', 'a'): 0.01 * np.eye(25),
+                                                              ('c', 'a'): np.zeros((7, 25)), ('a', 'c'): np.zeros((25, 7))})
+    assert abs(ml - float(g('logml'))) <= 1e-9 * abs(float(g('logml')))
+    m, c = gp.predfromdata({'c': g('yc')}, ['a', 'b'], {('c', 'c'): g('ccov')}, raw=True)
+    np.testing.assert_allclose(m['a'], g('mean_a'), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(m['b'], g('mean_b'), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(c['a', 'b'], g('cov_ab'), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(c['b', 'b'], g('cov_bb'), rtol=1e-9, atol=1e-10)
+    m, c = gp.predfromfit({'c': g('yc')}, 'b', {('c', 'c'): g('ccov')}, raw=True)
+    np.testing.assert_allclose(m, g('fit_mean_b'), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(c, g('fit_cov_bb'), rtol=1e-9, atol=1e-10)
