@@ -94,6 +94,23 @@ def generate():
     for name, k in kernels.items():
         out['gram_' + name] = np.asarray(k(xa[:, None], xb[None, :]))
 
+    # ---- input formats: a field with a shape (reduced with a sum over its last axis, _Kernel/_util.py:74-99), `dim=` on it,
+    # unstructured 1-D inputs with broadcasting, integer inputs
+    rng = np.random.default_rng(12)
+    xs_ = np.zeros(20, dtype=[('a', float), ('b', float, 3)])
+    ys_ = np.zeros(15, dtype=xs_.dtype)
+    xs_['a'], xs_['b'] = rng.uniform(0, 5, 20), rng.uniform(0, 5, (20, 3))
+    ys_['a'], ys_['b'] = rng.uniform(0, 5, 15), rng.uniform(0, 5, (15, 3))
+    out['fmt_xa'], out['fmt_xb'], out['fmt_ya'], out['fmt_yb'] = xs_['a'], xs_['b'], ys_['a'], ys_['b']
+    out['fmt_shaped'] = np.asarray(matern.Matern(nu=1.5, scale=1.3)(xs_[:, None], ys_[None, :]))
+    out['fmt_dim_b'] = np.asarray(basic.ExpQuad(scale=0.9, dim='b')(xs_[:, None], ys_[None, :]))
+    out['fmt_dim_a_times_b'] = np.asarray((basic.ExpQuad(dim='a') * basic.Cauchy(beta=2.0, dim='b'))(xs_[:, None], ys_[None, :]))
+    u1, v1 = rng.uniform(0, 5, 12), rng.uniform(0, 5, 9)
+    out['fmt_u'], out['fmt_v'] = u1, v1
+    out['fmt_plain'] = np.asarray(matern.Maternp(p=2, scale=0.8, loc=0.5)(u1[:, None], v1[None, :]))
+    ui, vi = np.arange(6), np.arange(4, 9)
+    out['fmt_int'] = np.asarray((2 * basic.ExpQuad(scale=3) + basic.White())(ui[:, None], vi[None, :]))
+
     # ---- Chol (reference tests/linalg/test_decomp.py matrices) with value, forward gradient and Fisher matrix
     from scipy import stats
     rng = np.random.default_rng(5)

@@ -297,3 +297,22 @@ def test_cuda_multikey_gp_matches_reference(vec):
     m, c = gp.predfromfit({'c': g('yc')}, 'b', {('c', 'c'): g('ccov')}, raw=True)
     np.testing.assert_allclose(m, g('fit_mean_b'), rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(c, g('fit_cov_bb'), rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_cuda_input_formats_match_reference(vec):
+    """ fields with a shape, `dim=` selecting such a field, unstructured inputs with broadcasting, integer inputs """
+    import lsqfitgp_b200 as lgp
+    xs = np.zeros(20, dtype=[('a', float), ('b', float, 3)])
+    ys = np.zeros(15, dtype=xs.dtype)
+    xs['a'], xs['b'], ys['a'], ys['b'] = vec['fmt_xa'], vec['fmt_xb'], vec['fmt_ya'], vec['fmt_yb']
+    K = lgp.Matern(nu=1.5, scale=1.3)(xs[:, None], ys[None, :])
+    assert relerr(K, vec['fmt_shaped']) <= 1e-13
+    K = lgp.ExpQuad(scale=0.9, dim='b')(xs[:, None], ys[None, :])
+    assert relerr(K, vec['fmt_dim_b']) <= 1e-13
+    K = (lgp.ExpQuad(dim='a') * lgp.Cauchy(beta=2.0, dim='b'))(xs[:, None], ys[None, :])
+    assert relerr(K, vec['fmt_dim_a_times_b']) <= 1e-13
+    K = lgp.Maternp(p=2, scale=0.8, loc=0.5)(vec['fmt_u'][:, None], vec['fmt_v'][None, :])
+    assert relerr(K, vec['fmt_plain']) <= 1e-13
+    K = (2 * lgp.ExpQuad(scale=3) + lgp.White())(np.arange(6)[:, None], np.arange(4, 9)[None, :])
+    assert relerr(K, vec['fmt_int']) <= 1e-13
