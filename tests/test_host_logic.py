@@ -98,3 +98,23 @@ def test_bart_preprocessing_matches_oracle(rng):
     xs = lgp.unstructured_to_structured(X)
     l3, s3 = lgp.BART.splits_from_coord(xs)
     np.testing.assert_array_equal(l1, l3)
+
+
+def test_peer_buffer_addressing():
+    """ address arithmetic of the symmetric allocation used by the fused TRSM -> broadcast path (no GPU needed) """
+    import types
+    import torch
+    from lsqfitgp_b200 import _dist
+    t = torch.zeros(64 + 100, dtype=torch.float64)
+    h = types.SimpleNamespace(buffer_ptrs=[0x1000, 0x9000], multicast_ptr=0x20000)
+    pb = _dist._PeerBuffer(t, h, 64)
+    assert pb.flag_addr(1, 0) == 0x9000 and pb.flag_addr(0, 17) == 0x1000 + 8 * 17
+    assert pb.data_addr(0, 0) == 0x1000 + 8 * 64 and pb.data_addr(1, 10) == 0x9000 + 8 * 74
+    assert pb.data_addr('mc', 3) == 0x20000 + 8 * 67
+    assert pb.data.numel() == 100 and pb.multicast == 0x20000
+    h2 = types.SimpleNamespace(buffer_ptrs=[0x1000], multicast_ptr=0)
+    assert _dist._PeerBuffer(t, h2, 64).multicast == 0
+    with pytest.raises(AssertionError):
+        pb.flag_addr(0, 64)
+    # without a process group the reservation is a no-op
+    assert _dist.peer_reserve(5000, 512, 'cpu') is False
