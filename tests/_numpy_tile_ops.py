@@ -143,3 +143,71 @@ class NumpyTileOps:
             return
         p = P.numpy()
         y.numpy()[...] += alpha * ((p.T @ x.numpy()) if trans else (p @ x.numpy()))
+
+
+class NumpyPeerTileOps(NumpyTileOps):
+    """ Adds a simulation of peer-mapped memory to the NumPy provider, so that the fused "panel solve -> broadcast" branch of
+    DistChol._factor (slab / diagonal buffers living in a symmetric allocation, release/acquire counters) runs on CPU:
+    the symmetric allocation of rank q is a tensor in POSIX shared memory that every process of the test maps
+    (`bufs[q]`), "addresses" are (rank + 1) << 44 | byte offset (rank index 15 = the multicast mapping: a store goes to every
+    rank), stores are NumPy copies, counters are int64 words of the same buffers polled with a sleep.  The processes run
+    concurrently, so the READY / DONE protocol is exercised for real. """
+
+    NFLAGS = 64
+    SHIFT = 44
+    MC = 15
+
+    def __init__(self, K, bufs, rank, multicast):
+        super().__init__(K)
+        self.bufs, self.rank, self.multicast = bufs, rank, multicast
+        self.device = torch.device('cpu')
+
+    def peer_setup(self, count, group):
+        import types
+        from lsqfitgp_b200 import _dist
+        t = self.bufs[self.rank]
+        assert t.numel() >= self.NFLAGS + count
+        t[:self.NFLAGS].zero_()
+        h = types.SimpleNamespace(buffer_ptrs=[(q + 1) << self.SHIFT for q in range(len(self.bufs))],
+                                  multicast_ptr=(self.MC + 1) << self.SHIFT if self.multicast else 0)
+        return _dist._PeerBuffer(t, h, self.NFLAGS)
+
+    def _targets(self, addr):
+        q = (addr >> self.SHIFT) - 1
+        off = (addr & ((1 << self.SHIFT) - 1)) // 8
+        return (list(range(len(self.bufs))) if q == self.MC else [q]), off
+
+    def _store(self, src, dst_ptrs, ld_dst):
+        rows, cols = src.shape
+        for addr in dst_ptrs:
+            ranks, off = self._targets(addr)
+            for q in ranks:
+                self.bufs[q][off:off + rows * ld_dst].view(rows, ld_dst)[:, :cols] = src
+
+    def trsm_right_bcast(self, L, invd, B, dst_ptrs, ld_dst, multimem):
+        if B.shape[0] == 0:
+            return
+        assert bool(multimem) == self.multicast and (len(dst_ptrs) == 1 or not multimem)
+        self.trsm_right(L, invd, B)
+        self._store(B, dst_ptrs, ld_dst)
+
+    def copy2d_bcast(self, src, dst_ptrs, ld_dst, multimem):
+        self._store(src, dst_ptrs, ld_dst)
+
+    def flag_signal(self, ptrs, value):
+        for addr in ptrs:
+            ranks, off = self._targets(addr)
+            assert off < self.NFLAGS and len(ranks) == 1
+            self.bufs[ranks[0]][:self.NFLAGS].view(torch.int64)[off] = int(value)
+
+    def flag_wait(self, addr, n, value, timeout_ms, err):
+        import time
+        ranks, off = self._targets(addr)
+        assert ranks == [self.rank] and off + n <= self.NFLAGS     # waits are on local memory only
+        flags = self.bufs[self.rank][:self.NFLAGS].view(torch.int64)
+        t0 = time.monotonic()
+        while not bool((flags[off:off + n] >= int(value)).all()):
+            if (time.monotonic() - t0) * 1e3 > timeout_ms:
+                err[0] = 1
+                return
+            time.sleep(0.0005)

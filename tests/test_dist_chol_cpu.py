@@ -142,3 +142,56 @@ def test_two_ranks_gloo(n, T, grid):
     for rank, status, ld in res:
         assert status == 'ok', (rank, status)
     assert res[0][2] == res[1][2]  # replicated result is bit-identical on the two ranks
+
+
+def _peer_count(n, T, grid):
+    """ doubles of the symmetric allocation DistChol asks for (mirrors DistChol.__init__) """
+    Pr, Pc = grid
+    lay = Layout(n, T, Pr, Pc, 0)
+    slab_cap = max(max(lay.panel_count(0, r) for r in range(Pr)), 1) * T * T
+    diag_cap = T * T + (T // 128) * 128 * 128 if Pr > 1 else 0
+    return 2 * Pr * slab_cap + 2 * diag_cap
+
+
+def _peer_worker(rank, world, port, n, T, grid, multicast, bufs, q):
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _numpy_tile_ops import NumpyPeerTileOps
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        K = _matrix(n)
+        b = np.random.default_rng(1).standard_normal(n)
+        x = torch.zeros(1, n, dtype=torch.float64)
+        dc = _dist.DistChol(None, x, tile=T, grid=grid, ops=NumpyPeerTileOps(K, bufs, rank, multicast), peer=True)
+        try:
+            assert dc.peer_mode == ('multimem' if multicast else 'p2p')
+            _check_against_oracle(dc, K, b)
+            q.put((rank, 'ok', dc.logdet()))
+        except AssertionError as e:
+            q.put((rank, 'fail: ' + str(e)[:500], None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n,T,grid,multicast', [(900, 128, (2, 1), True), (900, 128, (2, 1), False),
+                                                (900, 128, (1, 2), True), (520, 256, (2, 1), False)])
+def test_two_ranks_fused_panel_path_shared_memory(n, T, grid, multicast):
+    """ the peer-memory branch of the factorisation (slabs and diagonal tile stored into every rank's buffer by the
+    producer, READY / READYD / DONE counters instead of NCCL) with two concurrent processes over shared memory:
+    same results as the broadcast path and as the oracle """
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    count = _peer_count(n, T, grid)
+    bufs = [torch.zeros(64 + count, dtype=torch.float64).share_memory_() for _ in range(2)]
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, n, T, grid, multicast, bufs, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, status, ld in res:
+        assert status == 'ok', (rank, status)
+    assert res[0][2] == res[1][2]
