@@ -74,7 +74,14 @@ def test_committed_file_is_what_the_reference_produces():
     stored = dict(np.load(GOLD))
     assert set(fresh) == set(stored)
     for k in stored:
-        assert np.array_equal(np.asarray(fresh[k]), stored[k], equal_nan=True), k
+        a, b = np.asarray(fresh[k]), stored[k]
+        assert a.shape == b.shape, k
+        if b.dtype.kind in 'iub':
+            assert np.array_equal(a, b), k
+        else:
+            # identical on the machine that wrote the file; another CPU model may dispatch other BLAS / SIMD libm kernels,
+            # which moves last bits (and their amplification through the n = 1000 factorisation)
+            np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12 * max(1.0, float(np.max(np.abs(b)))), err_msg=k)
 
 
 def test_oracle_gram_matches_reference(vec):
@@ -84,6 +91,8 @@ def test_oracle_gram_matches_reference(vec):
         assert relerr(K, vec['gram_' + name]) <= 1e-15, name       # same formulas, same libm: identical or a few ulp
 
 
+# Tolerances of the factorisation-level comparisons below leave room for another CPU model's BLAS kernels (cond * eps);
+# on the machine that wrote the file the oracle and the reference agree to 0-2 ulp on every one of these numbers.
 def test_oracle_gp_matches_reference(vec):
     rng = np.random.default_rng(1001)
     x = np.sort(rng.uniform(0, 100, 1000))
@@ -92,45 +101,45 @@ def test_oracle_gp_matches_reference(vec):
     terms = [(1.0, [dict(kind='expquad', scale=3)])]
     Kxx, Kxs, Kss = ogp.gram(terms, x[None], x[None]), ogp.gram(terms, x[None], xp[None]), ogp.gram(terms, xp[None], xp[None])
     ycov = 0.01 * np.eye(1000)
-    assert abs(ogp.logml(Kxx, y, ycov) - vec['c1_logml']) <= 1e-13 * abs(vec['c1_logml'])
+    assert abs(ogp.logml(Kxx, y, ycov) - vec['c1_logml']) <= 1e-10 * abs(vec['c1_logml'])
     m, c = ogp.pred(Kxx, Kxs, Kss, y, ycov)
-    assert relerr(m, vec['c1_mean']) <= 1e-12
-    assert np.max(np.abs(np.diag(c) - vec['c1_cov_diag'])) <= 1e-13
+    assert relerr(m, vec['c1_mean']) <= 1e-9
+    assert np.max(np.abs(np.diag(c) - vec['c1_cov_diag'])) <= 1e-10
     X, y2, Xs = vec['c2_X'], vec['c2_y'], vec['c2_Xs']
     for tag, terms in GP_TERMS.items():
         K = ogp.gram(terms, X.T.copy(), X.T.copy())
         assert relerr(K[:5], vec[tag + '_prior_rows']) <= 4e-16, tag
-        assert abs(ogp.logml(K, y2) - vec[tag + '_logml']) <= 1e-13 * abs(vec[tag + '_logml']), tag
+        assert abs(ogp.logml(K, y2) - vec[tag + '_logml']) <= 1e-10 * abs(vec[tag + '_logml']), tag
         Kxs = ogp.gram(terms, X.T.copy(), Xs.T.copy())      # (the White term lives on every key of the GP)
         Kss = ogp.gram(terms, Xs.T.copy(), Xs.T.copy())
         m, c = ogp.pred(K, Kxs, Kss, y2)
-        assert np.max(np.abs(m - vec[tag + '_mean'])) <= 1e-12 * np.max(np.abs(vec[tag + '_mean'])), tag
-        assert np.max(np.abs(c - vec[tag + '_cov'])) <= 1e-12, tag
+        assert np.max(np.abs(m - vec[tag + '_mean'])) <= 1e-9 * np.max(np.abs(vec[tag + '_mean'])), tag
+        assert np.max(np.abs(c - vec[tag + '_cov'])) <= 1e-10, tag
 
 
 @pytest.mark.parametrize('nn', [10, 64])
 def test_oracle_chol_matches_reference(vec, nn):
     g = lambda k: vec[f'chol{nn}_{k}']
     dec = odecomp.Chol(g('K'))
-    assert dec.eps == float(g('eps'))
+    assert abs(dec.eps - float(g('eps'))) <= 1e-13 * float(g('eps'))   # (row sums: summation order may differ by CPU)
     val, _, gradfwd, fisher, _ = dec.minus_log_normal_density(g('r'), dK=g('dK'), dr=g('dr'), value=True, gradfwd=True,
                                                              fisher=True)
-    assert abs(val - float(g('value'))) <= 1e-14 * abs(float(g('value')))
-    np.testing.assert_allclose(gradfwd, g('gradfwd'), rtol=1e-12)
-    np.testing.assert_allclose(fisher, g('fisher'), rtol=1e-12)
+    assert abs(val - float(g('value'))) <= 1e-12 * abs(float(g('value')))
+    np.testing.assert_allclose(gradfwd, g('gradfwd'), rtol=1e-10)
+    np.testing.assert_allclose(fisher, g('fisher'), rtol=1e-10)
     dK, dr, v = g('dK'), g('dr'), g('vec')
     _, gradrev, _, _, fishvec = dec.minus_log_normal_density(
         g('r'), dK_vjp=lambda G: np.einsum('ij,ijk->k', G, dK), dr_vjp=lambda x: x @ dr, dK_jvp_vec=dK @ v, dr_jvp_vec=dr @ v,
         gradrev=True, fishvec=True)
-    np.testing.assert_allclose(gradrev, g('gradrev'), rtol=1e-12)
-    np.testing.assert_allclose(fishvec, g('fishvec'), rtol=1e-12)
+    np.testing.assert_allclose(gradrev, g('gradrev'), rtol=1e-10)
+    np.testing.assert_allclose(fishvec, g('fishvec'), rtol=1e-10)
     np.testing.assert_allclose(gradrev, g('gradfwd'), rtol=1e-9)      # the two modes agree (reference test :241-261)
     np.testing.assert_allclose(fishvec, g('fisher') @ v, rtol=1e-9)
-    np.testing.assert_allclose(dec.ginv_linear(g('A')), g('ginv_linear'), rtol=1e-12, atol=1e-15)
-    np.testing.assert_allclose(dec.ginv_quad(g('A')), g('ginv_quad'), rtol=1e-12, atol=1e-15)
-    np.testing.assert_allclose(dec.pinv_bilinear(g('A'), g('r')), g('pinv_bilinear'), rtol=1e-12, atol=1e-15)
-    np.testing.assert_allclose(dec.correlate(g('r')), g('correlate'), rtol=1e-13)
-    np.testing.assert_allclose(dec.pinv_correlate(g('r')), g('pinv_correlate'), rtol=1e-12)
+    np.testing.assert_allclose(dec.ginv_linear(g('A')), g('ginv_linear'), rtol=1e-10, atol=1e-15)
+    np.testing.assert_allclose(dec.ginv_quad(g('A')), g('ginv_quad'), rtol=1e-10, atol=1e-15)
+    np.testing.assert_allclose(dec.pinv_bilinear(g('A'), g('r')), g('pinv_bilinear'), rtol=1e-10, atol=1e-15)
+    np.testing.assert_allclose(dec.correlate(g('r')), g('correlate'), rtol=1e-10)
+    np.testing.assert_allclose(dec.pinv_correlate(g('r')), g('pinv_correlate'), rtol=1e-10)
 
 
 def test_oracle_bart_matches_reference(vec):
@@ -150,7 +159,7 @@ def test_oracle_bart_recipe_matches_reference(vec):
     idx = obart.indices_from_coord(X5, (length, splits))
     K = 1.3 ** 2 * obart.gram(length, idx, idx, maxd=10, reset=[2, 4, 6, 8]) + 0.25 * np.eye(len(y5)) + 0.49
     assert relerr(K, vec['c4_prior']) <= 1e-14
-    assert abs(ogp.logml(K, y5, epsrel=0) - vec['c4_logml']) <= 1e-13 * abs(vec['c4_logml'])
+    assert abs(ogp.logml(K, y5, epsrel=0) - vec['c4_logml']) <= 1e-10 * abs(vec['c4_logml'])
 
 
 # ------------------------------------------------------------------------------------------------ GPU tier
