@@ -45,6 +45,16 @@ const char *lgp_build_info(void);
 /* number of CUDA kernel launches issued by the library since load (instrumentation for bench.py) */
 long long lgp_launch_count(void);
 
+/* Roofline probe: launches ONE register-resident loop kernel on `stream` (2 CTAs of 256 threads per SM, `iters`
+ * iterations of 16 independent accumulators per thread) and stores the number of floating-point operations it performs
+ * in *flops_out (HOST).  kind = LGP_PEAK_DMMA: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the FP64 tensor pipe the
+ * factorisation runs on); LGP_PEAK_DFMA: scalar DFMA.  The caller times the launch with CUDA events: bench.py measures
+ * the denominators of roofline.frac in the run that reports them.  scratch: device, >= 512 * (number of SMs) doubles. */
+#define LGP_PEAK_DMMA 0
+#define LGP_PEAK_DFMA 1
+int lgp_peak_probe(lgp_stream_t stream, int kind, int iters, double *scratch, int64_t scratch_doubles,
+                   double *flops_out /*host*/);
+
 /* ------------------------------------------------------------------------------------------------
  * Gram matrix of a sum of products of isotropic kernel factors.
  * Replaces GPElements._makecovblock_points -> CrossKernel.__call__ -> IsotropicKernel core

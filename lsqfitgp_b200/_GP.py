@@ -217,6 +217,10 @@ class _FusedNegLogMLFn(torch.autograd.Function):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 ctx.low = dec.inverse_lower()
+            # the factor buffers belong to the main stream's allocator pool but are read by the side stream: keep the
+            # allocator from handing them out again (e.g. if backward never runs) before the side stream is done
+            dec._st.W.record_stream(side)
+            dec._st.aux.record_stream(side)
             ctx.side = side
         ldq, a = dec.logdet_quad(r)
         ctx.kern, ctx.xd, ctx.labels, ctx.dec, ctx.a = kern, xd, labels, dec, a

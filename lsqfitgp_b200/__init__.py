@@ -16,3 +16,4 @@ from ._kernels import Constant, White, ExpQuad, Cauchy, Maternp, Matern, BART
 from . import _linalg
 from ._GP import GP
 from ._fit import empbayes_fit
+from ._dist import eval_batch_sharded, eval_concurrent, DistChol

@@ -20,6 +20,7 @@ The reference has no parallelism of any kind.  Two thing
 import contextlib
 import ctypes
 import math
+import threading
 
 import numpy
 import torch
@@ -36,6 +37,7 @@ def shard_indices(nitems, rank, world):
 
 
 _WORKER_STREAMS = {}
+_WORKER_LOCK = threading.Lock()
 
 
 def _worker_stream(device, slot):
@@ -43,10 +45,11 @@ def _worker_stream(device, slot):
     reusing the streams keeps the (large) factor / inverse buffers of a slot warm from one batch to the next """
     dev = torch.device(device)
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), slot)
-    st = _WORKER_STREAMS.get(key)
-    if st is None:
-        st = _WORKER_STREAMS[key] = torch.cuda.Stream(dev)
-    return st
+    with _WORKER_LOCK:  # called from the worker threads themselves
+        st = _WORKER_STREAMS.get(key)
+        if st is None:
+            st = _WORKER_STREAMS[key] = torch.cuda.Stream(dev)
+        return st
 
 
 def eval_concurrent(fun, items, in_flight, device=None):
@@ -59,7 +62,6 @@ def eval_concurrent(fun, items, in_flight, device=None):
     in_flight = max(1, min(int(in_flight), len(items)))
     if in_flight == 1:
         return [fun(it) for it in items]
-    import threading
     out = [None] * len(items)
     errors = []
     cuda = device is not None and torch.device(device).type == 'cuda'
@@ -304,7 +306,7 @@ class CudaTileOps:
         from . import _ops
         ri = torch.as_tensor(numpy.minimum(rows, lay.n - 1), device=self.device)
         ci = torch.as_tensor(numpy.minimum(cols, lay.n - 1), device=self.device)
-        ld = max(len(cols), 2)
+        ld = max(len(cols) + (len(cols) & 1), 2)
         A = self.empty(max(len(rows), 1), ld)[:len(rows), :len(cols)]  # never a null pointer, even leading dimension
         if len(rows) and len(cols):
             _ops.gram_iso(descs, x.index_select(1, ri).contiguous(), x.index_select(1, ci).contiguous(), out=A)
@@ -413,6 +415,19 @@ class CudaTileOps:
         self._ck(self.lib.lgp_tile_trsv(self._sp(), self._p(L), L.stride(0), self._p(invd), T, self._p(b),
                                         int(bool(trans))), 'lgp_tile_trsv')
 
+    def trmv_tile(self, L, x, y, trans):
+        """ y += tril(L) x (trans False) or y += tril(L)^T x for one T x T tile: the DMMA GEMM with a triangular
+        k-range on a one-column operand (what lgp_chol_mult does for the whole factor) """
+        T = L.shape[0]
+        B = self.zeros(T, 2)
+        B[:, 0] = x
+        C = self.empty(T, 2)
+        lm = self._libmod
+        flags = lm.GEMM_BETA0 | (lm.GEMM_A_UPPER_K if trans else lm.GEMM_A_LOWER_K)
+        self._ck(self.lib.lgp_dgemm(self._sp(), 0 if trans else 1, 0, T, 1, T, 1.0, self._p(L), L.stride(0), self._p(B), 2,
+                                    self._p(C), 2, flags), 'lgp_dgemm')
+        y += C[:, 0]
+
     def gemv(self, P, x, y, alpha, trans):
         """ y += alpha P x (trans False) or y += alpha P^T x """
         rows, cols = P.shape
@@ -474,6 +489,7 @@ class DistChol:
         ops = self.ops
         self._timers = timers
         self._peer_opt = peer
+        self._descs, self._x = descs, x  # kept for matvec(): K is regenerated strip-wise, never stored
 
         # ---- Gram matrix, generated in place by the owner of each tile
         self._mark('start')
@@ -803,3 +819,71 @@ class DistChol:
         """ value of Chol.minus_log_normal_density (_decomp.py:484-488): (n log 2pi + log det K + r^T K^-1 r)/2 """
         n = self.lay.n
         return 0.5 * (n * math.log(2 * math.pi) + self.logdet() + self.quad(r))
+
+    def _local_rows_index(self):
+        gr = self.lay.global_rows()
+        return torch.as_tensor(gr, device=self.s.device)
+
+    def back_correlate(self, v):
+        """ L^T v with L = diag(s) Lt (Chol.back_correlate, _decomp.py:433-435), replicated.  Every rank sweeps its
+        local tiles once (HBM-streaming GEMV per tile column + the triangular diagonal tiles it owns), one all_reduce. """
+        lay, ops, A = self.lay, self.ops, self.A
+        T, Pr, Pc, pr, pc = lay.T, lay.Pr, lay.Pc, lay.pr, lay.pc
+        u = self._vec(v) * self.s
+        uloc = u.index_select(0, self._local_rows_index()) if lay.LR else u[:0]
+        out = ops.zeros(lay.npad)
+        for lj in range(lay.LC):
+            J = pc + Pc * lj
+            li0 = lay.panel_first(J)
+            seg = out[J * T:(J + 1) * T]
+            if lay.LR > li0:
+                ops.gemv(A[li0 * T:, lj * T:(lj + 1) * T], uloc[li0 * T:], seg, 1.0, True)
+            if lay.owner(J, J) == self.rank:
+                lkr = J // Pr
+                ops.trmv_tile(A[lkr * T:(lkr + 1) * T, lj * T:(lj + 1) * T], u[J * T:(J + 1) * T], seg, True)
+        self._allreduce(out)
+        return out[:lay.n]
+
+    def correlate(self, w):
+        """ L w (Chol.correlate, _decomp.py:429-431), replicated """
+        lay, ops, A = self.lay, self.ops, self.A
+        T, Pr, Pc, pr, pc = lay.T, lay.Pr, lay.Pc, lay.pr, lay.pc
+        wv = self._vec(w)
+        acc = ops.zeros(max(lay.LR, 1) * T)
+        for lj in range(lay.LC):
+            J = pc + Pc * lj
+            li0 = lay.panel_first(J)
+            wj = wv[J * T:(J + 1) * T]
+            if lay.LR > li0:
+                ops.gemv(A[li0 * T:, lj * T:(lj + 1) * T], wj, acc[li0 * T:], 1.0, False)
+            if lay.owner(J, J) == self.rank:
+                lkr = J // Pr
+                ops.trmv_tile(A[lkr * T:(lkr + 1) * T, lj * T:(lj + 1) * T], wj, acc[lkr * T:(lkr + 1) * T], False)
+        out = ops.zeros(lay.npad)
+        if lay.LR:
+            out.index_copy_(0, self._local_rows_index(), acc[:lay.LR * T])
+        self._allreduce(out)
+        return (out * self.s)[:lay.n]
+
+    def matvec(self, v, strip_bytes=1 << 30):
+        """ (K + eps diag(s^2)) v = L (L^T v) computed WITHOUT the factor: K is regenerated strip by strip from the
+        replicated points (strips dealt round-robin to the ranks, each at most `strip_bytes`), one all_reduce.  The
+        size-independent check of SURVEY.md section 8(d): |L(L^T v) - K v| / |K v|. """
+        lay, ops = self.lay, self.ops
+        n = lay.n
+        vv = self._vec(v)[:n].contiguous()
+        out = ops.zeros(n)
+        per = int(max(128, min(n, strip_bytes // (8 * n))))
+        per -= per % 2 if per > 2 else 0
+        allrows = numpy.arange(n)
+        for si, r0 in enumerate(range(0, n, per)):
+            if si % self.world != self.rank:
+                continue
+            strip = numpy.arange(r0, min(r0 + per, n))
+            # K is symmetric: (K v)[strip] = K[:, strip]^T v, with the transposed (atomics-per-column) GEMV
+            G = ops.gram_local(self._descs, self._x, allrows, strip, lay)
+            ops.gemv(G, vv, out[r0:r0 + len(strip)], 1.0, True)
+            del G
+        self._allreduce(out)
+        eps = self._epsout[1]
+        return out + eps * self.s[:n] ** 2 * vv

@@ -67,6 +67,7 @@ SIGNATURES = {
     'lgp_abi_version': (_int, []),
     'lgp_build_info': (ctypes.c_char_p, []),
     'lgp_launch_count': (ctypes.c_longlong, []),
+    'lgp_peak_probe': (_int, [_vp, _int, _int, _vp, _i64, c_double_p]),
     'lgp_gram_iso': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int]),
     'lgp_gram_iso_vjp': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64,
                                 _vp, _int, _vp]),

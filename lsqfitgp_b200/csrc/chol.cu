@@ -295,6 +295,13 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double *__r
 // ------------------------------------------------------------------------------------------------
 // 3. small elementwise / reduction kernels
 // ------------------------------------------------------------------------------------------------
+constexpr int GRID_Y_MAX = 65535;
+// grid covering `cols` columns (256 per CTA) x `rows` rows, rows folded over (y, z) to respect the gridDim.y limit
+static inline dim3 rows_grid(int cols, int rows) {
+    return dim3((unsigned)((cols + 255) / 256), (unsigned)(rows < GRID_Y_MAX ? rows : GRID_Y_MAX),
+                (unsigned)((rows + GRID_Y_MAX - 1) / GRID_Y_MAX));
+}
+
 __global__ void row_scale_kernel(double *__restrict__ B, int64_t ldb, int n, int m, const double *__restrict__ f) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)n * m) return;
@@ -313,15 +320,15 @@ __global__ void row_scale_copy_kernel(const double *__restrict__ X, int64_t ldx,
 __global__ void get_factor_kernel(const double *__restrict__ W, int64_t ldw, const double *__restrict__ s, int n,
                                   double *__restrict__ L, int64_t ldl) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
-    if (j >= n) return;
+    int i = blockIdx.y + GRID_Y_MAX * blockIdx.z;  // gridDim.y is limited to 65535: rows continue along z
+    if (j >= n || i >= n) return;
     L[(int64_t)i * ldl + j] = (j <= i) ? W[(int64_t)i * ldw + j] * s[i] : 0.0;
 }
 
 // Kinv_ij *= sinv_i * sinv_j on the lower triangle (undo the equilibration of the inverse)
 __global__ void sym_scale_lower_kernel(double *__restrict__ A, int64_t lda, int n, const double *__restrict__ f) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = blockIdx.y + GRID_Y_MAX * blockIdx.z;
     if (j > i || i >= n) return;
     A[(int64_t)i * lda + j] = (A[(int64_t)i * lda + j] * f[j]) * f[i];
 }
@@ -386,6 +393,29 @@ static cudaError_t leaf_set_attrs() {
     cudaError_t e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(potrf_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM_BYTES);
+}
+// the > 48 KB shared-memory opt-in is a per-device attribute: once per device, not once per process
+static int leaf_attr() {
+    static DeviceOnce once;
+    const int dev = current_device();
+    if (dev < 0) return LGP_ERR_CUDA;
+    if (!once.done(dev)) {
+        if (leaf_set_attrs() != cudaSuccess) return LGP_ERR_CUDA;
+        once.set(dev);
+    }
+    return LGP_OK;
+}
+// experiment switches are read once per process
+static bool trace_enabled() {
+    static const bool v = getenv("LGP_TRACE") != nullptr;
+    return v;
+}
+static int panel_blocks() {
+    static const int v = [] {
+        const char *e = getenv("LGP_PANEL_BLOCKS");
+        return (e && atoi(e) > 0) ? atoi(e) : 4;
+    }();
+    return v;
 }
 static void leaf_launch(cudaStream_t st, double *Wblk, int64_t ld, double *invd, double *dvec, int32_t *info, int j0,
                         int version = 0) {
@@ -480,12 +510,18 @@ static void potrf_rec(CholCtx &c, int jb, int nb) {
 // The panel chain of small launches overlaps the big trailing update of the previous panel.
 // One panel stream per caller stream (up to 8; concurrent factorisations issued from different streams / host threads, e.g.
 // a batch of hyperparameter points in flight, must not serialise their panel chains behind each other).
+// The pool is per device: stream handles are only meaningful on the device they were created on, and the default
+// stream handle (0) is the same on every device.
 static cudaStream_t panel_stream(cudaStream_t caller) {
     static std::mutex mu;
-    static struct {
+    struct Slot {
         cudaStream_t caller, s;
         bool used;
-    } pool[8];
+    };
+    static Slot pools[MAX_DEVICES][8];
+    const int dev = current_device();
+    if (dev < 0) return nullptr;
+    Slot *pool = pools[dev];
     std::lock_guard<std::mutex> lock(mu);
     int free_slot = -1;
     for (int i = 0; i < 8; i++) {
@@ -503,47 +539,53 @@ static cudaStream_t panel_stream(cudaStream_t caller) {
     return s;
 }
 
+// cross-stream ordering helpers: a failed record / wait would silently drop an ordering constraint, so every return
+// code is checked and turned into LGP_ERR_CUDA
+static inline bool ev_record(cudaEvent_t e, cudaStream_t s) { return e && cudaEventRecord(e, s) == cudaSuccess; }
+static inline bool ev_wait(cudaStream_t s, cudaEvent_t e) { return e && cudaStreamWaitEvent(s, e, 0) == cudaSuccess; }
+
 static int potrf_lookahead(CholCtx &cm, int nblk, int pb) {
-    cudaStream_t ps = panel_stream(cm.st);
-    if (!ps || nblk <= pb) {
+    cudaStream_t ps = (nblk > pb) ? panel_stream(cm.st) : nullptr;
+    if (!ps) {
         potrf_rec(cm, 0, nblk);
         return cm.rc;
     }
-    const bool trace = getenv("LGP_TRACE") != nullptr;  // debug only: synchronises and prints a per-panel timeline
+    const bool trace = trace_enabled();  // debug only: synchronises and prints a per-panel timeline
     CholCtx cp = cm;
     cp.st = ps;
     const int np = (nblk + pb - 1) / pb;
-    const int nev = 2 * np + 1;
-    cudaEvent_t *ev = new cudaEvent_t[nev];
-    for (int i = 0; i < nev; i++) cudaEventCreateWithFlags(&ev[i], trace ? cudaEventDefault : cudaEventDisableTiming);
-    cudaEvent_t *e_panel = ev, *e_col = ev + np, e_fork = ev[2 * np];
-    cudaEvent_t *t_pstart = nullptr, *t_restend = nullptr;
+    cudaEvent_t e_fork = nullptr, e_last = nullptr;
+    cudaEvent_t *t_pstart = nullptr, *t_restend = nullptr, *t_panel = nullptr, *t_col = nullptr;
     if (trace) {
-        t_pstart = new cudaEvent_t[np];
-        t_restend = new cudaEvent_t[np];
-        for (int i = 0; i < np; i++) {
-            cudaEventCreate(&t_pstart[i]);
-            cudaEventCreate(&t_restend[i]);
-        }
+        t_pstart = new cudaEvent_t[4 * np + 1];
+        t_restend = t_pstart + np;
+        t_panel = t_restend + np;
+        t_col = t_panel + np;
+        for (int i = 0; i < 4 * np + 1; i++) cudaEventCreate(&t_pstart[i]);
+        e_fork = t_pstart[4 * np];
+    } else {
+        e_fork = ring_event();
     }
-    cudaEventRecord(e_fork, cm.st);
-    cudaStreamWaitEvent(ps, e_fork, 0);
+    bool ok = ev_record(e_fork, cm.st) && ev_wait(ps, e_fork);
     int rc = LGP_OK;
-    int last = 0;
-    for (int j = 0; j < np && rc == LGP_OK; j++) {
+    int last = -1;
+    cudaEvent_t e_colnext = nullptr;  // recorded on the main stream when the next panel's block column is updated
+    for (int j = 0; j < np && rc == LGP_OK && ok; j++) {
         const int jb = j * pb;
         const int w = (nblk - jb < pb) ? nblk - jb : pb;
         const int rest = nblk - jb - w;
         // ---- panel stream
-        if (j > 0) cudaStreamWaitEvent(ps, e_col[j], 0);
+        if (j > 0) ok = ok && ev_wait(ps, e_colnext);
         if (trace) cudaEventRecord(t_pstart[j], ps);
         potrf_rec(cp, jb, w);
         if (rest > 0) trsm_right_rec(cp, jb + w, rest * NB, jb, w);
-        cudaEventRecord(e_panel[j], ps);
+        cudaEvent_t e_panel = trace ? t_panel[j] : ring_event();
+        ok = ok && ev_record(e_panel, ps);
+        e_last = e_panel;
         last = j;
-        if ((rc = cp.rc) != LGP_OK || rest == 0) break;
+        if ((rc = cp.rc) != LGP_OK || rest == 0 || !ok) break;
         // ---- main stream
-        cudaStreamWaitEvent(cm.st, e_panel[j], 0);
+        ok = ok && ev_wait(cm.st, e_panel);
         const int w2 = rest < pb ? rest : pb;
         const int rest2 = rest - w2;
         const int K = w * NB;
@@ -551,37 +593,38 @@ static int potrf_lookahead(CholCtx &cm, int nblk, int pb) {
         // diagonal is scratch (never read: leaves and LOWER kernels only touch r >= c)
         rc = gemm_launch(cm.st, true, true, rest * NB, w2 * NB, K, -1.0, Wp(cm, jb + w, jb), cm.ldw, Wp(cm, jb + w, jb),
                          cm.ldw, Wp(cm, jb + w, jb + w), cm.ldw, 0);
-        cudaEventRecord(e_col[j + 1], cm.st);
+        e_colnext = trace ? t_col[j] : ring_event();
+        ok = ok && ev_record(e_colnext, cm.st);
         // rest of the trailing matrix
         if (rc == LGP_OK && rest2 > 0)
             rc = gemm_launch(cm.st, true, true, rest2 * NB, rest2 * NB, K, -1.0, Wp(cm, jb + w + w2, jb), cm.ldw,
                              Wp(cm, jb + w + w2, jb), cm.ldw, Wp(cm, jb + w + w2, jb + w + w2), cm.ldw, GEMM_LOWER);
         if (trace) cudaEventRecord(t_restend[j], cm.st);
     }
-    cudaStreamWaitEvent(cm.st, e_panel[last], 0);  // join
+    if (e_last) ok = ev_wait(cm.st, e_last) && ok;  // join
+    if (!ok) {
+        // an ordering constraint could not be enqueued: drain both streams so that nothing runs out of order, and fail
+        cudaStreamSynchronize(ps);
+        cudaStreamSynchronize(cm.st);
+        if (rc == LGP_OK) rc = LGP_ERR_CUDA;
+    }
     if (trace) {
         cudaStreamSynchronize(cm.st);
         cudaStreamSynchronize(ps);
         for (int j = 0; j <= last; j++) {
             float a = 0, b = 0, c2 = 0, d = 0;
             cudaEventElapsedTime(&a, e_fork, t_pstart[j]);
-            cudaEventElapsedTime(&b, e_fork, e_panel[j]);
+            cudaEventElapsedTime(&b, e_fork, t_panel[j]);
             if (j < last) {
-                cudaEventElapsedTime(&c2, e_fork, e_col[j + 1]);
+                cudaEventElapsedTime(&c2, e_fork, t_col[j]);
                 cudaEventElapsedTime(&d, e_fork, t_restend[j]);
             }
             fprintf(stderr, "[lgp trace] panel %3d: start %8.3f done %8.3f (%.3f ms) | colupd done %8.3f rest done %8.3f\n", j,
                     a, b, b - a, c2, d);
         }
-        for (int i = 0; i < np; i++) {
-            cudaEventDestroy(t_pstart[i]);
-            cudaEventDestroy(t_restend[i]);
-        }
+        for (int i = 0; i < 4 * np + 1; i++) cudaEventDestroy(t_pstart[i]);
         delete[] t_pstart;
-        delete[] t_restend;
     }
-    for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
-    delete[] ev;
     if (rc == LGP_OK && cudaGetLastError() != cudaSuccess) rc = LGP_ERR_CUDA;
     return rc;
 }
@@ -842,14 +885,16 @@ struct InvCtx {
 constexpr int TRTRI_FORK_DEPTH = 4;
 static cudaStream_t trtri_side_stream(int idx) {
     static std::mutex mu;
-    static cudaStream_t pool[1 << TRTRI_FORK_DEPTH];
-    static bool init[1 << TRTRI_FORK_DEPTH];
+    static cudaStream_t pools[MAX_DEVICES][1 << TRTRI_FORK_DEPTH];
+    static bool inits[MAX_DEVICES][1 << TRTRI_FORK_DEPTH];
+    const int dev = current_device();
+    if (dev < 0) return nullptr;
     std::lock_guard<std::mutex> lock(mu);
-    if (!init[idx]) {
-        if (cudaStreamCreateWithFlags(&pool[idx], cudaStreamNonBlocking) != cudaSuccess) pool[idx] = nullptr;
-        init[idx] = true;
+    if (!inits[dev][idx]) {
+        if (cudaStreamCreateWithFlags(&pools[dev][idx], cudaStreamNonBlocking) != cudaSuccess) pools[dev][idx] = nullptr;
+        inits[dev][idx] = true;
     }
-    return pool[idx];
+    return pools[dev][idx];
 }
 
 static void trtri_rec(InvCtx &c, int jb, int nb, int depth = 0, int path = 1) {
@@ -865,19 +910,20 @@ static void trtri_rec(InvCtx &c, int jb, int nb, int depth = 0, int path = 1) {
     int n1 = nb / 2, n2 = nb - n1;
     cudaStream_t side = (depth < TRTRI_FORK_DEPTH && nb >= 4) ? trtri_side_stream(path) : nullptr;
     if (side) {
-        cudaEvent_t fork, join;
-        cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
-        cudaEventRecord(fork, c.st);
-        cudaStreamWaitEvent(side, fork, 0);
+        // fork: if the ordering cannot be enqueued, the right half simply stays on this stream
+        cudaEvent_t fork = ring_event();
+        if (!(ev_record(fork, c.st) && ev_wait(side, fork))) side = nullptr;
+    }
+    if (side) {
         InvCtx cs = c;
         cs.st = side;
         trtri_rec(c, jb, n1, depth + 1, 2 * path);
         trtri_rec(cs, jb + n1, n2, depth + 1, 2 * path + 1);
-        cudaEventRecord(join, side);
-        cudaStreamWaitEvent(c.st, join, 0);
-        cudaEventDestroy(fork);
-        cudaEventDestroy(join);
+        cudaEvent_t join = ring_event();
+        if (!(ev_record(join, side) && ev_wait(c.st, join))) {
+            cudaStreamSynchronize(side);  // never let the combining products overtake the side stream
+            c.rc = LGP_ERR_CUDA;
+        }
         if (cs.rc) c.rc = cs.rc;
     } else {
         trtri_rec(c, jb, n1, depth + 1, 2 * path);
@@ -918,11 +964,7 @@ int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const dou
     if ((ldw & 1) || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(aux) & 15))
         return LGP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr = false;
-    if (!attr) {
-        if (leaf_set_attrs() != cudaSuccess) return LGP_ERR_CUDA;
-        attr = true;
-    }
+    if (leaf_attr()) return LGP_ERR_CUDA;
     if (epsrel < 0) epsrel = (double)n * 2.220446049250313e-16;
     chol_diag_scale_kernel<<<(npad + 255) / 256, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, aux);
     LGP_CUDA_CHECK_LAUNCH();
@@ -932,10 +974,7 @@ int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const dou
     LGP_CUDA_CHECK_LAUNCH();
     CholCtx c{st, W, ldw, aux + LGP_AUX_INVDIAG(npad), aux + LGP_AUX_DIAG(npad), info, LGP_OK};
     {
-        int pb = 4;
-        const char *e = getenv("LGP_PANEL_BLOCKS");
-        if (e && atoi(e) > 0) pb = atoi(e);
-        int rc = potrf_lookahead(c, npad / NB, pb);
+        int rc = potrf_lookahead(c, npad / NB, panel_blocks());
         if (rc) return rc;
     }
     finalize_info_kernel<<<1, 1, 0, st>>>(info, n);
@@ -949,7 +988,7 @@ int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const dou
 // debug/benchmark hook (not in the public header): run the 128x128 leaf `reps` times back to back
 int lgp_debug_leaf(lgp_stream_t stream, double *Wblk, int64_t ld, double *invd, double *dvec, int32_t *info, int reps,
                    int variant) {
-    if (leaf_set_attrs() != cudaSuccess) return LGP_ERR_CUDA;
+    if (leaf_attr()) return LGP_ERR_CUDA;
     for (int i = 0; i < reps; i++) leaf_launch((cudaStream_t)stream, Wblk, ld, invd, dvec, info, 0, variant);
     LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
@@ -1012,7 +1051,7 @@ int lgp_chol_get_factor(lgp_stream_t stream, const double *W, int64_t ldw, const
                         double *Lout, int64_t ldl) {
     if (n64 < 1 || !W || !aux || !Lout) return LGP_ERR_BADARG;
     const int n = (int)n64, npad = (int)lgp_chol_npad(n);
-    dim3 g((n + 255) / 256, n);
+    dim3 g = rows_grid(n, n);
     get_factor_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(W, ldw, aux + LGP_AUX_S(npad), n, Lout, ldl);
     LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
@@ -1027,7 +1066,7 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
         return LGP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     InvCtx c{st, W, ldw, aux + LGP_AUX_INVDIAG(npad), scratch, (int64_t)npad, LGP_OK};
-    const bool trace = getenv("LGP_TRACE") != nullptr;
+    const bool trace = trace_enabled();
     cudaEvent_t t0, t1, t2;
     if (trace) {
         cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
@@ -1040,7 +1079,7 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
     int rc = gemm_launch(st, false, false, npad, npad, npad, 1.0, scratch, npad, scratch, npad, Kinv, ldk,
                          GEMM_BETA0 | GEMM_LOWER | GEMM_A_UPPER_K);
     if (rc) return rc;
-    dim3 g((n + 255) / 256, n);
+    dim3 g = rows_grid(n, n);
     sym_scale_lower_kernel<<<g, 256, 0, st>>>(Kinv, ldk, n, aux + LGP_AUX_SINV(npad));
     LGP_CUDA_CHECK_LAUNCH();
     if (trace) {
@@ -1056,15 +1095,6 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
 }
 
 // ---- tile-level entry points: building blocks of the block-cyclic multi-GPU factorisation (lsqfitgp_b200/_dist.py)
-static int leaf_attr() {
-    static bool attr = false;
-    if (!attr) {
-        if (leaf_set_attrs() != cudaSuccess) return LGP_ERR_CUDA;
-        attr = true;
-    }
-    return LGP_OK;
-}
-
 int lgp_tile_potrf(lgp_stream_t stream, double *A, int64_t lda, int64_t t, double *invd, double *dvec, int32_t *info,
                    int64_t j0) {
     if (t < NB || t % NB || t > (1 << 20) || !A || !invd || !dvec || !info || j0 < 0) return LGP_ERR_BADARG;

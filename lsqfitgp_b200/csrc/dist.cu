@@ -270,13 +270,21 @@ int lgp_dist_trailing_update(lgp_stream_t stream, const lgp_grid_t *grid, double
 
 int lgp_dgemv(lgp_stream_t stream, int trans, const double *P, int64_t ldp, int64_t rows, int64_t cols,
               const double *x, double *y, double alpha) {
-    if (rows < 0 || cols < 0 || cols > (1 << 20) || !P || !x || !y) return LGP_ERR_BADARG;
+    if (rows < 0 || cols < 0 || cols > (1 << 30) || !P || !x || !y) return LGP_ERR_BADARG;
     if (rows == 0 || cols == 0) return LGP_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (!trans) {
-        if (cols * 8 > 48 * 1024) return LGP_ERR_UNSUPPORTED;
-        gemv_n_kernel<<<(unsigned)((rows + 7) / 8), 256, (size_t)cols * 8, st>>>(P, ldp, rows, (int)cols, x, y, alpha);
+        // x is staged in shared memory: wide matrices go in column chunks (y accumulates)
+        constexpr int64_t CH = 4096;
+        for (int64_t c0 = 0; c0 < cols; c0 += CH) {
+            const int64_t cc = cols - c0 < CH ? cols - c0 : CH;
+            gemv_n_kernel<<<(unsigned)((rows + 7) / 8), 256, (size_t)cc * 8, st>>>(P + c0, ldp, rows, (int)cc, x + c0, y,
+                                                                                  alpha);
+            LGP_CUDA_CHECK_LAUNCH();
+        }
+        return LGP_OK;
     } else {
+        if (cols > (1 << 20)) return LGP_ERR_UNSUPPORTED;
         dim3 grid((unsigned)((cols + 255) / 256), (unsigned)((rows + 127) / 128));
         if (grid.y > 65535) return LGP_ERR_UNSUPPORTED;
         gemv_t_kernel<<<grid, 256, 0, st>>>(P, ldp, rows, (int)cols, x, y, alpha);

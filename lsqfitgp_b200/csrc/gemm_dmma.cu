@@ -12,12 +12,13 @@ static int launch_cfg(cudaStream_t stream, GemmParams &p) {
     int64_t grid = (p.flags & GEMM_LOWER) ? (int64_t)(Cfg::BM >= Cfg::BN ? Cfg::BM / Cfg::BN : 1) * p.tiles_m * (p.tiles_m + 1) / 2
                                           : (int64_t)p.tiles_m * p.tiles_n;
     if (grid > 2147483647LL) return LGP_ERR_UNSUPPORTED;
-    static bool attr_set = false;  // one flag per template instantiation
-    if (!attr_set) {
+    static DeviceOnce attr_set;  // one flag per template instantiation and device
+    const int dev = current_device();
+    if (!attr_set.done(dev)) {
         if (cudaFuncSetAttribute(gemm_dmma_kernel<Cfg, AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES) != cudaSuccess)
             return LGP_ERR_CUDA;
-        attr_set = true;
+        attr_set.set(dev);
     }
     gemm_dmma_kernel<Cfg, AK, BK_><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
     LGP_CUDA_CHECK_LAUNCH();

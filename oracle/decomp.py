@@ -23,6 +23,31 @@ def diag_scale_pow2(K):
         return np.where(d, np.exp2(np.rint(0.5 * np.log2(d))), 1)
 
 
+def chol_inplace(K, *, epsrel='auto', epsabs=0):
+    """ Chol.__init__ (:380-393) on ONE buffer: K (C-contiguous, exactly symmetric) is equilibrated, jittered and
+    factored in place; returns (L, Chol.eps) with L = diag(s) Lt a Fortran-ordered view of the same memory.  Same
+    arithmetic as the `Chol` class below (division by powers of two is exact whatever the order; dpotrf on the
+    transposed view of a symmetric matrix is the same call), without its four n x n temporaries. """
+    n = len(K)
+    assert K.flags.c_contiguous and K.shape == (n, n)
+    s = diag_scale_pow2(K)
+    K /= s
+    K /= s[:, None]
+    machine_eps = np.finfo(float).eps
+    if isinstance(epsrel, str) and epsrel == 'auto':
+        epsrel = n * machine_eps
+    if isinstance(epsabs, str) and epsabs == 'auto':
+        epsabs = machine_eps
+    maxeigv = max(np.max(np.sum(np.abs(K[i:i + 1024]), axis=1)) for i in range(0, n, 1024))
+    eps = epsrel * maxeigv + epsabs
+    K[np.diag_indices_from(K)] += eps
+    L = linalg.cholesky(K.T, lower=True, overwrite_a=True, check_finite=False)  # K.T: Fortran-ordered view, no copy
+    if not np.all(np.isfinite(np.diagonal(L))):
+        raise np.linalg.LinAlgError('cholesky decomposition not finite, probably matrix not pos def numerically')
+    L *= s[:, None]
+    return L, eps * np.min(s * s)
+
+
 class Chol:
 
     def __init__(self, K, *, epsrel='auto', epsabs=0):

@@ -97,19 +97,32 @@ def pred(Kxx, Kxxs, Kxsxs, y, ycov=None, **kw):
     return mean, cov
 
 
-def logml_and_grad(terms, x, y, params, **kw):
+def logml_and_grad(terms, x, y, params, timers=None, **kw):
     """ -logML value and gradient w.r.t. a list of hyperparameters, in the reference's formulation
     (L^-1 I, invL' invL, two contractions; _decomp.py:466-472,505-509).
     params: list of ('amp', term_index) | ('logscale', term_index, factor_index): derivative w.r.t. the
-    amplitude of a term / the log of the scale of a factor. """
+    amplitude of a term / the log of the scale of a factor.
+    timers: optional dict, filled with the wall-clock seconds of each phase (bench.py's CPU baseline extrapolates every
+    phase with its own exponent): 'gram' O(n^2), 'chol' O(n^3), 'solve' O(n^2), 'inverse' O(n^3), 'dgram' O(n^2). """
+    import time
     from scipy import linalg
+
+    def lap(name, t0):
+        if timers is not None:
+            timers[name] = timers.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+    t = time.perf_counter()
     K = gram_chunked(terms, x, x)
+    t = lap('gram', t)
     dec = Chol(K, **kw)
     L = dec._L
+    t = lap('chol', t)
     invLr = linalg.solve_triangular(L, y, lower=True)
     invKr = linalg.solve_triangular(L.T, invLr, lower=False)
+    t = lap('solve', t)
     invL = linalg.solve_triangular(L, np.eye(len(L)), lower=True)
     invK = invL.T @ invL
+    t = lap('inverse', t)
     value = 1 / 2 * (len(L) * np.log(2 * np.pi) + 2 * np.sum(np.log(np.diag(L))) + invLr @ invLr)
     grads = []
     for par in params:
@@ -128,4 +141,29 @@ def logml_and_grad(terms, x, y, params, **kw):
         tr_invK_dK = np.sum(invK * dK)
         r_invK_dK_invK_r = invKr @ dK @ invKr
         grads.append(1 / 2 * (tr_invK_dK - r_invK_dK_invK_r))
+    lap('dgram', t)
     return value, np.array(grads)
+
+
+def logml_value_lean(terms, x, y, timers=None, chunk=1024, **kw):
+    """ -logML value only, with one n x n buffer (Gram written chunk-wise, equilibrated / jittered / factored in place by
+    decomp.chol_inplace): the same numbers as `logml`, for sizes where the temporaries of the plain restatement would
+    not fit the host (n = 20000 ... 30000 in bench.py). """
+    import time
+    from scipy import linalg
+    from .decomp import chol_inplace
+    t0 = time.perf_counter()
+    n = x.shape[1]
+    K = np.empty((n, n))
+    for s in range(0, n, chunk):
+        K[s:s + chunk] = gram(terms, x[:, s:s + chunk], x)
+    t1 = time.perf_counter()
+    L, eps = chol_inplace(K, **kw)
+    del K
+    t2 = time.perf_counter()
+    invLr = linalg.solve_triangular(L, y, lower=True, check_finite=False)
+    value = 1 / 2 * (n * np.log(2 * np.pi) + 2 * np.sum(np.log(np.diagonal(L))) + invLr @ invLr)
+    t3 = time.perf_counter()
+    if timers is not None:
+        timers.update(gram=t1 - t0, chol=t2 - t1, solve=t3 - t2)
+    return value, L, eps

@@ -138,6 +138,10 @@ class NumpyTileOps:
         bn = b.numpy()
         bn[...] = scipy.linalg.solve_triangular(np.tril(L.numpy()), bn, lower=True, trans=1 if trans else 0, check_finite=False)
 
+    def trmv_tile(self, L, x, y, trans):
+        l = np.tril(L.numpy())
+        y.numpy()[...] += (l.T if trans else l) @ x.numpy()
+
     def gemv(self, P, x, y, alpha, trans):
         if P.shape[0] == 0 or P.shape[1] == 0:
             return

@@ -80,6 +80,15 @@ def _check_against_oracle(dc, K, b):
     assert abs(dc.minus_log_normal_density(b) - v) <= 1e-10 * abs(v)
     np.testing.assert_allclose(dc.pinv_correlate(b).numpy(), ref.pinv_correlate(b), rtol=1e-8,
                                atol=1e-10 * np.abs(b).max())
+    # products with the factor, and the size-independent check of SURVEY 8(d): L (L^T v) = (K + eps S^2) v
+    lc, lbc = ref.correlate(b), ref.back_correlate(b)
+    np.testing.assert_allclose(dc.correlate(b).numpy(), lc, rtol=1e-10, atol=1e-12 * np.abs(lc).max())
+    np.testing.assert_allclose(dc.back_correlate(b).numpy(), lbc, rtol=1e-10, atol=1e-12 * np.abs(lbc).max())
+    kv = dc.matvec(b).numpy()
+    llv = dc.correlate(dc.back_correlate(b)).numpy()
+    assert np.linalg.norm(llv - kv) <= 1e-12 * np.linalg.norm(kv)
+    s = np.asarray(dc.s[:n])
+    np.testing.assert_allclose(kv, K @ b + float(dc._epsout[1]) * s ** 2 * b, rtol=1e-12, atol=1e-13 * np.abs(kv).max())
 
 
 @pytest.mark.parametrize('n,T', [(300, 128), (700, 256), (128, 128), (1, 128)])
