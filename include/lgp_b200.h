@@ -137,6 +137,41 @@ int lgp_gram_bart(lgp_stream_t stream, int p, const int32_t *nsplits /*host*/, c
                   const double *psi /*device: psi[k] = digamma(k), k <= max(nsplits)+1; needed for width 3*/,
                   const int32_t *ix, int64_t ldx, int64_t n, const int32_t *iy, int64_t ldy, int64_t m,
                   double *K_out, int64_t ldk, int flags);
+
+/* General form: a chain of `nstages` bracket stages (the brackets of BART.correlation that do not fold into one
+ * `repeat` sequence, _bart.py:447-455: the per-pair result of one stage is the gamma of the next), optional derivative
+ * outputs, optional symmetric evaluation.
+ *   stage_width[s] in 1..3, stage_nrows[s] >= 1 (HOST); rows: sum(stage_nrows) rows of THREE doubles each (entries beyond
+ *   the stage's width ignored), in evaluation order (deepest bracket first); at most LGP_BART_MAX_ROWS rows in total.
+ *   drows (HOST, may be NULL when no derivative is requested): 2 x (total rows) x 3: d rows / d alpha, then d rows / d beta
+ *   (for pnt_d = alpha / (1 + d)^beta: pnt_d / alpha and -pnt_d log(1 + d); 0 for entries fixed to 1).
+ *   K_out = amp * corr (may be NULL if only derivatives are wanted); dKa_out = amp * d corr / d alpha, dKb_out likewise
+ *   for beta (each may be NULL; ld = ldd): what jax.jacfwd of the BART kernel gives `bayestree.bart`
+ *   (src/lsqfitgp/bayestree/_bart.py:175-227 with forward=True, _fit.py:679-685).
+ *   flags: LGP_BART_SYMMETRIC asserts ix == iy (same pointer) and n == m: only tiles on or below the diagonal are
+ *   evaluated and mirrored. */
+#define LGP_BART_MAX_ROWS 16
+#define LGP_BART_MAX_STAGES 8
+#define LGP_BART_SYMMETRIC 1
+int lgp_gram_bart_stages(lgp_stream_t stream, int p, const int32_t *nsplits /*host*/, const double *w /*host*/,
+                         int nstages, const int32_t *stage_width /*host*/, const int32_t *stage_nrows /*host*/,
+                         const double *rows /*host*/, const double *drows /*host*/, double gamma, double amp,
+                         const double *psi /*device*/, const int32_t *ix, int64_t ldx, int64_t n, const int32_t *iy,
+                         int64_t ldy, int64_t m, double *K_out, int64_t ldk, double *dKa_out, double *dKb_out,
+                         int64_t ldd, int flags);
+
+/* Reverse-mode contraction of the BART Gram build without materialising the derivatives (what jax.vjp of the kernel
+ * gives empbayes_fit in reverse mode, src/lsqfitgp/_fit.py:687-702 with _linalg/_decomp.py:505-509):
+ *   out[0] = sum_ij G_ij corr_ij            (= d/d amp)
+ *   out[1] = sum_ij G_ij amp d corr_ij / d alpha,   out[2] likewise for beta
+ * symlower = 0: G dense n x m.  symlower = 1: ix == iy and G_ij = w_ij (G[i][j] - b_i b_j) read from the LOWER triangle
+ * only, w = 2 off the diagonal (b may be NULL), as in lgp_gram_iso_vjp.  out: device, 3 doubles (zeroed by the call;
+ * accumulated with atomicAdd). */
+int lgp_gram_bart_vjp(lgp_stream_t stream, int p, const int32_t *nsplits /*host*/, const double *w /*host*/, int nstages,
+                      const int32_t *stage_width /*host*/, const int32_t *stage_nrows /*host*/,
+                      const double *rows /*host*/, const double *drows /*host*/, double gamma, double amp,
+                      const double *psi /*device*/, const int32_t *ix, int64_t ldx, int64_t n, const int32_t *iy,
+                      int64_t ldy, int64_t m, const double *G, int64_t ldg, const double *b, int symlower, double *out);
 /* fills HOST buffer psi_out[k] = digamma(k), k = 1..len-1 (psi_out[0] = -inf): jspecial.digamma of integers
  * (_bart.py:735-743) by an extended-precision recurrence */
 int lgp_bart_digamma_table(double *psi_out, int64_t len);

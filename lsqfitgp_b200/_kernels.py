@@ -123,8 +123,11 @@ class _BartSpec:
                 raise NotImplementedError(f'gradient w.r.t. BART {name}')
         return out
 
-    def rows(self):
-        """ bracket folding of BART.correlation (reference _bart.py:372-447) -> (rows (R, W), gamma) """
+    def stages(self):
+        """ bracket folding of BART.correlation (reference _bart.py:372-447) -> (stage_width, stage_nrows, rows, drows,
+        gamma): the stages in evaluation order (deepest bracket first), each `nrows` rows of `width` probabilities stored
+        3 per row; drows[0] / drows[1] = derivative of every entry w.r.t. alpha / beta (pnt_d = alpha / (1 + d)^beta:
+        pnt_d / alpha and -pnt_d log(1 + d); 0 for the entries the folding fixes to 1), None for a user-given `pnt`. """
         if self.pnt is None:
             assert self.maxd == int(self.maxd) and self.maxd >= 0, self.maxd
             alpha, beta = _f(self.alpha), _f(self.beta)
@@ -132,17 +135,22 @@ class _BartSpec:
             assert beta >= 0, 'beta must be in [0, inf)'
             d = numpy.arange(int(self.maxd) + 1)
             pnt = alpha / (1 + d) ** beta
+            dpa = 1 / (1 + d) ** beta
+            dpb = -pnt * numpy.log1p(d)
         else:
             pnt = numpy.asarray(self.pnt, dtype=float)
+            dpa = dpb = None
         assert numpy.all((0 <= pnt) & (pnt <= 1)), 'pnt must be in [0, 1]'
         gamma = self.gamma
         if isinstance(gamma, str):
             raise NotImplementedError("gamma='auto'")
         gamma = _f(gamma)
         assert 0 <= gamma <= 1, 'gamma must be in [0, 1]'
+        depth = numpy.arange(len(pnt))  # which pnt_d an entry is; -1: fixed to 1
         if not self.intercept:
             pnt = pnt.copy()
             pnt[0] = 1
+            depth[0] = -1
         reset = self.reset
         if reset is None:
             reset = []
@@ -159,25 +167,38 @@ class _BartSpec:
                 brackets[-1] = lt, b, lr + 1
             else:
                 brackets.append((t, b, 1))
-        stages = []
+        widths, nrows, rows, idxs = [], [], [], []
         for t, b, repeat in reversed(brackets):
-            probs = pnt[t:b + 1].copy()
+            idx = depth[t:b + 1].copy()
             if t > 0:
-                probs[0] = 1
+                idx[0] = -1
             if repeat > 1:
-                head = probs[0:1]
-                one = numpy.ones_like(head)
-                pieces = [[head if i == 0 else one, p] for i, p in enumerate(numpy.split(probs[1:], repeat))]
-                probs = numpy.concatenate(sum(reversed(pieces), start=[]))
+                head = idx[0:1]
+                one = numpy.full_like(head, -1)
+                pieces = [[head if i == 0 else one, p] for i, p in enumerate(numpy.split(idx[1:], repeat))]
+                idx = numpy.concatenate(sum(reversed(pieces), start=[]))
             else:
                 repeat = 1
-            width = len(probs) // repeat
+            width = len(idx) // repeat
             if width > 3:
                 raise NotImplementedError(
                     f'BART bracket of depth {width - 1} > 2: the exponential-cost generic recursion '
                     '(reference _bart.py:759-806) is not implemented on the device; use reset= to keep brackets <= 2')
-            stages.append(probs.reshape(repeat, width))
-        return stages, gamma
+            widths.append(width)
+            nrows.append(repeat)
+            idx3 = numpy.full((repeat, 3), -1)
+            idx3[:, :width] = idx.reshape(repeat, width)
+            idxs.append(idx3)
+        idx = numpy.concatenate(idxs, axis=0)
+        if len(idx) > _lib.BART_MAX_ROWS or len(widths) > _lib.BART_MAX_STAGES:
+            raise NotImplementedError(f'BART: more than {_lib.BART_MAX_ROWS} rows / {_lib.BART_MAX_STAGES} stages')
+        fixed = idx < 0
+        safe = numpy.where(fixed, 0, idx)
+        rows = numpy.where(fixed, 1.0, pnt[safe])
+        drows = None
+        if dpa is not None:
+            drows = numpy.stack([numpy.where(fixed, 0.0, dpa[safe]), numpy.where(fixed, 0.0, dpb[safe])])
+        return numpy.array(widths, numpy.int32), numpy.array(nrows, numpy.int32), rows, drows, gamma
 
     def gram_device(self, xd, yd, labels, out=None):
         length, splits = self.splits

@@ -23,6 +23,7 @@ ERRORS = {-1: 'bad argument', -2: 'misaligned pointer or odd leading dimension',
 K_EXPQUAD, K_MATERNP, K_CAUCHY, K_WHITE, K_CONSTANT, K_MATERN = range(6)
 GRAM_SYMMETRIC, GRAM_GENERAL, GRAM_LIBM = 1, 2, 4  # LGP_GRAM_* flags of lgp_gram_iso
 MAX_FACTORS = 8
+BART_MAX_ROWS, BART_MAX_STAGES, BART_SYMMETRIC = 16, 8, 1
 MAX_DIMS = 32
 
 GEMM_LOWER, GEMM_BETA0, GEMM_A_LOWER_K, GEMM_B_LOWER_K, GEMM_A_UPPER_K, GEMM_B_UPPER_K = 1, 2, 4, 8, 16, 32
@@ -76,6 +77,10 @@ SIGNATURES = {
     'lgp_frob_dot': (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     'lgp_gram_bart': (_int, [_vp, _int, c_int32_p, c_double_p, c_double_p, _int, _int, _dbl, _dbl, _vp,
                              _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int]),
+    'lgp_gram_bart_stages': (_int, [_vp, _int, c_int32_p, c_double_p, _int, c_int32_p, c_int32_p, c_double_p, c_double_p,
+                                    _dbl, _dbl, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _int]),
+    'lgp_gram_bart_vjp': (_int, [_vp, _int, c_int32_p, c_double_p, _int, c_int32_p, c_int32_p, c_double_p, c_double_p,
+                                 _dbl, _dbl, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _int, _vp]),
     'lgp_bart_digamma_table': (_int, [c_double_p, _i64]),
     'lgp_dgemm': (_int, [_vp, _int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _vp, _i64, _int]),
     'lgp_axpby': (_int, [_vp, _i64, _i64, _dbl, _vp, _i64, _dbl, _vp, _i64, _dbl]),
