@@ -196,6 +196,33 @@ int lgp_dgemm(lgp_stream_t stream, int a_kmajor, int b_kmajor, int64_t M, int64_
 int lgp_axpby(lgp_stream_t stream, int64_t n, int64_t m, double alpha, const double *X, int64_t ldx, double beta,
               double *Y, int64_t ldy, double gamma);
 
+/* Y += c over an n x m block: blocks of scalar covariances broadcast through addtransf (the `k^2 11^T` term of
+ * bayestree.bart, src/lsqfitgp/bayestree/_bart.py:199-204, _GP/_elements.py:581-601). */
+int lgp_add_scalar(lgp_stream_t stream, int64_t n, int64_t m, double *Y, int64_t ldy, double c);
+
+/* out (n x n, ldo) = scale * (sym(low) - b b^T) as a FULL symmetric matrix, `low` given by its LOWER triangle (ldl; the
+ * upper triangle is not read), b optional n-vector: dvalue/dK = 1/2 (K^-1 - K^-1 r r^T K^-1) of the normal density for
+ * consumers that need the full matrix (generic dK_vjp callbacks, reverse mode through assembled blocks),
+ * src/lsqfitgp/_linalg/_decomp.py:505-509.  One pass: reads n^2/2, writes n^2. */
+int lgp_sym_expand_sub(lgp_stream_t stream, const double *low, int64_t ldl, const double *b, int64_t n, double scale,
+                       double *out, int64_t ldo);
+
+/* out[0] = sum_ij (G_ij - b_i b_j) D_ij with symmetric G given by its LOWER triangle (`low`, ldl) and D any n x n matrix
+ * (ldd): tr(K^-1 dK) - r^T K^-1 dK K^-1 r of the forward-mode gradient, einsum('ij,ijk->k') and einsum('i,ijk,j->k') of
+ * src/lsqfitgp/_linalg/_decomp.py:524-531, one k per call.  out: device, 1 double (zeroed by the call; atomicAdd). */
+int lgp_symlower_dot(lgp_stream_t stream, const double *low, int64_t ldl, const double *b, const double *D, int64_t ldd,
+                     int64_t n, double *out);
+
+/* out[j] = sum_i A[i*lda + j]^2, j < cols: diag(A^T K^-1 A) from L^-1 A, Chol.ginv_diagquad,
+ * src/lsqfitgp/_linalg/_decomp.py:422-427.  out: device, cols doubles (zeroed by the call; atomicAdd). */
+int lgp_colsumsq(lgp_stream_t stream, const double *A, int64_t lda, int64_t rows, int64_t cols, double *out);
+
+/* BART bin indices on the device: out[d*ldo + i] = searchsorted(splits[:, d], x[d*ldx + i], side='left') over the whole
+ * padded column, d < p, i < n (BART.indices_from_coord, src/lsqfitgp/_kernels/_bart.py:294-299,503-514).
+ * splits: maxlen x p row-major (as BART.splits_from_coord returns it, padded with the dtype maximum), DEVICE memory. */
+int lgp_searchsorted(lgp_stream_t stream, const double *splits, int64_t maxlen, int p, const double *x, int64_t ldx,
+                     int64_t n, int32_t *out, int64_t ldo);
+
 /* ------------------------------------------------------------------------------------------------
  * Cholesky with lsqfitgp's equilibration + Gershgorin jitter (Chol.__init__,
  * src/lsqfitgp/_linalg/_decomp.py:245-255,349-361,380-393):

@@ -27,6 +27,7 @@ from . import _Kernel
 from . import _lib
 from . import _linalg
 from . import _ops
+from . import _timing
 
 __all__ = ['GP']
 
@@ -102,6 +103,7 @@ class _GramFn(torch.autograd.Function):
             descs, index = kern._descriptor(labels)
             vjp = _ops.gram_iso_vjp_general(descs, xd, yd, _ops.as_aligned(G.contiguous())).cpu()
             pos = {tf: i for i, tf in enumerate(index)}
+        bart_vjp = {}  # one fused pass per BART term: [d/d amp, d/d alpha, d/d beta]
         for kind, ti, fi, tensor in hyper:
             if kind == 'amp':
                 g = vjp[pos[(ti, 0)], 0]
@@ -109,10 +111,11 @@ class _GramFn(torch.autograd.Function):
                 g = vjp[pos[(ti, fi)], 1] / tensor.detach().cpu()
             elif kind == 'par1':
                 g = vjp[pos[(ti, fi)], 2]
-            elif kind == 'bart_amp':
+            elif kind in ('bart_amp', 'bart_alpha', 'bart_beta'):
                 spec = ti
-                corr = spec.scaled(1.0 / float(spec.amp.detach())).gram_device(xd, yd, labels)
-                g = (G * corr).sum().cpu()
+                if id(spec) not in bart_vjp:
+                    bart_vjp[id(spec)] = spec.vjp_device(xd, yd, _ops.as_aligned(G.contiguous())).cpu()
+                g = bart_vjp[id(spec)][('bart_amp', 'bart_alpha', 'bart_beta').index(kind)]
             else:  # pragma: no cover
                 raise NotImplementedError(kind)
             grads.append(g.to(tensor.device, tensor.dtype).reshape(tensor.shape))
@@ -131,7 +134,7 @@ class _GramFn(torch.autograd.Function):
             pos = {tf: i for i, tf in enumerate(index)}
             tan = numpy.zeros((len(descs), 3))
             for (kind, ti, fi, tensor), t in zip(hyper, tangents):
-                if t is None or kind == 'bart_amp':
+                if t is None or kind.startswith('bart_'):
                     continue
                 tv = float(t.detach())
                 if kind == 'amp':
@@ -143,12 +146,26 @@ class _GramFn(torch.autograd.Function):
                 else:  # pragma: no cover
                     raise NotImplementedError(kind)
             D = _ops.gram_iso_jvp(descs, xd, yd, tan)
+        # BART terms: D += t_amp corr + t_alpha amp dcorr/dalpha + t_beta amp dcorr/dbeta, one kernel pass per term
+        bart_tan = {}
         for (kind, ti, fi, tensor), t in zip(hyper, tangents):
-            if kind == 'bart_amp' and t is not None:
-                spec = ti
-                corr = spec.scaled(1.0 / float(spec.amp.detach() if isinstance(spec.amp, torch.Tensor) else spec.amp)).gram_device(xd, yd, labels)
-                corr *= float(t.detach())
-                D = corr if D is None else D.add_(corr)
+            if kind.startswith('bart_') and t is not None:
+                bart_tan.setdefault(id(ti), [ti, 0.0, 0.0, 0.0])[1 + ('bart_amp', 'bart_alpha', 'bart_beta').index(kind)] \
+                    += float(t.detach())
+        for spec, ta, tal, tbe in bart_tan.values():
+            amp = float(spec.amp.detach() if isinstance(spec.amp, torch.Tensor) else spec.amp)
+            need_d = tal != 0.0 or tbe != 0.0
+            res = spec.gram_device(xd, yd, labels, deriv=need_d)
+            Kb, dKa, dKb = res if need_d else (res, None, None)
+            if D is None:
+                D = torch.zeros(xd.shape[1], yd.shape[1], dtype=f64, device=xd.device)
+                D = _ops.as_aligned(D)
+            if ta != 0.0:
+                _ops.axpby(ta / amp, Kb, 1.0, D)
+            if tal != 0.0:
+                _ops.axpby(tal, dKa, 1.0, D)
+            if tbe != 0.0:
+                _ops.axpby(tbe, dKb, 1.0, D)
         if D is None:
             D = torch.zeros(xd.shape[1], yd.shape[1], dtype=f64, device=xd.device)
         return D
@@ -160,7 +177,9 @@ class _NegLogDensityFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, K, r, kw):
+        _timing.mark('gp&cov')
         dec = _linalg.Chol(K, **kw)
+        _timing.mark('decomp')
         ldq, a = dec.logdet_quad(r)
         ctx.dec, ctx.a = dec, a
         n = dec.n
@@ -173,10 +192,8 @@ class _NegLogDensityFn(torch.autograd.Function):
         b = dec._solve(a[:, None], True)[:, 0]
         gK = gr = None
         if ctx.needs_input_grad[0]:
-            low = dec.inverse_lower()
-            gK = torch.tril(low) + torch.tril(low, -1).T
-            gK -= torch.outer(b, b)
-            gK *= 0.5 * g
+            # g/2 (K^-1 - b b') as a full matrix, one kernel pass over the lower triangle of the inverse
+            gK = _ops.sym_expand_sub(dec.inverse_lower(), b.contiguous(), scale=0.5 * float(g))
         if ctx.needs_input_grad[1]:
             gr = g * b
         return gK, gr, None
@@ -206,7 +223,9 @@ class _FusedNegLogMLFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, kern, xd, labels, r, kw, *params):
         K = kern._gram_device(xd, xd, labels, symmetric=True)
+        _timing.mark('gp&cov')
         dec = _linalg.Chol(K, **kw)
+        _timing.mark('decomp')
         del K
         ctx.low = ctx.side = None
         if any(ctx.needs_input_grad[5:]):
@@ -286,8 +305,10 @@ class GP:
         if self._halfmatrix:
             assert not self._checksym, 'halfmatrix=True requires checksym=False'
         decomp = self._getdecomp(solver)
+        self._solver_name = solver
         self._solverkw = dict(kw)
         self._decompclass = lambda K, **kwargs: decomp(K, **kwargs, **self._solverkw)
+        self._decompbase = decomp
 
     def _clone(self):
         new = object.__new__(type(self))
@@ -512,11 +533,82 @@ class GP:
         assert tuple(cov.shape) == tuple(x.shape) + (y.size,), (cov.shape, x.shape, y.size)
         return cov.reshape(x.size, y.size)
 
+    # ---- scalar linear combinations (addtransf with scalar tensors, e.g. the bayestree.bart recipe
+    # train = trainmean + trainnoise + mean): cov(x, y) = sum_ab c_a c_b cov(a, b) accumulated block by block straight
+    # into one matrix, structurally zero blocks skipped (the generic path materialises every block, zeros included, and
+    # sums them with one pass each: reference _elements.py:581-601)
+    def _expand_scalar(self, key):
+        """ [(coefficient, base key), ...] if `key` is a scalar linear combination of non-transformed elements with
+        plain-number coefficients, else None """
+        e = self._elements[key]
+        if not isinstance(e, _LinTransf):
+            return [(1.0, key)]
+        if e.tensors is None:
+            return None
+        out = []
+        for k, t in e.tensors.items():
+            if t.ndim != 0 or t.requires_grad:
+                return None
+            sub = self._expand_scalar(k)
+            if sub is None:
+                return None
+            c = float(t)
+            out += [(c * cs, ks) for cs, ks in sub]
+        return out
+
+    def _scalar_shapes_ok(self, key, parts):
+        """ every base element of the combination has the size of the result or size 1 (broadcast scalar) """
+        size = self._elements[key].size
+        return all(self._elements[k].size in (size, 1) for _, k in parts)
+
+    def _structurally_zero(self, a, b):
+        ea, eb = self._elements[a], self._elements[b]
+        if isinstance(ea, _Points) and isinstance(eb, _Points):
+            return False
+        if isinstance(ea, _Cov) and isinstance(eb, _Cov):
+            return not (ea.blocks is eb.blocks and (a, b) in ea.blocks)
+        return True   # points and user covariances are independent
+
+    def _makecovblock_scalar_combination(self, xkey, ykey, xs, ys):
+        x, y = self._elements[xkey], self._elements[ykey]
+        n, m = x.size, y.size
+        grad = self._grad_mode() or any(getattr(b, 'requires_grad', False) for e in self._elements.values()
+                                        if isinstance(e, _Cov) for b in e.blocks.values())
+        acc = None
+        for ca, a in xs:
+            for cb, b in ys:
+                if self._structurally_zero(a, b) or ca * cb == 0.0:
+                    continue
+                blk = self._covblock(a, b)
+                c = ca * cb
+                if grad or blk.requires_grad:
+                    term = blk * c if c != 1.0 else blk
+                    if tuple(term.shape) != (n, m):
+                        term = term.expand(n, m)
+                    acc = term if acc is None else acc + term
+                    continue
+                if acc is None:
+                    acc = _ops.aligned_empty(n, m, _device(), zero=True)
+                if tuple(blk.shape) == (n, m):
+                    _ops.axpby(c, blk if blk.stride(1) == 1 else blk.contiguous(), 1.0, acc)
+                elif blk.numel() == 1:
+                    _ops.add_scalar(acc, c * float(blk.reshape(())))
+                else:
+                    acc.add_(blk.expand(n, m), alpha=c)   # other broadcast patterns: rare, generic
+        if acc is None:
+            acc = torch.zeros((n, m), dtype=f64, device=_device())
+        return acc
+
     def _makecovblock(self, xkey, ykey, out=None):
         x = self._elements[xkey]
         y = self._elements[ykey]
+        xs = ys = None
+        if isinstance(x, _LinTransf) or isinstance(y, _LinTransf):
+            xs, ys = self._expand_scalar(xkey), self._expand_scalar(ykey)
         if isinstance(x, _Points) and isinstance(y, _Points):
             cov = self._makecovblock_points(xkey, ykey, out=out)
+        elif xs is not None and ys is not None and self._scalar_shapes_ok(xkey, xs) and self._scalar_shapes_ok(ykey, ys):
+            cov = self._makecovblock_scalar_combination(xkey, ykey, xs, ys)
         elif isinstance(x, _LinTransf):
             cov = self._makecovblock_lintransf_any(xkey, ykey)
         elif isinstance(y, _LinTransf):
@@ -601,16 +693,32 @@ class GP:
             cache = self._decompcache.get(keys)
             if cache is not None:
                 return cache
+        if (hasattr(self._decompbase, 'from_kernel') and len(keys) == 1 and ycov is None and not covtransf
+                and isinstance(self._elements[keys[0]], _Points) and self._covfun._terms and not self._covfun._bart
+                and (keys[0], keys[0]) not in self._covblocks):
+            # distributed solver on one set of points with a kernel-only covariance: every rank generates its own tiles
+            # from the replicated points; the n x n matrix is never assembled (the case that outgrows one GPU)
+            elem = self._elements[keys[0]]
+            descs, _ = self._covfun._descriptor(elem.labels)
+            _timing.mark('gp&cov')
+            skw = dict(self._solverkw)
+            skw.update(kw)
+            decomp = self._decompbase.from_kernel(descs, elem.xd, **skw)
+            _timing.mark('decomp')
+            self._decompcache[keys] = decomp
+            return decomp
         Kxx = self._assemblecovblocks(keys)
         if covtransf:
             if ycov is not None:
                 Kxx = Kxx + ycov
                 ycov = None
             Kxx = covtransf(Kxx)
+        _timing.mark('gp&cov')
         if ycov is not None:
             decomp = self._decompclass(Kxx, _addmat=ycov, **kw)  # Kxx + ycov fused into the equilibration pass
         else:
             decomp = self._decompclass(Kxx, **kw)
+        _timing.mark('decomp')
         if ycov is None and not covtransf:
             self._decompcache[keys] = decomp
         return decomp
@@ -712,6 +820,15 @@ class GP:
                 solver = self._solver(inkeys, ycov)
             else:
                 solver = self._solver(inkeys)
+            if not hasattr(solver, '_solve'):
+                # generic Decomposition (e.g. the distributed solver): the two interface calls of the reference
+                # (_compute.py:259-260)
+                mean = solver.pinv_bilinear(Kxxs, ymean)
+                cov = Kxsxs - solver.ginv_quad(Kxxs)
+                if not fromdata and ycov is not None:
+                    A = solver.ginv_linear(Kxxs)
+                    cov = cov + A.T @ ycov @ A
+                return self._pred_out(mean, cov, outkeys, outslices, strip)
             # mean = (L⁻¹Kxxs)'(L⁻¹y), cov = Kxsxs - (L⁻¹Kxxs)'(L⁻¹Kxxs): one TRSM shared by both
             invLA = solver._solve(_ops.as_aligned(Kxxs), False)
             invLy = solver._solve(ymean[:, None], False)
@@ -725,6 +842,9 @@ class GP:
                 Ainv = solver._solve(invLA, True)  # K⁻¹ Kxxs
                 T = solver._matmul_tn(_ops.as_aligned(ycov.contiguous()), Ainv)  # ycov' A (ycov symmetric)
                 cov = cov + solver._matmul_tn(Ainv, T)
+        return self._pred_out(mean, cov, outkeys, outslices, strip)
+
+    def _pred_out(self, mean, cov, outkeys, outslices, strip):
         mean = mean.cpu().numpy()
         cov = cov.cpu().numpy()
         if not strip:
@@ -789,6 +909,9 @@ class GP:
                 decomp = self._solver(inkeys, ycov, **kw)
                 mll, _, _, _, _ = decomp.minus_log_normal_density(ymean, value=True)
             return -float(mll)
+        if self._solver_name != 'chol':
+            raise NotImplementedError(f"derivatives of marginal_likelihood with solver={self._solver_name!r}: the "
+                                      "distributed decomposition is value-only, use solver='chol' for gradients")
         solverkw = dict(self._solverkw)
         solverkw.update(kw)
         if (len(inkeys) == 1 and ycov is None and isinstance(self._elements[inkeys[0]], _Points)
@@ -803,6 +926,11 @@ class GP:
 
     @staticmethod
     def _getdecomp(solver):
+        """ solver registry (reference _compute.py:424-428: {'chol': Chol}); 'chol-dist' is the same decomposition
+        sharded 2-D block-cyclic over the GPUs of the default process group (lsqfitgp_b200._dist) """
+        if solver == 'chol-dist':
+            from . import _dist
+            return _dist.DistCholDecomposition
         return {'chol': _linalg.Chol}[solver]
 
     @classmethod

@@ -17,3 +17,5 @@ from . import _linalg
 from ._GP import GP
 from ._fit import empbayes_fit
 from ._dist import eval_batch_sharded, eval_concurrent, DistChol
+from ._fastraniter import raniter, sample, sample_batch
+from . import bayestree

@@ -26,7 +26,8 @@ import numpy
 import torch
 import torch.distributed as dist
 
-__all__ = ['shard_indices', 'eval_concurrent', 'eval_batch_sharded', 'peer_reserve', 'Layout', 'default_grid', 'DistChol', 'CudaTileOps']
+__all__ = ['shard_indices', 'eval_concurrent', 'eval_batch_sharded', 'peer_reserve', 'Layout', 'default_grid', 'DistChol', 'CudaTileOps',
+           'DistCholDecomposition']
 
 INT_MAX = 2 ** 31 - 1
 
@@ -887,3 +888,174 @@ class DistChol:
         self._allreduce(out)
         eps = self._epsout[1]
         return out + eps * self.s[:n] ** 2 * vv
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DistChol behind the operator API: GP(..., solver='chol-dist')
+# ---------------------------------------------------------------------------------------------------------------
+
+class _MatrixTileOps(CudaTileOps):
+    """ tile provider that cuts the local tiles out of a matrix replicated on every rank (a user matrix, or an
+    assembled multi-block covariance) instead of generating them from kernel descriptors """
+
+    def __init__(self, device, K, addmat=None):
+        super().__init__(device)
+        self._K, self._add = K, addmat
+
+    def gram_local(self, descs, x, rows, cols, lay):
+        ri = torch.as_tensor(numpy.minimum(rows, lay.n - 1), device=self.device)
+        ci = torch.as_tensor(numpy.minimum(cols, lay.n - 1), device=self.device)
+        ld = max(len(cols) + (len(cols) & 1), 2)
+        A = self.empty(max(len(rows), 1), ld)[:len(rows), :len(cols)]
+        if len(rows) and len(cols):
+            A.copy_(self._K.index_select(0, ri).index_select(1, ci))
+            if self._add is not None:
+                A.add_(self._add.index_select(0, ri).index_select(1, ci))
+        return A
+
+
+def _decomposition_base():
+    from . import _linalg
+    return _linalg.Decomposition
+
+
+class DistCholDecomposition(_decomposition_base()):
+    """`Chol` sharded over the ranks of the default process group: the solver behind ``GP(..., solver='chol-dist')`` and
+    ``GP.decompose(K, solver='chol-dist')`` (reference seam: GPCompute._getdecomp, src/lsqfitgp/_GP/_compute.py:424-428).
+
+    Same regularisation semantics as `Chol` (_decomp.py:380-393); 2-D block-cyclic factorisation by `DistChol`.  Every rank
+    must make the same calls (they are collective); results are replicated.  Two ways in:
+      * ``DistCholDecomposition(K)``: K replicated on every rank (each rank keeps only its tiles for the factorisation);
+      * ``DistCholDecomposition.from_kernel(descs, xd)``: tiles generated in place from kernel descriptors and the
+        replicated points, the n x n matrix never exists anywhere (the GP uses this for a single set of points with a
+        kernel-only covariance, the case that outgrows one GPU).
+    Value-level interface (solves, products, log-density value); derivatives need the single-GPU `Chol`.
+    Keywords: tile (default 1024, reduced for small matrices), grid, peer (see DistChol). """
+
+    def __init__(self, K, *, epsrel='auto', epsabs=0, tile=None, grid=None, peer='auto', _addmat=None, _adddiag=None,
+                 _check=True):
+        from . import _linalg
+        Kd, self._torch_in = _linalg._todev(K)
+        if Kd.ndim != 2 or Kd.shape[0] != Kd.shape[1] or Kd.shape[0] < 1:
+            raise ValueError(f'matrix must be square and non-empty, found shape {tuple(Kd.shape)}')
+        if _adddiag is not None:
+            _addmat = torch.diag(_adddiag) if _addmat is None else _addmat + torch.diag(_adddiag)
+        self._K, self._Kd, self._addmat = K, Kd, _addmat
+        n = Kd.shape[0]
+        x = torch.zeros(1, n, dtype=torch.float64, device=Kd.device)
+        self._dc = DistChol(None, x, tile=self._tile_for(n, tile), grid=grid, epsrel=epsrel, epsabs=epsabs,
+                            ops=_MatrixTileOps(Kd.device, Kd, _addmat), check=_check, peer=peer)
+        self._dc._matvec_src = (Kd, _addmat)
+
+    @classmethod
+    def from_kernel(cls, descs, xd, *, epsrel='auto', epsabs=0, tile=None, grid=None, peer='auto', _check=True):
+        self = object.__new__(cls)
+        self._torch_in = False
+        self._K = self._Kd = self._addmat = None
+        self._dc = DistChol(descs, xd, tile=cls._tile_for(xd.shape[1], tile), grid=grid, epsrel=epsrel, epsabs=epsabs,
+                            check=_check, peer=peer)
+        return self
+
+    @staticmethod
+    def _tile_for(n, tile):
+        if tile is not None:
+            return int(tile)
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        t = 1024
+        while t > 128 and n < 2 * world * t:   # keep a few tiles per rank on small problems
+            t //= 2
+        return t
+
+    # ---- helpers
+    def _vecs(self, X):
+        from . import _linalg
+        Xd, like = _linalg._todev(X)
+        vec = Xd.ndim < 2
+        if vec:
+            Xd = Xd[:, None]
+        if Xd.shape[0] != self.n:
+            raise ValueError(f'shape mismatch: matrix is {self.n}x{self.n}, right-hand side has {Xd.shape[0]} rows')
+        return Xd, vec, like
+
+    def _apply(self, fun, X):
+        """ column-by-column application of a vector operation (the distributed solves are vector sweeps) """
+        Xd, vec, like = self._vecs(X)
+        cols = [fun(Xd[:, j].contiguous()) for j in range(Xd.shape[1])]
+        out = cols[0] if vec else torch.stack(cols, dim=1)
+        return out if like else out.cpu().numpy()
+
+    # ---- Decomposition interface
+    def matrix(self):
+        if self._K is None:
+            raise NotImplementedError('the matrix of a from_kernel decomposition is never materialised')
+        if self._addmat is None:
+            return self._K
+        K = self._Kd + self._addmat
+        return K if self._torch_in else K.cpu().numpy()
+
+    @property
+    def n(self):
+        return self._dc.n
+
+    m = n
+
+    @property
+    def _eps(self):
+        return self._dc.eps
+
+    def ginv_linear(self, X):
+        return self._apply(self._dc.solve, X)
+
+    def pinv_correlate(self, x):
+        return self._apply(self._dc.pinv_correlate, x)
+
+    def correlate(self, x):
+        return self._apply(self._dc.correlate, x)
+
+    def back_correlate(self, X):
+        return self._apply(self._dc.back_correlate, X)
+
+    def pinv_bilinear(self, A, r):
+        Ad, avec, like = self._vecs(A)
+        rd, rvec, _ = self._vecs(r)
+        invLA = torch.stack([self._dc.pinv_correlate(Ad[:, j].contiguous()) for j in range(Ad.shape[1])], dim=1)
+        invLr = torch.stack([self._dc.pinv_correlate(rd[:, j].contiguous()) for j in range(rd.shape[1])], dim=1)
+        out = invLA.T @ invLr
+        if avec and rvec:
+            out = out[0, 0]
+        elif avec:
+            out = out[0]
+        elif rvec:
+            out = out[:, 0]
+        return out if like else out.cpu().numpy()
+
+    def pinv_bilinear_robj(self, A, r):
+        raise NotImplementedError('object arrays (gvars) with the distributed solver')
+
+    def ginv_quad(self, A):
+        Ad, vec, like = self._vecs(A)
+        invLA = torch.stack([self._dc.pinv_correlate(Ad[:, j].contiguous()) for j in range(Ad.shape[1])], dim=1)
+        out = invLA.T @ invLA
+        out = out[0, 0] if vec else out
+        return out if like else out.cpu().numpy()
+
+    def ginv_diagquad(self, A):
+        Ad, vec, like = self._vecs(A)
+        out = torch.stack([(self._dc.pinv_correlate(Ad[:, j].contiguous()) ** 2).sum() for j in range(Ad.shape[1])])
+        out = out[0] if vec else out
+        return out if like else out.cpu().numpy()
+
+    def logdet(self):
+        return self._dc.logdet()
+
+    def minus_log_normal_density(self, r, *, dr_vjp=None, dK_vjp=None, dr_jvp_vec=None, dK_jvp_vec=None, dr=None,
+                                 dK=None, value=False, gradrev=False, gradfwd=False, fisher=False, fishvec=False):
+        if gradrev or gradfwd or fisher or fishvec:
+            raise NotImplementedError("derivatives of the log-density with solver='chol-dist': use solver='chol'")
+        rd, _, like = self._vecs(r)
+        val = None
+        if value:
+            val = self._dc.minus_log_normal_density(rd[:, 0].contiguous())
+            if like:
+                val = torch.tensor(val, dtype=torch.float64, device=rd.device)
+        return val, None, None, None, None

@@ -27,13 +27,33 @@ import torch
 from scipy import optimize
 
 from . import _linalg
+from . import _timing
 
 __all__ = ['empbayes_fit']
 
 f64 = torch.float64
 
-_EXT = re.compile(r'^(\w+)\((.+)\)$')
-_INV = {'log': torch.exp, 'sqrt': torch.square}
+_EXT = re.compile(r'^([\w{}., ]+)\((.+)\)$')
+
+
+def _copula_beta21(z):
+    """ Normal -> Beta(2, 1): ppf(Phi(z)) with ppf(u) = sqrt(u) (reference copula.beta(2, 1), copula/_copulas.py:43-50) """
+    return torch.exp(0.5 * torch.special.log_ndtr(z))
+
+
+def _copula_invgamma11(z):
+    """ Normal -> InvGamma(1, 1): ppf(u) = -1/log(u), evaluated through the upper tail for z >= 0 as the reference does
+    (copula/_copulas.py:141-163) """
+    lo = -1.0 / torch.special.log_ndtr(torch.clamp(z, max=0.0))
+    hi = -1.0 / torch.log1p(-torch.exp(torch.special.log_ndtr(-torch.clamp(z, min=0.0))))
+    return torch.where(z < 0, lo, hi)
+
+
+# key 'f(x)' in the hyperprior is exposed to gpfactory as hp['x'] = f^-1(value), like gvar.BufferDict does
+# (reference _patch_gvar.py:58-63); the two copula names are the ones copula.makedict produces for the priors of
+# bayestree.bart (bayestree/_bart.py:175-184), the only closed-form members of that family needed on this path
+_INV = {'log': torch.exp, 'sqrt': torch.square,
+        '__copula_beta{2, 1}': _copula_beta21, '__copula_invgamma{1, 1}': _copula_invgamma11}
 
 
 class _HyperDict(dict):
@@ -48,6 +68,12 @@ class _HyperDict(dict):
 
     def __contains__(self, key):
         return dict.__contains__(self, key) or any(dict.__contains__(self, f'{n}({key})') for n in _INV)
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
 
 
 class Logger:
@@ -71,11 +97,16 @@ class empbayes_fit(Logger):
 
     def __init__(self, hyperprior, gpfactory, data, *, raises=True, minkw={}, gpfactorykw={}, jit=True,
                  method='gradient', initial='priormean', verbosity=0, covariance='auto', fix=None, mlkw={},
-                 forward=False, additional_loss=None):
+                 forward=False, additional_loss=None, multistart=0, multistart_seed=0, in_flight=1):
         Logger.__init__(self, verbosity)
         self.log('**** call lsqfitgp_b200.empbayes_fit ****')
         assert callable(gpfactory)
-        del jit, forward  # no tracing compiler here; derivatives are always reverse-mode through the CUDA VJP kernels
+        # `jit`: there is no tracing compiler here.  `forward`: the reference's forward mode materialises dK (n, n, k) with
+        # jax.jacfwd and contracts it (_fit.py:679-685, _decomp.py:524-531); the same gradient is obtained here in ONE
+        # reverse sweep by the fused VJP kernels (lgp_gram_iso_vjp / lgp_gram_bart_vjp), whatever the flag says: the
+        # values are identical (tests/test_gpu_api.py::test_gradfwd_equals_gradrev), only the work differs.
+        self._forward = bool(forward)
+        del jit
 
         hpinitial, hpunflat = self._parse_hyperprior(hyperprior, initial, fix)
         self.data = data
@@ -92,7 +123,8 @@ class empbayes_fit(Logger):
         self.gpfactory = gpfactory
         self.gpfactorykw = gpfactorykw
         self._ncalls = {'fun': 0, 'fun&jac': 0}
-        self._times = {'gp&cov+decomp+likelihood': 0.0}
+        self._timer = _timing.PhaseTimer()   # device time of the three phases of the reference's timer (_fit.py:410-442)
+        self._hpunflat = hpunflat
 
         def objective(p, need_grad):
             pt = torch.tensor(numpy.asarray(p, dtype=float), dtype=f64, requires_grad=need_grad)
@@ -102,9 +134,12 @@ class empbayes_fit(Logger):
                 args = data(hp, **gpfactorykw) if cachedargs is None else cachedargs
                 if not isinstance(args, tuple):
                     args = (args,)
-                t0 = time.perf_counter()
-                ml = gp.marginal_likelihood(*args, **mlkw)
-                self._times['gp&cov+decomp+likelihood'] += time.perf_counter() - t0
+                self._timer.start()
+                try:
+                    ml = gp.marginal_likelihood(*args, **mlkw)
+                except BaseException:
+                    self._timer.stop()
+                    raise
                 loss = -ml
                 prior = 1 / 2 * (len(pt) * math.log(2 * math.pi) + pt @ pt)
                 if isinstance(loss, torch.Tensor):
@@ -115,8 +150,12 @@ class empbayes_fit(Logger):
                     extra = additional_loss(hp)
                     total = total + (extra.cpu() if isinstance(extra, torch.Tensor) else extra)
             if not need_grad:
+                self._timer.stop()
                 return float(total)
-            grad, = torch.autograd.grad(total, pt, allow_unused=True)
+            try:
+                grad, = torch.autograd.grad(total, pt, allow_unused=True)
+            finally:
+                self._timer.stop()
             if grad is None:
                 grad = torch.zeros_like(pt)
             return float(total.detach()), grad.numpy().astype(float)
@@ -195,6 +234,30 @@ class empbayes_fit(Logger):
                     self.log('iteration', 3)
         minargs.update(callback=callback)
         minargs.update(minkw)
+
+        # multi-start (not in the reference, whose optimiser evaluates one point at a time, _fit.py:338): the objective
+        # at `multistart` draws of the whitened parameters from their prior N(0, I), plus the requested starting point,
+        # is evaluated as ONE batch sharded over the GPUs of the process group (lsqfitgp_b200.eval_batch_sharded, with
+        # `in_flight` evaluations kept in flight per GPU); the best point starts the minimiser.  Every rank gets the
+        # same batch results, hence runs the same (replicated) minimisation afterwards.
+        self.multistart = None
+        if multistart and len(hpinitial):
+            from . import _dist
+            rng = numpy.random.default_rng(multistart_seed)
+            starts = numpy.vstack([hpinitial, rng.standard_normal((int(multistart), len(hpinitial)))])
+
+            def safe(p):
+                try:
+                    return numpy.array([objective(p, False)])
+                except (numpy.linalg.LinAlgError, RuntimeError):
+                    return numpy.array([numpy.inf])
+            dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None
+            vals = _dist.eval_batch_sharded(safe, starts, device=dev, in_flight=in_flight)[:, 0]
+            vals = numpy.where(numpy.isfinite(vals), vals, numpy.inf)
+            best = int(numpy.argmin(vals))
+            self.multistart = dict(starts=starts, values=vals, best=best)
+            self.log(f'multistart: best of {len(starts)} starting points has objective {vals[best]:.6g}', 2)
+            minargs.update(x0=starts[best])
         self.log(f'minimizer method {minargs["method"]!r}', 2)
         total = time.perf_counter()
         result = optimize.minimize(**minargs)
@@ -212,8 +275,14 @@ class empbayes_fit(Logger):
                 self.log(msg)
 
         cov = self._posterior_covariance(method, covariance, result, fisher)
-        self.log(f'calls: {self._ncalls}; total time {total:.3g} s; in marginal_likelihood '
-                 f'{self._times["gp&cov+decomp+likelihood"]:.3g} s')
+        self._pcov_p = cov
+        # the reference's totals line (_fit.py:775-794): device time per phase, the rest of the wall clock as 'other'
+        times = dict(self._timer.totals)
+        times['other'] = max(total - sum(times.values()), 0.0)
+        self.times = times
+        self.log(f'calls: {self._ncalls}')
+        self.log(f'total time: {total:.3g} s')
+        self.log('partials: ' + ', '.join(f'{k} {v:.3g} s' for k, v in times.items()), 2)
 
         # posterior of the hyperparameters in the original parametrisation: hp = mean + L p (linear map)
         xt = torch.tensor(result.x, dtype=f64)
@@ -233,6 +302,33 @@ class empbayes_fit(Logger):
         self.log('**** exit lsqfitgp_b200.empbayes_fit ****')
 
     # ------------------------------------------------------------------------------------------------
+    def hp_at(self, p):
+        """ hyperparameters (as `gpfactory` receives them: a dictionary that also resolves transformed keys such as
+        hp['x'] for a stored 'log(x)') at the whitened parameter vector p, detached """
+        with torch.no_grad():
+            return self._hpunflat(torch.tensor(numpy.asarray(p, dtype=float), dtype=f64))
+
+    def hp_sdev(self, p, names):
+        """ first-order standard deviation of the (transformed) hyperparameters `names` at p from the posterior
+        covariance of p: what gvar's error propagation gives fit.p['x'] in the reference """
+        cov = numpy.asarray(self._pcov_p)
+        out = {}
+        for name in names:
+            pt = torch.tensor(numpy.asarray(p, dtype=float), dtype=f64, requires_grad=True)
+            v = self._hpunflat(pt)[name]
+            g, = torch.autograd.grad(v.sum(), pt, allow_unused=True)
+            g = numpy.zeros(len(cov)) if g is None else g.numpy()
+            out[name] = float(numpy.sqrt(max(g @ cov @ g, 0.0))) if cov.ndim == 2 and numpy.all(numpy.isfinite(cov)) \
+                else float('nan')
+        return out
+
+    def hp_sample(self, rng=None):
+        """ hyperparameters at a sample of p from its Gaussian posterior approximation (the reference samples
+        fit.pmean / fit.pcov with _fastraniter.sample, bayestree/_bart.py:229-238) """
+        from . import _fastraniter
+        x = _fastraniter.sample(numpy.asarray(self.minresult.x), numpy.asarray(self._pcov_p), rng=rng)
+        return self.hp_at(x)
+
     def _parse_hyperprior(self, hyperprior, initial, fix):
         """ -> (x0, hpunflat); whitening with Chol of the prior covariance (reference _fit.py:444-489) """
         self._isdict = hasattr(hyperprior, 'keys')

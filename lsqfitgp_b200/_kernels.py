@@ -114,10 +114,17 @@ class _BartSpec:
         return self
 
     def hyperparams(self):
+        """ (kind, spec, 0, tensor) for the torch scalars that require grad: amplitude, alpha, beta """
         out = []
         if isinstance(self.amp, torch.Tensor) and self.amp.requires_grad:
             out.append(('bart_amp', self, 0, self.amp))
         for name in ('alpha', 'beta'):
+            v = getattr(self, name)
+            if isinstance(v, torch.Tensor) and v.requires_grad:
+                if self.pnt is not None:
+                    raise NotImplementedError(f'gradient w.r.t. BART {name} with explicit pnt')
+                out.append(('bart_' + name, self, 0, v))
+        for name in ('gamma', 'weights', 'pnt'):
             v = getattr(self, name)
             if isinstance(v, torch.Tensor) and v.requires_grad:
                 raise NotImplementedError(f'gradient w.r.t. BART {name}')
@@ -200,7 +207,7 @@ class _BartSpec:
             drows = numpy.stack([numpy.where(fixed, 0.0, dpa[safe]), numpy.where(fixed, 0.0, dpb[safe])])
         return numpy.array(widths, numpy.int32), numpy.array(nrows, numpy.int32), rows, drows, gamma
 
-    def gram_device(self, xd, yd, labels, out=None):
+    def _indices(self, xd, yd):
         length, splits = self.splits
         length = numpy.asarray(length)
         p = xd.shape[0]
@@ -214,22 +221,34 @@ class _BartSpec:
             iy = _bart_indices_device(yd, splits) if yd is not xd else ix
         w = numpy.ones(p) if self.weights is None else numpy.asarray(self.weights, dtype=float)
         assert numpy.all(w >= 0), 'weights must be in [0, inf)'
-        stages, gamma = self.rows()
-        if len(stages) != 1:
-            # several unmergeable brackets: gamma of one stage is the per-pair output of the previous one.
-            raise NotImplementedError('BART reset pattern that does not fold into a single bracket sequence')
-        return _ops.gram_bart(length, w, stages[0], gamma, _f(self.amp), ix, iy, out=out)
+        return length, w, ix, iy
+
+    def gram_device(self, xd, yd, labels, out=None, deriv=False):
+        """ amp * BART correlation on the device; deriv: also amp * d corr / d alpha, d beta (forward mode) """
+        length, w, ix, iy = self._indices(xd, yd)
+        widths, nrows, rows, drows, gamma = self.stages()
+        if deriv and drows is None:
+            raise NotImplementedError('derivatives w.r.t. alpha / beta with explicit pnt')
+        return _ops.gram_bart_stages(length, w, widths, nrows, rows, drows, gamma, _f(self.amp), ix, iy, out=out,
+                                     deriv=deriv, symmetric=iy is ix)
+
+    def vjp_device(self, xd, yd, G, b=None, symlower=False):
+        """ device tensor [dL/d amp, dL/d alpha, dL/d beta] for the cotangent G of the Gram block (reverse mode, one pass,
+        nothing materialised); symlower: G_ij = w_ij (G[i][j] - b_i b_j) from the lower triangle """
+        length, w, ix, iy = self._indices(xd, xd if symlower else yd)
+        widths, nrows, rows, drows, gamma = self.stages()
+        if drows is None:
+            drows = numpy.zeros((2,) + rows.shape)
+        return _ops.gram_bart_vjp(length, w, widths, nrows, rows, drows, gamma, _f(self.amp), ix, iy, G, b=b,
+                                  symlower=symlower)
 
 
 def _bart_indices_device(xd, splits):
-    """ searchsorted(side='left') per dimension (reference _bart.py:503-514) on the device """
+    """ searchsorted(side='left') per dimension (reference _bart.py:503-514) on the device: lgp_searchsorted """
     s = torch.as_tensor(numpy.asarray(splits), dtype=torch.float64, device=xd.device)
     if s.ndim == 1:
         s = s[:, None]
-    out = torch.empty(xd.shape, dtype=torch.int32, device=xd.device)
-    for i in range(xd.shape[0]):
-        out[i] = torch.searchsorted(s[:, i].contiguous(), xd[i].contiguous()).to(torch.int32)
-    return out
+    return _ops.searchsorted(s, xd)
 
 
 class BART(Kernel):
@@ -341,8 +360,12 @@ class BART(Kernel):
         for u, nu in enumerate(uniq):
             sel = numpy.nonzero(inv == u)[0]
             spec = _BartSpec(1.0, (nu, None), True, alpha, beta, maxd, gamma, pnt, intercept, weights, reset)
-            xd = torch.from_numpy(numpy.ascontiguousarray(fx[sel].T.astype(numpy.float64))).to(dev)
-            yd = torch.from_numpy(numpy.ascontiguousarray(fy[sel].T.astype(numpy.float64))).to(dev)
-            G = spec.gram_device(xd, yd, None)
-            out[sel] = torch.diagonal(G).cpu().numpy()
+            # pair-wise evaluation: 64 x 64 blocks of pairs, of which only the diagonal is wanted (never an m x m Gram)
+            xa = torch.from_numpy(numpy.ascontiguousarray(fx[sel].T.astype(numpy.float64))).to(dev)
+            ya = torch.from_numpy(numpy.ascontiguousarray(fy[sel].T.astype(numpy.float64))).to(dev)
+            res = torch.empty(len(sel), dtype=torch.float64, device=dev)
+            for s0 in range(0, len(sel), 64):
+                G = spec.gram_device(xa[:, s0:s0 + 64].contiguous(), ya[:, s0:s0 + 64].contiguous(), None)
+                res[s0:s0 + 64] = torch.diagonal(G)
+            out[sel] = res.cpu().numpy()
         return out.reshape(shape)

@@ -84,6 +84,11 @@ SIGNATURES = {
     'lgp_bart_digamma_table': (_int, [c_double_p, _i64]),
     'lgp_dgemm': (_int, [_vp, _int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _vp, _i64, _int]),
     'lgp_axpby': (_int, [_vp, _i64, _i64, _dbl, _vp, _i64, _dbl, _vp, _i64, _dbl]),
+    'lgp_add_scalar': (_int, [_vp, _i64, _i64, _vp, _i64, _dbl]),
+    'lgp_sym_expand_sub': (_int, [_vp, _vp, _i64, _vp, _i64, _dbl, _vp, _i64]),
+    'lgp_symlower_dot': (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
+    'lgp_colsumsq': (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
+    'lgp_searchsorted': (_int, [_vp, _vp, _i64, _int, _vp, _i64, _i64, _vp, _i64]),
     'lgp_chol_npad': (_i64, [_i64]),
     'lgp_chol_aux_doubles': (_i64, [_i64]),
     'lgp_chol_factor': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, _i64, _vp, _vp]),

@@ -258,7 +258,7 @@ class Chol(Decomposition):
         # diag(A'K⁻¹A) = sum_j (L⁻¹A)_ji^2                                   (reference _decomp.py:422-427)
         Ad, vec, like = self._rhs(A)
         invLA = self._solve(Ad, False)
-        out = (invLA * invLA).sum(0)
+        out = _ops.colsumsq(invLA)
         return _out(out[0] if vec else out, like)
 
     def correlate(self, x):
@@ -304,9 +304,9 @@ class Chol(Decomposition):
             invLr = self._solve(rd, False)
         if grad:
             invKr = self._solve(invLr, True)
+        low = None
         if (gradrev and dK_vjp is not None) or (gradfwd and dK is not None):
-            low = self.inverse_lower()
-            invK = torch.tril(low) + torch.tril(low, -1).T  # full symmetric matrix for generic callbacks
+            low = self.inverse_lower()   # lower triangle of (K + eps)^-1: the contractions below read only that
 
         def conv(x):
             return x if like else x.cpu().numpy()
@@ -325,10 +325,10 @@ class Chol(Decomposition):
         if gradrev:
             g = 0
             if dK_vjp is not None:
-                b = invKr[:, 0]
-                tr_invK_dK = todev(dK_vjp(conv(invK)))
-                r_invK_dK_invK_r = todev(dK_vjp(conv(torch.outer(b, b))))
-                g = g + 1 / 2 * (tr_invK_dK - r_invK_dK_invK_r)
+                # the VJP is linear: dK_vjp(invK) - dK_vjp(outer(b, b)) = dK_vjp(invK - outer(b, b)), one call on the
+                # full symmetric matrix written by one kernel pass from the lower triangle
+                b = invKr[:, 0].contiguous()
+                g = g + 1 / 2 * todev(dK_vjp(conv(_ops.sym_expand_sub(low, b))))
             if dr_vjp is not None:
                 g = g + todev(dr_vjp(conv(invKr[:, 0])))
             out['gradrev'] = conv(g) if isinstance(g, torch.Tensor) else g
@@ -338,11 +338,15 @@ class Chol(Decomposition):
         if gradfwd:
             g = 0
             if dK is not None:
-                dKd = todev(dK)
-                b = invKr[:, 0]
-                tr_invK_dK = torch.einsum('ij,ijk->k', invK, dKd)
-                r_invK_dK_invK_r = torch.einsum('i,ijk,j->k', b, dKd, b)
-                g = g + 1 / 2 * (tr_invK_dK - r_invK_dK_invK_r)
+                # einsum('ij,ijk->k', invK, dK) - einsum('i,ijk,j->k', b, dK, b), one fused pass per k over the lower
+                # triangle of invK (lgp_symlower_dot); dK: (n, n, k) array or a sequence of k (n, n) matrices
+                if isinstance(dK, (list, tuple)):
+                    dlist = [todev(m) for m in dK]
+                else:
+                    dKd = todev(dK)
+                    dlist = [dKd[:, :, q] for q in range(dKd.shape[2])]
+                b = invKr[:, 0].contiguous()
+                g = g + 1 / 2 * torch.cat([_ops.symlower_dot(low, b, m) for m in dlist])
             if dr is not None:
                 g = g + invKr[:, 0] @ todev(dr)
             out['gradfwd'] = conv(g) if isinstance(g, torch.Tensor) else g

@@ -151,24 +151,148 @@ def frob_dot(A, B):
     return out
 
 
+def add_scalar(Y, c):
+    """ Y += c in place (Y: 2-D, unit column stride) """
+    lib = _lib.load()
+    assert Y.ndim == 2 and Y.stride(1) == 1
+    check(lib.lgp_add_scalar(stream_ptr(), Y.shape[0], Y.shape[1], ptr(Y), Y.stride(0), float(c)), 'lgp_add_scalar')
+    return Y
+
+
+def sym_expand_sub(low, b=None, scale=1.0):
+    """ full symmetric (n, n) matrix scale * (sym(lower triangle of low) - b b') """
+    lib = _lib.load()
+    n = low.shape[0]
+    assert low.shape == (n, n) and low.stride(1) == 1
+    out = aligned_empty(n, n, low.device)
+    if b is not None:
+        b = b.contiguous()
+    check(lib.lgp_sym_expand_sub(stream_ptr(), ptr(low), low.stride(0), ptr(b), n, float(scale), ptr(out), out.stride(0)),
+          'lgp_sym_expand_sub')
+    return out
+
+
+def symlower_dot(low, b, D):
+    """ 1-element device tensor sum_ij (G_ij - b_i b_j) D_ij, G symmetric given by the lower triangle of `low` """
+    lib = _lib.load()
+    n = low.shape[0]
+    assert low.shape == (n, n) and D.shape == (n, n) and low.stride(1) == 1
+    if D.stride(1) != 1:
+        D = D.contiguous()
+    if b is not None:
+        b = b.contiguous()
+    out = torch.empty(1, dtype=f64, device=low.device)
+    check(lib.lgp_symlower_dot(stream_ptr(), ptr(low), low.stride(0), ptr(b), ptr(D), D.stride(0), n, ptr(out)),
+          'lgp_symlower_dot')
+    return out
+
+
+def colsumsq(A):
+    """ device vector of the column sums of squares of A (2-D, unit column stride) """
+    lib = _lib.load()
+    if A.stride(1) != 1:
+        A = A.contiguous()
+    out = torch.empty(A.shape[1], dtype=f64, device=A.device)
+    check(lib.lgp_colsumsq(stream_ptr(), ptr(A), A.stride(0), A.shape[0], A.shape[1], ptr(out)), 'lgp_colsumsq')
+    return out
+
+
+def searchsorted(splits, x):
+    """ splits: (maxlen, p) float64 device (row-major), x: (p, n) float64 device -> (p, n) int32 bin indices (side='left') """
+    lib = _lib.load()
+    splits = splits.contiguous()
+    x = x.contiguous()
+    p, n = x.shape
+    assert splits.ndim == 2 and splits.shape[1] == p
+    out = torch.empty((p, n), dtype=torch.int32, device=x.device)
+    check(lib.lgp_searchsorted(stream_ptr(), ptr(splits), splits.shape[0], p, ptr(x), x.stride(0) if p else 0, n,
+                               ptr(out), out.stride(0) if p else 0), 'lgp_searchsorted')
+    return out
+
+
 _psi_cache = {}
 
 
 def digamma_table(length, device):
-    key = (str(device), length)
+    """ device table psi[k] = digamma(k), at least `length` entries (one growing table per device) """
+    key = str(device)
     t = _psi_cache.get(key)
-    if t is None:
+    if t is None or t.numel() < length:
         lib = _lib.load()
         host = numpy.empty(length, dtype=numpy.float64)
         check(lib.lgp_bart_digamma_table(host.ctypes.data_as(_lib.c_double_p), length), 'lgp_bart_digamma_table')
-        t = torch.from_numpy(host).to(device)
-        _psi_cache.clear()
-        _psi_cache[key] = t
+        t = _psi_cache[key] = torch.from_numpy(host).to(device)
     return t
 
 
+def _bart_cargs(nsplits, w, widths, nrows, rows, drows):
+    """ host-side ctypes views of a BART stage description (see lgp_gram_bart_stages) """
+    nsplits = numpy.ascontiguousarray(nsplits, dtype=numpy.int32)
+    w = numpy.ascontiguousarray(w, dtype=numpy.float64)
+    widths = numpy.ascontiguousarray(widths, dtype=numpy.int32)
+    nrows = numpy.ascontiguousarray(nrows, dtype=numpy.int32)
+    rows = numpy.ascontiguousarray(rows, dtype=numpy.float64)
+    assert rows.ndim == 2 and rows.shape == (int(nrows.sum()), 3) and len(widths) == len(nrows)
+    keep = [nsplits, w, widths, nrows, rows]
+    dptr = None
+    if drows is not None:
+        drows = numpy.ascontiguousarray(drows, dtype=numpy.float64)
+        assert drows.shape == (2,) + rows.shape
+        keep.append(drows)
+        dptr = drows.ctypes.data_as(_lib.c_double_p)
+    args = (len(nsplits), nsplits.ctypes.data_as(_lib.c_int32_p), w.ctypes.data_as(_lib.c_double_p), len(widths),
+            widths.ctypes.data_as(_lib.c_int32_p), nrows.ctypes.data_as(_lib.c_int32_p),
+            rows.ctypes.data_as(_lib.c_double_p), dptr)
+    return args, keep, nsplits
+
+
+def gram_bart_stages(nsplits, w, widths, nrows, rows, drows, gamma, amp, ix, iy, out=None, deriv=False, symmetric=False):
+    """ BART Gram through lgp_gram_bart_stages.  ix: (p, n) int32 device, iy: (p, m) int32 device (the same tensor for
+    symmetric=True).  Returns K, or (K, dKa, dKb) = amp * (corr, d corr / d alpha, d corr / d beta) when deriv. """
+    lib = _lib.load()
+    p, n = ix.shape
+    m = iy.shape[1]
+    args, keep, nsplits = _bart_cargs(nsplits, w, widths, nrows, rows, drows)
+    if out is None:
+        out = aligned_empty(n, m, ix.device)
+    dKa = dKb = None
+    if deriv:
+        dKa = aligned_empty(n, m, ix.device)
+        dKb = aligned_empty(n, m, ix.device)
+    psi = digamma_table(int(nsplits.max(initial=0)) + 2, ix.device) if p else None
+    ix = ix.contiguous()
+    iy = ix if symmetric else iy.contiguous()
+    check(lib.lgp_gram_bart_stages(stream_ptr(), *args, float(gamma), float(amp), ptr(psi), ptr(ix),
+                                   ix.stride(0) if p else 0, n, ptr(iy), iy.stride(0) if p else 0, m, ptr(out),
+                                   out.stride(0), ptr(dKa), ptr(dKb), dKa.stride(0) if deriv else 0,
+                                   _lib.BART_SYMMETRIC if (symmetric and p) else 0), 'lgp_gram_bart_stages')
+    del keep
+    return (out, dKa, dKb) if deriv else out
+
+
+def gram_bart_vjp(nsplits, w, widths, nrows, rows, drows, gamma, amp, ix, iy, G, b=None, symlower=False):
+    """ device tensor [sum G corr, sum G amp dcorr/dalpha, sum G amp dcorr/dbeta] (lgp_gram_bart_vjp); symlower: G read
+    from its lower triangle as w_ij (G_ij - b_i b_j) """
+    lib = _lib.load()
+    p, n = ix.shape
+    m = iy.shape[1]
+    args, keep, nsplits = _bart_cargs(nsplits, w, widths, nrows, rows, drows)
+    assert G.shape == (n, m) and G.stride(1) == 1
+    psi = digamma_table(int(nsplits.max(initial=0)) + 2, ix.device) if p else None
+    ix = ix.contiguous()
+    iy = ix if symlower else iy.contiguous()
+    out = torch.empty(3, dtype=f64, device=ix.device)
+    if b is not None:
+        b = b.contiguous()
+    check(lib.lgp_gram_bart_vjp(stream_ptr(), *args, float(gamma), float(amp), ptr(psi), ptr(ix),
+                                ix.stride(0) if p else 0, n, ptr(iy), iy.stride(0) if p else 0, m, ptr(G), G.stride(0),
+                                ptr(b), 1 if symlower else 0, ptr(out)), 'lgp_gram_bart_vjp')
+    del keep
+    return out
+
+
 def gram_bart(nsplits, w, rows, gamma, amp, ix, iy, out=None):
-    """ ix: (p, n) int32 device, iy: (p, m) int32 device; rows: (nrows, width) host array """
+    """ single-bracket form (lgp_gram_bart). ix: (p, n) int32 device, iy: (p, m) int32 device; rows: (nrows, width) host """
     lib = _lib.load()
     p, n = ix.shape
     m = iy.shape[1]

@@ -1,5 +1,5 @@
 // Per-pair arithmetic of the BART prior correlation (fast path, brackets of width <= 3), shared by the CUDA kernels of
-// gram_bart.cu and by a host build used by the CPU accuracy tests (oracle/bart_core_host.c compiles this very header
+// gram_bart.cu and by a host build used by the CPU accuracy tests (the test-side harness compiles this very header
 // with g++).  Plain C++.
 //
 // Reference: BART._correlation, src/lsqfitgp/_kernels/_bart.py:628-757, with the bracket folding of BART.correlation

@@ -512,3 +512,164 @@ def test_reference_gp_shell_semantics():
     ml = gp.marginal_likelihood({0: z}, {(0, 0): c})
     Kxx = ogp.gram([(1.0, [dict(kind='expquad')])], x[None], x[None])
     assert abs(ml - ogp.logml(Kxx, z, c)) <= 1e-12 * abs(ml)
+
+
+def test_gradfwd_equals_gradrev_and_kernel_contractions():
+    """ Chol.minus_log_normal_density: forward-mode gradient (explicit dK, contracted by lgp_symlower_dot over the lower
+    triangle of the inverse) == reverse-mode gradient (dK_vjp called on the full matrix written by lgp_sym_expand_sub)
+    == oracle (reference _decomp.py:505-531); ginv_diagquad through lgp_colsumsq """
+    rng = np.random.default_rng(17)
+    n, k = 333, 3
+    A = rng.standard_normal((n, n))
+    K = A @ A.T / n + np.eye(n)
+    r = rng.standard_normal(n)
+    dK = rng.standard_normal((n, n, k))
+    dK = dK + dK.transpose(1, 0, 2)
+    dKn = dK + 0.1 * rng.standard_normal((n, n, k))       # not exactly symmetric: the contraction must not assume it
+    dec, ref = lgp._linalg.Chol(K), odecomp.Chol(K)
+    for d in (dK, dKn):
+        _, _, gf, _, _ = dec.minus_log_normal_density(r, dK=d, gradfwd=True)
+        _, _, gf_o, _, _ = ref.minus_log_normal_density(r, dK=d, gradfwd=True)
+        np.testing.assert_allclose(gf, gf_o, rtol=1e-10, atol=1e-12)
+        _, gr, _, _, _ = dec.minus_log_normal_density(r, dK_vjp=lambda G, d=d: np.einsum('ij,ijk->k', G, d), gradrev=True)
+        np.testing.assert_allclose(gr, gf_o, rtol=1e-10, atol=1e-12)
+    _, _, gl, _, _ = dec.minus_log_normal_density(r, dK=[dK[:, :, q].copy() for q in range(k)], gradfwd=True)
+    np.testing.assert_allclose(gl, gf_o if False else ref.minus_log_normal_density(r, dK=dK, gradfwd=True)[2], rtol=1e-10)
+    B = rng.standard_normal((n, 37))
+    np.testing.assert_allclose(dec.ginv_diagquad(B), ref.ginv_diagquad(B), rtol=1e-10)
+    np.testing.assert_allclose(dec.ginv_diagquad(B[:, 0]), ref.ginv_diagquad(B[:, :1])[0], rtol=1e-10)
+
+
+def test_raniter_sample_match_oracle_path():
+    """ raniter / sample (reference _fastraniter.py:36-121): same seed -> mean + L z with the oracle's Chol factor """
+    rng = np.random.default_rng(3)
+    n = 50
+    A = rng.standard_normal((n, n))
+    cov = A @ A.T / n + 0.1 * np.eye(n)
+    mean = rng.standard_normal(n)
+    L = odecomp.Chol(cov)._L
+    zs = np.random.default_rng(99)
+    got = list(lgp.raniter(mean, cov, n=3, rng=99))
+    for g in got:
+        np.testing.assert_allclose(g, mean + L @ zs.standard_normal(n), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(lgp.sample(mean, cov, rng=99), got[0], rtol=1e-13)
+    batch = lgp.sample_batch(mean, cov, 3, rng=99)
+    np.testing.assert_allclose(batch, np.stack(got), rtol=1e-10, atol=1e-12)
+    # dictionary form, scalar form, empirical covariance of a device-generated batch
+    md = {'a': mean[:20].reshape(4, 5), 'b': mean[20:]}
+    cd = {('a', 'a'): cov[:20, :20].reshape(4, 5, 4, 5), ('a', 'b'): cov[:20, 20:].reshape(4, 5, 30),
+          ('b', 'a'): cov[20:, :20].reshape(30, 4, 5), ('b', 'b'): cov[20:, 20:]}
+    sd = lgp.sample(md, cd, rng=99)
+    np.testing.assert_allclose(np.r_[sd['a'].reshape(-1), sd['b']], got[0], rtol=1e-10, atol=1e-12)
+    assert isinstance(lgp.sample(1.0, 4.0, rng=1), float)
+    big = lgp.sample_batch(mean, cov, 20000, rng=5, device_rng=True)
+    emp = np.cov(big.T)
+    assert np.max(np.abs(emp - cov)) < 0.05 * np.max(np.abs(cov))
+    with pytest.raises(np.linalg.LinAlgError):
+        lgp.sample(np.zeros(2), np.array([[1.0, 2.0], [2.0, 1.0]]), eps=0)
+
+
+def test_solver_chol_dist_single_process_matches_chol():
+    """ GP(..., solver='chol-dist') (reference seam _compute.py:424-428) on a 1 x 1 process grid: same marginal
+    likelihood and posterior as solver='chol'; GP.decompose with the distributed class; multi-rank runs of the same code
+    are in tests/test_gpu_dist.py """
+    rng = np.random.default_rng(8)
+    n = 700
+    X = rng.uniform(0, 10, (n, 2))
+    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(n)
+    xs = lgp.unstructured_to_structured(X, names=['a', 'b'])
+    kern = 1.3 * lgp.ExpQuad(scale=1.7) + 0.01 * lgp.White()
+    out = {}
+    for solver in ('chol', 'chol-dist'):
+        gp = lgp.GP(kern, solver=solver, checkpos=False, checksym=False).addx(xs, 'd').addx(xs[:40], 'p')
+        out[solver] = (gp.marginal_likelihood({'d': y}), *gp.predfromdata({'d': y}, 'p', raw=True))
+    assert abs(out['chol'][0] - out['chol-dist'][0]) <= 1e-11 * abs(out['chol'][0])
+    np.testing.assert_allclose(out['chol-dist'][1], out['chol'][1], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(out['chol-dist'][2], out['chol'][2], rtol=1e-8, atol=1e-10)
+    K = ogp.gram([(1.3, [dict(kind='expquad', scale=1.7)]), (0.01, [dict(kind='white')])], X.T.copy(), X.T.copy())
+    dd = lgp.GP.decompose(K, solver='chol-dist')
+    ref = odecomp.Chol(K)
+    b = rng.standard_normal(n)
+    np.testing.assert_allclose(dd.ginv_linear(b), ref.ginv_linear(b), rtol=1e-8)
+    np.testing.assert_allclose(dd.correlate(b), ref.correlate(b), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(dd.ginv_diagquad(np.stack([b, 2 * b], 1)), ref.ginv_diagquad(np.stack([b, 2 * b], 1)), rtol=1e-9)
+    assert dd.eps == pytest.approx(ref.eps, rel=1e-14) and dd.n == n
+    with pytest.raises(NotImplementedError):
+        th = torch.tensor(1.7, dtype=torch.float64, requires_grad=True)
+        lgp.GP(lgp.ExpQuad(scale=th), solver='chol-dist').addx(xs, 'd').marginal_likelihood({'d': y})
+
+
+def test_empbayes_multistart_sharded_batch():
+    """ multistart: the starting points go through eval_batch_sharded as one batch; the best one starts the minimiser """
+    rng = np.random.default_rng(12)
+    n = 300
+    X = rng.uniform(0, 30, (n, 1))
+    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(n)
+    xs = lgp.unstructured_to_structured(X, names=['t'])
+    hyperprior = {'log(ell)': (np.log(10.0), 1.5), 'log(sn)': (np.log(0.3), 1.0)}
+
+    def gpfactory(hp):
+        return lgp.GP(lgp.ExpQuad(scale=hp['ell']) + hp['sn'] ** 2 * lgp.White(), checkpos=False, checksym=False).addx(xs, 'd')
+    fit = lgp.empbayes_fit(hyperprior, gpfactory, {'d': y}, raises=False, multistart=6, in_flight=2)
+    ms = fit.multistart
+    assert ms['starts'].shape == (7, 2) and np.all(ms['starts'][0] == 0) and ms['values'][ms['best']] == ms['values'].min()
+    assert np.array_equal(fit.minargs['x0'], ms['starts'][ms['best']])
+    plain = lgp.empbayes_fit(hyperprior, gpfactory, {'d': y}, raises=False)
+    assert fit.minresult.fun <= plain.minresult.fun + 1e-6
+
+
+def test_bart_indices_device_kernel_matches_host():
+    """ lgp_searchsorted (BART.indices_from_coord on the device, reference _bart.py:294-299,503-514): bit-equal to the host """
+    rng = np.random.default_rng(4)
+    X = np.concatenate([rng.standard_normal((500, 3)), rng.integers(0, 4, (500, 2)).astype(float)], axis=1)
+    splits = lgp.BART.splits_from_coord(X)
+    want = lgp.BART.indices_from_coord(X, splits)
+    from lsqfitgp_b200._kernels import _bart_indices_device
+    xd = torch.tensor(np.ascontiguousarray(X.T), device='cuda')
+    got = _bart_indices_device(xd, splits[1]).cpu().numpy().T
+    assert np.array_equal(got, want)
+    Xq = rng.standard_normal((77, 5)) * 3          # points outside the training range
+    got = _bart_indices_device(torch.tensor(np.ascontiguousarray(Xq.T), device='cuda'), splits[1]).cpu().numpy().T
+    assert np.array_equal(got, lgp.BART.indices_from_coord(Xq, splits))
+
+
+def test_chol_on_two_devices_in_one_process():
+    """ stream pools and kernel attributes are per device: factor on cuda:0 then on cuda:1 """
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    rng = np.random.default_rng(2)
+    n = 1500
+    A = rng.standard_normal((n, n))
+    K = A @ A.T / n + np.eye(n)
+    b = rng.standard_normal(n)
+    want = odecomp.Chol(K).ginv_linear(b)
+    for d in (0, 1, 0):
+        with torch.cuda.device(d):
+            dec = lgp._linalg.Chol(K)
+            np.testing.assert_allclose(dec.ginv_linear(b), want, rtol=1e-9)
+            low = dec.inverse_lower()
+            assert low.device.index == d and torch.isfinite(torch.tril(low)).all()
+
+
+def test_get_factor_beyond_grid_y_limit():
+    """ row counts above 65535 (gridDim.y limit): lgp_chol_get_factor on a synthetic factor state """
+    n = 65536 + 300
+    st = _ops_state(n)
+    L = lgp._ops.chol_get_factor(st)
+    rows = torch.tensor([0, 1, 65534, 65535, 65536, n - 1], device='cuda')
+    sub = L.index_select(0, rows).cpu().numpy()
+    for q, i in enumerate(rows.cpu().numpy()):
+        assert np.all(sub[q, :i + 1] == 2.0 * 0.5) and np.all(sub[q, i + 1:] == 0.0), i
+    del L, st
+    torch.cuda.empty_cache()
+
+
+def _ops_state(n):
+    from lsqfitgp_b200 import _ops, _lib
+    lib = _lib.load()
+    st = _ops.FactorState()
+    st.n, st.npad, st.device = n, int(lib.lgp_chol_npad(n)), torch.device('cuda', torch.cuda.current_device())
+    st.W = torch.full((st.npad, st.npad), 0.5, dtype=torch.float64, device=st.device)
+    st.aux = torch.full((int(lib.lgp_chol_aux_doubles(n)),), 2.0, dtype=torch.float64, device=st.device)
+    st.info = torch.zeros(1, dtype=torch.int32, device=st.device)
+    return st

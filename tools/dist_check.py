@@ -116,6 +116,29 @@ def main():
         e_eps = abs(dc.eps - ref.eps) / ref.eps
         out.update(err_logdet=e_ld, err_solve=e_sol, err_eps=e_eps)
         ok = ok and e_ld <= 1e-12 and e_sol <= 1e-9 and e_eps <= 1e-13
+        # products with the factor and the size-independent L (L^T v) = (K + eps S^2) v check
+        lc = ref.correlate(b)
+        e_cor = float(np.max(np.abs(dc.correlate(bd).cpu().numpy() - lc)) / np.max(np.abs(lc)))
+        kv = dc.matvec(bd)
+        e_llt = float(((dc.correlate(dc.back_correlate(bd)) - kv).norm() / kv.norm()).item())
+        out.update(err_correlate=e_cor, err_llt=e_llt)
+        ok = ok and e_cor <= 1e-11 and e_llt <= 1e-12
+        # the operator API on the same ranks: GP(..., solver='chol-dist') (tiles generated from the kernel, no n x n
+        # matrix anywhere) and GP.decompose(K, solver='chol-dist') (replicated matrix cut into tiles)
+        import lsqfitgp_b200 as lgp
+        xs = lgp.unstructured_to_structured(X, names=['a', 'b'])
+        kern = lgp.ExpQuad(scale=args.scale) + 0.01 * lgp.White()
+        gp = lgp.GP(kern, solver='chol-dist', tile=args.tile, grid=grid, checkpos=False, checksym=False).addx(xs, 'd') \
+            .addx(xs[:25], 'p')
+        ml = gp.marginal_likelihood({'d': b})
+        ml_ref = ogp.logml(K, b)
+        mean, cov = gp.predfromdata({'d': b}, 'p', raw=True)
+        mean_ref, cov_ref = ogp.pred(K, K[:, :25], K[:25, :25], b)
+        dd = lgp.GP.decompose(K, solver='chol-dist', tile=args.tile, grid=grid)
+        e_api = max(abs(ml - ml_ref) / abs(ml_ref), float(np.max(np.abs(mean - mean_ref)) / np.max(np.abs(mean_ref))),
+                    float(np.max(np.abs(dd.ginv_linear(b) - sol_ref)) / np.max(np.abs(sol_ref))))
+        out.update(err_api=e_api)
+        ok = ok and e_api <= 1e-9
     if rank == 0:
         print(json.dumps(out))
         if args.out:
