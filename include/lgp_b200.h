@@ -121,6 +121,24 @@ int lgp_gram_iso_jvp(lgp_stream_t stream, const lgp_factor_t *factors, int nfact
                      int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, const double *tangent,
                      double *D_out, int64_t ldd);
 
+/* Variants with DEVICE-RESIDENT hyperparameters: what an XLA-FFI custom call needs, where traced scalars arrive as device
+ * buffers and must not be read on the host (the boundary B3 of SURVEY.md section 8b: jax.ffi handlers wrapping these are in
+ * lsqfitgp_b200/csrc/xla_ffi_shim.cc).  `factors` (HOST) carries only the structure: kind, term,
+ * dimmask, ipar and par0 (Matern order / Maternp offset / Cauchy alpha: static, not differentiable, as in the reference);
+ * its other fields are ignored.  `devpar` (DEVICE): LGP_DEVPAR_STRIDE doubles per factor, in the order scale_x, scale_y,
+ * loc_x, loc_y, par1, amp.  `tangent_dev` (DEVICE): 3*nfactors doubles.  Same results as the host-descriptor entry points
+ * for the same numbers; they run the general (sum-of-products) kernels, not the single-term fast paths. */
+#define LGP_DEVPAR_STRIDE 6
+int lgp_gram_iso_dev(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *devpar,
+                     const double *x, int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, double *K_out,
+                     int64_t ldk, int flags);
+int lgp_gram_iso_vjp_dev(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *devpar,
+                         const double *x, int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m,
+                         const double *G, int64_t ldg, const double *b, int symlower, double *out);
+int lgp_gram_iso_jvp_dev(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *devpar,
+                         const double *x, int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m,
+                         const double *tangent_dev, double *D_out, int64_t ldd);
+
 /* out[0] = sum_{i<rows, j<cols} A[i*lda+j] * B[i*ldb+j]: the contraction einsum('kij,qij->kq') of the Fisher matrix
  * (src/lsqfitgp/_linalg/_decomp.py:553), one (k, q) pair per call.  out: device memory, 1 double. */
 int lgp_frob_dot(lgp_stream_t stream, const double *A, int64_t lda, const double *B, int64_t ldb, int64_t rows,

@@ -23,6 +23,7 @@ ERRORS = {-1: 'bad argument', -2: 'misaligned pointer or odd leading dimension',
 K_EXPQUAD, K_MATERNP, K_CAUCHY, K_WHITE, K_CONSTANT, K_MATERN = range(6)
 GRAM_SYMMETRIC, GRAM_GENERAL, GRAM_LIBM = 1, 2, 4  # LGP_GRAM_* flags of lgp_gram_iso
 MAX_FACTORS = 8
+DEVPAR_STRIDE = 6  # scale_x, scale_y, loc_x, loc_y, par1, amp
 BART_MAX_ROWS, BART_MAX_STAGES, BART_SYMMETRIC = 16, 8, 1
 MAX_DIMS = 32
 
@@ -74,6 +75,12 @@ SIGNATURES = {
                                 _vp, _int, _vp]),
     'lgp_gram_iso_jvp': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _i64, c_double_p,
                                 _vp, _i64]),
+    'lgp_gram_iso_dev': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64,
+                                _int]),
+    'lgp_gram_iso_vjp_dev': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp,
+                                    _i64, _vp, _int, _vp]),
+    'lgp_gram_iso_jvp_dev': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp,
+                                    _vp, _i64]),
     'lgp_frob_dot': (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     'lgp_gram_bart': (_int, [_vp, _int, c_int32_p, c_double_p, c_double_p, _int, _int, _dbl, _dbl, _vp,
                              _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int]),

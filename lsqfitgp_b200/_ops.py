@@ -141,6 +141,70 @@ def gram_iso_jvp(descs, x, y, tangent, out=None):
     return out
 
 
+def devpar_of(descs, device):
+    """ (nfactors, 6) device tensor of the numeric descriptor fields in the LGP_DEVPAR_STRIDE order
+    (scale_x, scale_y, loc_x, loc_y, par1, amp): what a traced caller keeps on the device """
+    rows = [[d.get('scale_x', 1.0), d.get('scale_y', 1.0), d.get('loc_x', 0.0), d.get('loc_y', 0.0), d.get('par1', 0.0),
+             d.get('amp', 1.0)] for d in descs]
+    return torch.tensor(rows, dtype=f64, device=device)
+
+
+def _structure_only(descs):
+    """ descriptor list with the numeric (device-resident) fields blanked: only kind, term, dimmask, ipar, par0 are kept """
+    return [dict(kind=d['kind'], term=d['term'], dimmask=d['dimmask'], ipar=d.get('ipar', 0), par0=d.get('par0', 0.0),
+                 scale_x=float('nan'), scale_y=float('nan'), loc_x=float('nan'), loc_y=float('nan'), par1=float('nan'),
+                 amp=float('nan')) for d in descs]
+
+
+def gram_iso_dev(descs, devpar, x, y, out=None):
+    """ lgp_gram_iso_dev: Gram matrix with the hyperparameters read from the device tensor `devpar` """
+    lib = _lib.load()
+    ndim, n = x.shape
+    m = y.shape[1]
+    x = x.contiguous() if x.stride(1) != 1 else x
+    y = y.contiguous() if y.stride(1) != 1 else y
+    if out is None:
+        out = aligned_empty(n, m, x.device)
+    facs = make_factors(_structure_only(descs))
+    devpar = devpar.contiguous()
+    check(lib.lgp_gram_iso_dev(stream_ptr(), facs, len(descs), ndim, ptr(devpar), ptr(x), x.stride(0) if ndim else 0, n,
+                               ptr(y), y.stride(0) if ndim else 0, m, ptr(out), out.stride(0), 0), 'lgp_gram_iso_dev')
+    return out
+
+
+def gram_iso_vjp_dev(descs, devpar, x, y, G, b=None, symlower=False):
+    lib = _lib.load()
+    ndim, n = x.shape
+    m = y.shape[1]
+    x = x.contiguous() if x.stride(1) != 1 else x
+    y = x if symlower else (y.contiguous() if y.stride(1) != 1 else y)
+    buf = torch.empty(3 * len(descs) + 8, dtype=f64, device=x.device)
+    facs = make_factors(_structure_only(descs))
+    devpar = devpar.contiguous()
+    check(lib.lgp_gram_iso_vjp_dev(stream_ptr(), facs, len(descs), ndim, ptr(devpar), ptr(x), x.stride(0) if ndim else 0,
+                                   n, ptr(y), y.stride(0) if ndim else 0, m, ptr(G), G.stride(0), ptr(b),
+                                   1 if symlower else 0, ptr(buf)), 'lgp_gram_iso_vjp_dev')
+    return buf[:3 * len(descs)].reshape(len(descs), 3)
+
+
+def gram_iso_jvp_dev(descs, devpar, x, y, tangent_dev, out=None):
+    lib = _lib.load()
+    ndim, n = x.shape
+    m = y.shape[1]
+    x = x.contiguous() if x.stride(1) != 1 else x
+    y = y.contiguous() if y.stride(1) != 1 else y
+    if out is None:
+        out = aligned_empty(n, m, x.device)
+    facs = make_factors(_structure_only(descs))
+    devpar = devpar.contiguous()
+    tangent_dev = tangent_dev.contiguous().reshape(-1)
+    assert tangent_dev.numel() == 3 * len(descs)
+    check(lib.lgp_gram_iso_jvp_dev(stream_ptr(), facs, len(descs), ndim, ptr(devpar), ptr(x), x.stride(0) if ndim else 0,
+                                   n, ptr(y), y.stride(0) if ndim else 0, m, ptr(tangent_dev), ptr(out), out.stride(0)),
+          'lgp_gram_iso_jvp_dev')
+    return out
+
+
 def frob_dot(A, B):
     """ sum_ij A_ij B_ij as a 1-element device tensor (A, B: 2-D, unit column stride) """
     lib = _lib.load()

@@ -18,36 +18,49 @@ _current = threading.local()
 
 
 class PhaseTimer:
+    """ accumulates device time per phase over many evaluations; evaluations may run concurrently on several host
+    threads (one stream each: empbayes_fit's multistart batch), so the events of an evaluation live in thread-local
+    storage and only the totals are shared """
+
     def __init__(self):
         self.totals = dict.fromkeys(PHASES, 0.0)   # seconds of device time
         self.wall = 0.0
-        self._events = None
+        self._lock = threading.Lock()
 
-    def _event(self):
+    @staticmethod
+    def _event():
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
         return ev
 
     def start(self):
-        self._events = [(None, self._event())] if torch.cuda.is_available() else None
-        self._t0 = time.perf_counter()
         _current.timer = self
+        _current.events = [(None, self._event())] if torch.cuda.is_available() else None
+        _current.t0 = time.perf_counter()
 
     def mark(self, name):
-        if self._events is not None and self._events[-1][0] != name:
-            self._events.append((name, self._event()))
+        events = getattr(_current, 'events', None)
+        if events is not None and events[-1][0] != name:
+            events.append((name, self._event()))
 
     def stop(self):
-        _current.timer = None
-        self.wall += time.perf_counter() - self._t0
-        if self._events is None:
+        events = getattr(_current, 'events', None)
+        t0 = getattr(_current, 't0', None)
+        _current.timer = _current.events = _current.t0 = None
+        if t0 is None:
             return
-        # whatever follows the last mark (value, gradient) is the likelihood phase
-        self._events.append(('likelihood', self._event()))
-        self._events[-1][1].synchronize()
-        for (_, e0), (name, e1) in zip(self._events, self._events[1:]):
-            self.totals[name] += e0.elapsed_time(e1) * 1e-3
-        self._events = None
+        wall = time.perf_counter() - t0
+        parts = {}
+        if events is not None:
+            # whatever follows the last mark (value, gradient) is the likelihood phase
+            events.append(('likelihood', self._event()))
+            events[-1][1].synchronize()
+            for (_, e0), (name, e1) in zip(events, events[1:]):
+                parts[name] = parts.get(name, 0.0) + e0.elapsed_time(e1) * 1e-3
+        with self._lock:
+            self.wall += wall
+            for k, v in parts.items():
+                self.totals[k] += v
 
 
 def mark(name):

@@ -179,30 +179,67 @@ __device__ __forceinline__ void stage_points(const GramDesc &d, double *s, const
     }
 }
 
+// Device-resident hyperparameters (the XLA-FFI path: traced scalars live in device buffers).
+// `devpar` holds LGP_DEVPAR_STRIDE doubles per factor: scale_x, scale_y, loc_x, loc_y, par1, amp; the structural fields
+// (kind, term, dimmask, ipar, par0) stay host-side attributes.  The DEV instantiations of the general kernels copy the
+// descriptor into shared memory and overwrite the numeric fields from `devpar` before anything else.
+template <bool DEV>
+struct DevDescStore {
+    char unused;
+};
+template <>
+struct DevDescStore<true> {
+    GramDesc d;
+};
+__device__ __forceinline__ void load_dev_desc(const GramDesc &d, const double *__restrict__ devpar, GramDesc &sd, int tid) {
+    const int *src = reinterpret_cast<const int *>(&d);
+    int *dst = reinterpret_cast<int *>(&sd);
+    for (int i = tid; i < (int)(sizeof(GramDesc) / sizeof(int)); i += G_THREADS) dst[i] = src[i];
+    __syncthreads();
+    if (tid < d.nfactors) {
+        const double *q = devpar + LGP_DEVPAR_STRIDE * tid;
+        sd.scale_x[tid] = q[0];
+        sd.scale_y[tid] = q[1];
+        sd.loc_x[tid] = q[2];
+        sd.loc_y[tid] = q[3];
+        sd.par1[tid] = q[4];
+        sd.amp[tid] = q[5];
+    }
+    __syncthreads();
+}
+template <bool DEV>
 __global__ void __launch_bounds__(G_THREADS) gram_iso_kernel(const __grid_constant__ GramDesc d,
                                                              const double *__restrict__ x, int64_t ldx, int64_t n,
                                                              const double *__restrict__ y, int64_t ldy, int64_t m,
-                                                             double *__restrict__ K, int64_t ldk, int vec_ok) {
+                                                             double *__restrict__ K, int64_t ldk, int vec_ok, const double *__restrict__ devpar) {
+    __shared__ DevDescStore<DEV> sdesc;
+    if constexpr (DEV) load_dev_desc(d, devpar, sdesc.d, threadIdx.x);
+    const GramDesc &dd = [&]() -> const GramDesc & {
+        if constexpr (DEV)
+            return sdesc.d;
+        else
+            return d;
+    }();
     extern __shared__ __align__(16) double gsm[];
     double *su = gsm;
-    double *sv = gsm + (size_t)d.nslots * GT;
+    double *sv = gsm + (size_t)dd.nslots * GT;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int64_t i0 = (int64_t)blockIdx.y * GT, j0 = (int64_t)blockIdx.x * GT;
-    stage_points(d, su, x, ldx, n, i0, false, tid);
-    stage_points(d, sv, y, ldy, m, j0, true, tid);
+    stage_points(dd, su, x, ldx, n, i0, false, tid);
+    stage_points(dd, sv, y, ldy, m, j0, true, tid);
     __syncthreads();
 
     double sum[4][4];
     double prod[4][4];
     int cur_term = -1;
     bool first_term = true;
-    for (int f = 0; f < d.nfactors; f++) {
+    for (int f = 0; f < dd.nfactors; f++) {
         double r2[4][4];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int c = 0; c < 4; c++) r2[a][c] = 0.0;
-        for (int s = d.slot0[f]; s < d.slot0[f] + d.nslot[f]; s++) {
+        for (int s = dd.slot0[f]; s < dd.slot0[f] + dd.nslot[f]; s++) {
             double uu[4], vv[4];
 #pragma unroll
             for (int a = 0; a < 4; a++) uu[a] = su[s * GT + ty + 16 * a];
@@ -218,10 +255,10 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_kernel(const __grid_consta
                 for (int c = 0; c < 4; c++) {
                     double df = __dsub_rn(uu[a], vv[c]);
                     double sq = __dmul_rn(df, df);
-                    r2[a][c] = (s == d.slot0[f]) ? sq : __dadd_rn(r2[a][c], sq);
+                    r2[a][c] = (s == dd.slot0[f]) ? sq : __dadd_rn(r2[a][c], sq);
                 }
         }
-        const bool new_term = d.term[f] != cur_term;
+        const bool new_term = dd.term[f] != cur_term;
         if (new_term && cur_term != -1) {
 #pragma unroll
             for (int a = 0; a < 4; a++)
@@ -229,13 +266,13 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_kernel(const __grid_consta
                 for (int c = 0; c < 4; c++) sum[a][c] = first_term ? prod[a][c] : __dadd_rn(sum[a][c], prod[a][c]);
             first_term = false;
         }
-        cur_term = d.term[f];
-        const double amp = d.amp[f];
+        cur_term = dd.term[f];
+        const double amp = dd.amp[f];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                double v = __dmul_rn(amp, core_value(d, f, r2[a][c]));
+                double v = __dmul_rn(amp, core_value(dd, f, r2[a][c]));
                 prod[a][c] = new_term ? v : __dmul_rn(prod[a][c], v);
             }
     }
@@ -268,15 +305,24 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_kernel(const __grid_consta
 // symlower = 1: x == y, only j <= i is visited, G_ij = w_ij (Ginv[i][j] - b_i b_j) with w = 2 off the diagonal
 //               (the collapsed dK_vjp(invK) - dK_vjp(outer(invKr, invKr)) of _decomp.py:505-509).
 // acc layout per factor: [0] d/d amp, [1] d/d log(scale), [2] d/d par1
+template <bool DEV>
 __global__ void __launch_bounds__(G_THREADS) gram_iso_vjp_kernel(const __grid_constant__ GramDesc d,
                                                                  const double *__restrict__ x, int64_t ldx,
                                                                  int64_t n, const double *__restrict__ y, int64_t ldy,
                                                                  int64_t m, const double *__restrict__ G, int64_t ldg,
                                                                  const double *__restrict__ bvec, int symlower,
-                                                                 int tiles_n, double *__restrict__ out) {
+                                                                 int tiles_n, double *__restrict__ out, const double *__restrict__ devpar) {
+    __shared__ DevDescStore<DEV> sdesc;
+    if constexpr (DEV) load_dev_desc(d, devpar, sdesc.d, threadIdx.x);
+    const GramDesc &dd = [&]() -> const GramDesc & {
+        if constexpr (DEV)
+            return sdesc.d;
+        else
+            return d;
+    }();
     extern __shared__ __align__(16) double gsm[];
     double *su = gsm;
-    double *sv = gsm + (size_t)d.nslots * GT;
+    double *sv = gsm + (size_t)dd.nslots * GT;
     __shared__ double red[G_THREADS / 32][3 * LGP_MAX_FACTORS];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     int tm, tn;
@@ -291,8 +337,8 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_vjp_kernel(const __grid_co
         tn = blockIdx.x % tiles_n;
     }
     const int64_t i0 = (int64_t)tm * GT, j0 = (int64_t)tn * GT;
-    stage_points(d, su, x, ldx, n, i0, false, tid);
-    stage_points(d, sv, y, ldy, m, j0, true, tid);
+    stage_points(dd, su, x, ldx, n, i0, false, tid);
+    stage_points(dd, sv, y, ldy, m, j0, true, tid);
     __syncthreads();
 
     double acc[3 * LGP_MAX_FACTORS];
@@ -316,28 +362,28 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_vjp_kernel(const __grid_co
             double val[LGP_MAX_FACTORS], dr2[LGP_MAX_FACTORS], dp1[LGP_MAX_FACTORS], r2s[LGP_MAX_FACTORS];
 #pragma unroll
             for (int f = 0; f < LGP_MAX_FACTORS; f++) {
-                if (f < d.nfactors) {
+                if (f < dd.nfactors) {
                     double r2 = 0.0;
-                    for (int s = d.slot0[f]; s < d.slot0[f] + d.nslot[f]; s++) {
+                    for (int s = dd.slot0[f]; s < dd.slot0[f] + dd.nslot[f]; s++) {
                         double df = su[s * GT + ty + 16 * a] - sv[s * GT + cc];
                         r2 += df * df;
                     }
                     r2s[f] = r2;
-                    core_derivs(d, f, r2, val[f], dr2[f], dp1[f]);
+                    core_derivs(dd, f, r2, val[f], dr2[f], dp1[f]);
                 }
             }
 #pragma unroll
             for (int f = 0; f < LGP_MAX_FACTORS; f++) {
-                if (f < d.nfactors) {
+                if (f < dd.nfactors) {
                     // product of the other factors of the same term (with their amps)
                     double others = 1.0;
 #pragma unroll
                     for (int h = 0; h < LGP_MAX_FACTORS; h++)
-                        if (h < d.nfactors && h != f && d.term[h] == d.term[f]) others *= d.amp[h] * val[h];
+                        if (h < dd.nfactors && h != f && dd.term[h] == dd.term[f]) others *= dd.amp[h] * val[h];
                     const double go = g * others;
                     acc[3 * f + 0] += go * val[f];
-                    acc[3 * f + 1] += go * d.amp[f] * dr2[f] * (-2.0 * r2s[f]);
-                    acc[3 * f + 2] += go * d.amp[f] * dp1[f];
+                    acc[3 * f + 1] += go * dd.amp[f] * dr2[f] * (-2.0 * r2s[f]);
+                    acc[3 * f + 2] += go * dd.amp[f] * dp1[f];
                 }
             }
         }
@@ -349,7 +395,7 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_vjp_kernel(const __grid_co
         if (lane == 0) red[warp][k] = v;
     }
     __syncthreads();
-    if (tid < 3 * d.nfactors) {
+    if (tid < 3 * dd.nfactors) {
         double v = 0.0;
         for (int w = 0; w < G_THREADS / 32; w++) v += red[w][tid];
         atomicAdd(out + tid, v);
@@ -364,18 +410,27 @@ struct GramTangent {
     double t[3 * LGP_MAX_FACTORS];
 };
 
+template <bool DEV>
 __global__ void __launch_bounds__(G_THREADS) gram_iso_jvp_kernel(const __grid_constant__ GramDesc d,
                                                                  const __grid_constant__ GramTangent tan,
                                                                  const double *__restrict__ x, int64_t ldx, int64_t n,
                                                                  const double *__restrict__ y, int64_t ldy, int64_t m,
-                                                                 double *__restrict__ D, int64_t ldd) {
+                                                                 double *__restrict__ D, int64_t ldd, const double *__restrict__ devpar, const double *__restrict__ devtan) {
+    __shared__ DevDescStore<DEV> sdesc;
+    if constexpr (DEV) load_dev_desc(d, devpar, sdesc.d, threadIdx.x);
+    const GramDesc &dd = [&]() -> const GramDesc & {
+        if constexpr (DEV)
+            return sdesc.d;
+        else
+            return d;
+    }();
     extern __shared__ __align__(16) double gsm[];
     double *su = gsm;
-    double *sv = gsm + (size_t)d.nslots * GT;
+    double *sv = gsm + (size_t)dd.nslots * GT;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int64_t i0 = (int64_t)blockIdx.y * GT, j0 = (int64_t)blockIdx.x * GT;
-    stage_points(d, su, x, ldx, n, i0, false, tid);
-    stage_points(d, sv, y, ldy, m, j0, true, tid);
+    stage_points(dd, su, x, ldx, n, i0, false, tid);
+    stage_points(dd, sv, y, ldy, m, j0, true, tid);
     __syncthreads();
 #pragma unroll 1
     for (int a = 0; a < 4; a++) {
@@ -389,20 +444,22 @@ __global__ void __launch_bounds__(G_THREADS) gram_iso_jvp_kernel(const __grid_co
             double total = 0.0;
             // walk the terms: value of the term P = prod_f amp_f v_f, derivative sum_f (dlog-free product rule)
             int f = 0;
-            while (f < d.nfactors) {
-                const int term = d.term[f];
+            while (f < dd.nfactors) {
+                const int term = dd.term[f];
                 double prod = 1.0;   // product of amp_h * val_h over the factors seen so far
                 double dsum = 0.0;   // derivative of that product along the tangent
-                for (; f < d.nfactors && d.term[f] == term; f++) {
+                for (; f < dd.nfactors && dd.term[f] == term; f++) {
                     double r2 = 0.0;
-                    for (int s = d.slot0[f]; s < d.slot0[f] + d.nslot[f]; s++) {
+                    for (int s = dd.slot0[f]; s < dd.slot0[f] + dd.nslot[f]; s++) {
                         const double df = su[s * GT + ty + 16 * a] - sv[s * GT + cc];
                         r2 += df * df;
                     }
                     double val, dr2, dp1;
-                    core_derivs(d, f, r2, val, dr2, dp1);
-                    const double v = d.amp[f] * val;
-                    const double dv = tan.t[3 * f] * val + d.amp[f] * (tan.t[3 * f + 1] * dr2 * (-2.0 * r2) + tan.t[3 * f + 2] * dp1);
+                    core_derivs(dd, f, r2, val, dr2, dp1);
+                    const double v = dd.amp[f] * val;
+                    const double t0 = DEV ? devtan[3 * f] : tan.t[3 * f], t1 = DEV ? devtan[3 * f + 1] : tan.t[3 * f + 1],
+                                 t2 = DEV ? devtan[3 * f + 2] : tan.t[3 * f + 2];
+                    const double dv = t0 * val + dd.amp[f] * (t1 * dr2 * (-2.0 * r2) + t2 * dp1);
                     dsum = dsum * v + prod * dv;
                     prod *= v;
                 }
@@ -1377,6 +1434,92 @@ __global__ void zero_kernel(double *p, int n) {
     if (i < n) p[i] = 0.0;
 }
 
+
+// ---- launchers of the general kernels: numeric descriptor fields from the host struct (devpar == nullptr) or from
+// device memory (the *_dev entry points)
+template <class F>
+static int general_smem_attr(F kernel, size_t smem) {
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return LGP_ERR_CUDA;
+    return LGP_OK;
+}
+
+static int gram_general(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *devpar,
+                        const double *x, int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, double *K_out,
+                        int64_t ldk) {
+    GramDesc d;
+    int rc = build_desc(factors, nfactors, ndim, d);
+    if (rc) return rc;
+    const size_t smem = (size_t)2 * d.nslots * GT * sizeof(double);
+    dim3 grid((unsigned)((m + GT - 1) / GT), (unsigned)((n + GT - 1) / GT));
+    if (grid.y > 65535) return LGP_ERR_UNSUPPORTED;
+    const int vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K_out) & 15) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (devpar) {
+        if (general_smem_attr(gram_iso_kernel<true>, smem)) return LGP_ERR_CUDA;
+        gram_iso_kernel<true><<<grid, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, K_out, ldk, vec_ok, devpar);
+    } else {
+        if (general_smem_attr(gram_iso_kernel<false>, smem)) return LGP_ERR_CUDA;
+        gram_iso_kernel<false><<<grid, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, K_out, ldk, vec_ok, nullptr);
+    }
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+static int vjp_general(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *devpar,
+                       const double *x, int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, const double *G,
+                       int64_t ldg, const double *b, int symlower, double *out) {
+    GramDesc d;
+    int rc = build_desc(factors, nfactors, ndim, d);
+    if (rc) return rc;
+    const size_t smem = (size_t)2 * d.nslots * GT * sizeof(double);
+    cudaStream_t st = (cudaStream_t)stream;
+    zero_kernel<<<1, 32, 0, st>>>(out, 3 * nfactors);
+    LGP_CUDA_CHECK_LAUNCH();
+    const int64_t tm = (n + GT - 1) / GT, tn = (m + GT - 1) / GT;
+    const int64_t nblk = symlower ? tm * (tm + 1) / 2 : tm * tn;
+    if (nblk > 2147483647LL) return LGP_ERR_UNSUPPORTED;
+    if (devpar) {
+        if (general_smem_attr(gram_iso_vjp_kernel<true>, smem)) return LGP_ERR_CUDA;
+        gram_iso_vjp_kernel<true><<<(unsigned)nblk, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, G, ldg, b, symlower,
+                                                                           (int)tn, out, devpar);
+    } else {
+        if (general_smem_attr(gram_iso_vjp_kernel<false>, smem)) return LGP_ERR_CUDA;
+        gram_iso_vjp_kernel<false><<<(unsigned)nblk, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, G, ldg, b, symlower,
+                                                                            (int)tn, out, nullptr);
+    }
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+static int jvp_general(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *devpar,
+                       const double *tangent_host, const double *tangent_dev, const double *x, int64_t ldx, int64_t n,
+                       const double *y, int64_t ldy, int64_t m, double *D_out, int64_t ldd) {
+    GramDesc d;
+    int rc = build_desc(factors, nfactors, ndim, d);
+    if (rc) return rc;
+    GramTangent tan;
+    memset(&tan, 0, sizeof(tan));
+    if (tangent_host)
+        for (int i = 0; i < 3 * nfactors; i++) tan.t[i] = tangent_host[i];
+    const size_t smem = (size_t)2 * d.nslots * GT * sizeof(double);
+    dim3 grid((unsigned)((m + GT - 1) / GT), (unsigned)((n + GT - 1) / GT));
+    if (grid.y > 65535) return LGP_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (devpar) {
+        if (general_smem_attr(gram_iso_jvp_kernel<true>, smem)) return LGP_ERR_CUDA;
+        gram_iso_jvp_kernel<true><<<grid, G_THREADS, smem, st>>>(d, tan, x, ldx, n, y, ldy, m, D_out, ldd, devpar,
+                                                                 tangent_dev);
+    } else {
+        if (general_smem_attr(gram_iso_jvp_kernel<false>, smem)) return LGP_ERR_CUDA;
+        gram_iso_jvp_kernel<false><<<grid, G_THREADS, smem, st>>>(d, tan, x, ldx, n, y, ldy, m, D_out, ldd, nullptr,
+                                                                  nullptr);
+    }
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
 }  // namespace lgp
 
 using namespace lgp;
@@ -1416,21 +1559,18 @@ int lgp_gram_iso(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors,
             return launch_fast<LGP_K_CAUCHY>(st, fd, x, ldx, n, y, ldy, m, K_out, ldk, sym);
         }
     }
-    GramDesc d;
-    int rc = build_desc(factors, nfactors, ndim, d);
-    if (rc) return rc;
-    size_t smem = (size_t)2 * d.nslots * GT * sizeof(double);
-    if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(gram_iso_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
-            return LGP_ERR_CUDA;
-    }
-    dim3 grid((unsigned)((m + GT - 1) / GT), (unsigned)((n + GT - 1) / GT));
-    if (grid.y > 65535) return LGP_ERR_UNSUPPORTED;
-    int vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K_out) & 15) == 0);
-    gram_iso_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(d, x, ldx, n, y, ldy, m, K_out, ldk, vec_ok);
-    LGP_CUDA_CHECK_LAUNCH();
-    return LGP_OK;
+    return gram_general(stream, factors, nfactors, ndim, nullptr, x, ldx, n, y, ldy, m, K_out, ldk);
+}
+
+int lgp_gram_iso_dev(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *devpar,
+                     const double *x, int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, double *K_out,
+                     int64_t ldk, int flags) {
+    (void)flags;
+    if (!factors || !devpar || !K_out || n < 0 || m < 0) return LGP_ERR_BADARG;
+    if (n == 0 || m == 0) return LGP_OK;
+    if (ndim > 0 && (!x || !y)) return LGP_ERR_BADARG;
+    if (ldk < m) return LGP_ERR_BADARG;
+    return gram_general(stream, factors, nfactors, ndim, devpar, x, ldx, n, y, ldy, m, K_out, ldk);
 }
 
 int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
@@ -1481,48 +1621,29 @@ int lgp_gram_iso_vjp(lgp_stream_t stream, const lgp_factor_t *factors, int nfact
             return LGP_OK;
         }
     }
-    GramDesc d;
-    int rc = build_desc(factors, nfactors, ndim, d);
-    if (rc) return rc;
-    size_t smem = (size_t)2 * d.nslots * GT * sizeof(double);
-    if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(gram_iso_vjp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
-            return LGP_ERR_CUDA;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    zero_kernel<<<1, 32, 0, st>>>(out, 3 * nfactors);
-    LGP_CUDA_CHECK_LAUNCH();
-    int64_t tm = (n + GT - 1) / GT, tn = (m + GT - 1) / GT;
-    int64_t nblk = symlower ? tm * (tm + 1) / 2 : tm * tn;
-    if (nblk > 2147483647LL) return LGP_ERR_UNSUPPORTED;
-    gram_iso_vjp_kernel<<<(unsigned)nblk, G_THREADS, smem, st>>>(d, x, ldx, n, y, ldy, m, G, ldg, b, symlower, (int)tn,
-                                                                 out);
-    LGP_CUDA_CHECK_LAUNCH();
-    return LGP_OK;
+    return vjp_general(stream, factors, nfactors, ndim, nullptr, x, ldx, n, y, ldy, m, G, ldg, b, symlower, out);
+}
+
+int lgp_gram_iso_vjp_dev(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *devpar,
+                         const double *x, int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m,
+                         const double *G, int64_t ldg, const double *b, int symlower, double *out) {
+    if (!factors || !devpar || !G || !out || n < 1 || m < 1) return LGP_ERR_BADARG;
+    if (symlower && (n != m)) return LGP_ERR_BADARG;
+    return vjp_general(stream, factors, nfactors, ndim, devpar, x, ldx, n, y, ldy, m, G, ldg, b, symlower, out);
 }
 
 int lgp_gram_iso_jvp(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
                      int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m, const double *tangent,
                      double *D_out, int64_t ldd) {
     if (!factors || !tangent || !D_out || n < 1 || m < 1 || ldd < m) return LGP_ERR_BADARG;
-    GramDesc d;
-    int rc = build_desc(factors, nfactors, ndim, d);
-    if (rc) return rc;
-    GramTangent tan;
-    memset(&tan, 0, sizeof(tan));
-    for (int i = 0; i < 3 * nfactors; i++) tan.t[i] = tangent[i];
-    size_t smem = (size_t)2 * d.nslots * GT * sizeof(double);
-    if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(gram_iso_jvp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
-            return LGP_ERR_CUDA;
-    }
-    dim3 grid((unsigned)((m + GT - 1) / GT), (unsigned)((n + GT - 1) / GT));
-    if (grid.y > 65535) return LGP_ERR_UNSUPPORTED;
-    gram_iso_jvp_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(d, tan, x, ldx, n, y, ldy, m, D_out, ldd);
-    LGP_CUDA_CHECK_LAUNCH();
-    return LGP_OK;
+    return jvp_general(stream, factors, nfactors, ndim, nullptr, tangent, nullptr, x, ldx, n, y, ldy, m, D_out, ldd);
+}
+
+int lgp_gram_iso_jvp_dev(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *devpar,
+                         const double *x, int64_t ldx, int64_t n, const double *y, int64_t ldy, int64_t m,
+                         const double *tangent_dev, double *D_out, int64_t ldd) {
+    if (!factors || !devpar || !tangent_dev || !D_out || n < 1 || m < 1 || ldd < m) return LGP_ERR_BADARG;
+    return jvp_general(stream, factors, nfactors, ndim, devpar, nullptr, tangent_dev, x, ldx, n, y, ldy, m, D_out, ldd);
 }
 
 int lgp_frob_dot(lgp_stream_t stream, const double *A, int64_t lda, const double *B, int64_t ldb, int64_t rows,

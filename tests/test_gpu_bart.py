@@ -30,7 +30,7 @@ def _dev_idx(idx):
 
 @pytest.mark.parametrize('kw', [dict(maxd=3, reset=[1]), dict(maxd=6, reset=[1, 2, 4]),
                                 dict(maxd=7, reset=[2, 3, 5], intercept=False, gamma=0.4),
-                                dict(maxd=5, reset=[2], weights=np.r_[1., 0., 2., 0.5, 1., 3.]),
+                                dict(maxd=4, reset=[2], weights=np.r_[1., 0., 2., 0.5, 1., 3.]),
                                 dict(maxd=10, reset=[2, 4, 6, 8])])
 def test_chained_stages_and_symmetry_vs_oracle(kw):
     X, splits, idx = _data(333)
@@ -161,7 +161,7 @@ def test_bayestree_bart_fit_vs_oracle():
     assert fit.meansdev[0] == pytest.approx(ksm / ko, rel=1e-12) and fit.sigma[0] == pytest.approx(np.sqrt(s2o), rel=1e-12)
     m, c = fit.pred()
     Kf = (ksm / ko) ** 2 * obart.gram(splits[0], idx, idx, alpha=ao, beta=bo, maxd=10, reset=[2, 4, 6, 8])
-    m_o, c_o = ogp.pred(Kf + s2o * np.eye(n) + ksm ** 2, Kf + ksm ** 2, Kf + ksm ** 2, y - mu_mu, epsrel=0)
+    m_o, c_o = ogp.pred(Kf + s2o * np.eye(n) + ksm ** 2, Kf, Kf, y - mu_mu, epsrel=0)   # 'trainmean': the latent f only
     np.testing.assert_allclose(m, m_o + mu_mu, rtol=1e-8, atol=1e-9)
     Xt = rng.standard_normal((40, p))
     mt, ct = fit.pred(x_test=Xt, error=True)

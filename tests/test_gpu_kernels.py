@@ -315,3 +315,43 @@ def test_gram_rational_quadratic_fast_path(beta):
     K1 = _ops.gram_iso(descs[:1], xd, xd, symmetric=True)
     K2 = _ops.gram_iso(descs[:1], xd, xd, symmetric=True, flags=_lib.GRAM_LIBM) if hasattr(_lib, 'GRAM_LIBM') else K1
     assert float(((K1 - K2).abs() / K2).max()) < 1e-13
+
+
+def test_device_resident_descriptor_entry_points():
+    """ lgp_gram_iso_dev / _vjp_dev / _jvp_dev (the entry points an XLA-FFI handler binds: hyperparameters in device
+    memory, structure as host attributes) give the results of the host-descriptor entry points for the same numbers """
+    rng = np.random.default_rng(31)
+    n, m = 300, 170
+    x = torch.tensor(rng.uniform(0, 5, (3, n)), device='cuda')
+    y = torch.tensor(rng.uniform(0, 5, (3, m)), device='cuda')
+    descs = [dict(kind=_lib.K_MATERNP, term=0, dimmask=7, ipar=2, par0=0.0, scale_x=1.3, scale_y=1.3, amp=1.7),
+             dict(kind=_lib.K_EXPQUAD, term=0, dimmask=3, scale_x=2.1, scale_y=2.1, loc_x=0.3, loc_y=0.3, amp=1.0),
+             dict(kind=_lib.K_CAUCHY, term=1, dimmask=4, par0=2.0, par1=1.5, scale_x=0.8, scale_y=0.8, amp=0.6),
+             dict(kind=_lib.K_WHITE, term=2, dimmask=7, amp=0.01)]
+    devpar = _ops.devpar_of(descs, 'cuda')
+    K_host = _ops.gram_iso(descs, x, y, flags=_lib.GRAM_GENERAL)
+    K_dev = _ops.gram_iso_dev(descs, devpar, x, y)
+    assert torch.equal(K_dev, K_host)
+    # changing the device parameters changes the result without touching the host descriptor
+    descs2 = [dict(d) for d in descs]
+    descs2[0]['scale_x'] = descs2[0]['scale_y'] = 0.9
+    descs2[3]['amp'] = 0.05
+    K_dev2 = _ops.gram_iso_dev(descs, _ops.devpar_of(descs2, 'cuda'), x, y)
+    assert torch.equal(K_dev2, _ops.gram_iso(descs2, x, y, flags=_lib.GRAM_GENERAL))
+    G = torch.tensor(rng.standard_normal((n, m)), device='cuda')
+    v_host = _ops.gram_iso_vjp_general(descs, x, y, G)
+    v_dev = _ops.gram_iso_vjp_dev(descs, devpar, x, y, G)
+    np.testing.assert_allclose(v_dev.cpu().numpy(), v_host.cpu().numpy(), rtol=1e-12, atol=1e-12)
+    tan = rng.standard_normal((len(descs), 3))
+    D_host = _ops.gram_iso_jvp(descs, x, y, tan)
+    D_dev = _ops.gram_iso_jvp_dev(descs, devpar, x, y, torch.tensor(tan, device='cuda'))
+    np.testing.assert_allclose(D_dev.cpu().numpy(), D_host.cpu().numpy(), rtol=1e-13, atol=1e-14)
+    # symmetric lower-triangle form with the rank-one term
+    A = torch.tensor(rng.standard_normal((n, n)), device='cuda')
+    Gs = _ops.as_aligned(A + A.T)
+    b = torch.tensor(rng.standard_normal(n), device='cuda')
+    sym_descs = [descs[0], descs[3]]
+    sp = _ops.devpar_of(sym_descs, 'cuda')
+    vs = _ops.gram_iso_vjp_dev(sym_descs, sp, x, x, Gs, b=b, symlower=True).cpu().numpy()
+    vh = _ops.gram_iso_vjp(sym_descs, x, Gs, b).cpu().numpy()
+    np.testing.assert_allclose(vs, vh, rtol=1e-10, atol=1e-10 * np.abs(vh).max())
