@@ -61,3 +61,17 @@ def test_product_does_not_import_oracle():
         assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
     for f in (ROOT / 'lsqfitgp_b200' / 'csrc').glob('*.cu*'):
         assert 'oracle' not in f.read_text(), f
+
+
+def test_xla_ffi_shim_binds_only_declared_entry_points():
+    """ the (untested, jax-less) XLA-FFI shim forwards to C-ABI entry points: every lgp_* function it calls must be
+    declared in the header and exported by the library, and the JAX-side module must name exactly the handlers the shim
+    defines """
+    from lsqfitgp_b200 import _lib
+    shim = (ROOT / 'lsqfitgp_b200' / 'csrc' / 'xla_ffi_shim.cc').read_text()
+    called = set(re.findall(r'\b(lgp_(?!xla_)\w+)\s*\(', shim))
+    assert called and called <= set(_lib.SIGNATURES), called - set(_lib.SIGNATURES)
+    handlers = set(re.findall(r'XLA_FFI_DEFINE_HANDLER_SYMBOL\((lgp_xla_\w+),', shim))
+    py = (ROOT / 'lsqfitgp_b200' / '_jaxffi.py').read_text()
+    named = set(re.findall(r"'(lgp_xla_\w+)'", py))
+    assert handlers == named, handlers ^ named
