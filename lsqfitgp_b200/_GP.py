@@ -224,23 +224,17 @@ class _FusedNegLogMLFn(torch.autograd.Function):
     def forward(ctx, kern, xd, labels, r, kw, *params):
         K = kern._gram_device(xd, xd, labels, symmetric=True)
         _timing.mark('gp&cov')
-        dec = _linalg.Chol(K, **kw)
-        _timing.mark('decomp')
-        del K
-        ctx.low = ctx.side = None
         if any(ctx.needs_input_grad[5:]):
-            # the gradient will need K^-1: start TRTRI + LAUUM on a side stream right behind the factorisation, so that the
-            # latency-bound triangular solves below (and whatever the caller does before backward) overlap its GEMMs
+            # the gradient will need K^-1: factorisation and inverse-from-factor in ONE overlapped library call, the
+            # inverse on a persistent side stream: its leading half starts while the panel-chain-bound tail of the
+            # factorisation leaves SMs idle, and the latency-bound triangular solves below overlap its GEMMs
             main = torch.cuda.current_stream()
             side = _side_stream_for(main)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                ctx.low = dec.inverse_lower()
-            # the factor buffers belong to the main stream's allocator pool but are read by the side stream: keep the
-            # allocator from handing them out again (e.g. if backward never runs) before the side stream is done
-            dec._st.W.record_stream(side)
-            dec._st.aux.record_stream(side)
-            ctx.side = side
+            dec = _linalg.Chol(K, _inverse_stream=side, **kw)
+        else:
+            dec = _linalg.Chol(K, **kw)
+        _timing.mark('decomp')
+        del K
         ldq, a = dec.logdet_quad(r)
         ctx.kern, ctx.xd, ctx.labels, ctx.dec, ctx.a = kern, xd, labels, dec, a
         half = torch.tensor(0.5, dtype=f64, device=xd.device)
@@ -254,17 +248,11 @@ class _FusedNegLogMLFn(torch.autograd.Function):
         hyper = kern._hyperparams()
         grads = []
         if hyper:
-            if ctx.low is not None:
-                low = ctx.low
-                cur = torch.cuda.current_stream()
-                cur.wait_stream(ctx.side)
-                low.record_stream(cur)   # allocated on the side stream's pool, read here
-                ctx.low = None
-            else:
-                low = dec.inverse_lower()
+            low = dec.inverse_lower()   # joins the side stream if the inverse was started in forward
             descs, index = kern._descriptor(labels)
             vjp = (0.5 * _ops.gram_iso_vjp(descs, xd, low, b)).cpu()
             del low
+            dec._low = None   # 8 n^2 bytes: not needed again
             pos = {tf: i for i, tf in enumerate(index)}
             gc = g.cpu()
             for kind, ti, fi, tensor in hyper:

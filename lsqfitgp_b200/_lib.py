@@ -99,6 +99,8 @@ SIGNATURES = {
     'lgp_chol_npad': (_i64, [_i64]),
     'lgp_chol_aux_doubles': (_i64, [_i64]),
     'lgp_chol_factor': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, _i64, _vp, _vp]),
+    'lgp_chol_factor_inverse': (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, _i64, _vp, _vp, _vp, _vp,
+                                       _i64]),
     'lgp_chol_solve': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _int]),
     'lgp_chol_mult': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _int]),
     'lgp_chol_get_factor': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64]),

@@ -143,7 +143,7 @@ class Chol(Decomposition):
     factor is not finite, like the reference does outside jit.
     """
 
-    def __init__(self, K, *, epsrel='auto', epsabs=0, _addmat=None, _adddiag=None, _check=True):
+    def __init__(self, K, *, epsrel='auto', epsabs=0, _addmat=None, _adddiag=None, _check=True, _inverse_stream=None):
         Kd, self._torch_in = _todev(K)
         if Kd.ndim != 2 or Kd.shape[0] != Kd.shape[1] or Kd.shape[0] < 1:
             raise ValueError(f'matrix must be square and non-empty, found shape {tuple(Kd.shape)}')
@@ -151,7 +151,15 @@ class Chol(Decomposition):
         self._Kd = Kd
         self._addmat = _addmat
         self._adddiag = _adddiag
-        self._st = _ops.chol_factor(Kd, addmat=_addmat, adddiag=_adddiag, epsrel=epsrel, epsabs=epsabs)
+        self._low = self._low_stream = None
+        if _inverse_stream is not None:
+            # the caller will want (K + eps)^-1 (gradient): factorisation and inverse in one overlapped library call, the
+            # inverse on `_inverse_stream` (lgp_chol_factor_inverse)
+            self._st, self._low = _ops.chol_factor_inverse(Kd, _inverse_stream, addmat=_addmat, adddiag=_adddiag,
+                                                           epsrel=epsrel, epsabs=epsabs)
+            self._low_stream = _inverse_stream
+        else:
+            self._st = _ops.chol_factor(Kd, addmat=_addmat, adddiag=_adddiag, epsrel=epsrel, epsabs=epsabs)
         self._scal = None
         if _check:
             info = int(self._st.info.item())  # device -> host sync, like the eager isfinite check of the reference
@@ -281,6 +289,13 @@ class Chol(Decomposition):
 
     def inverse_lower(self):
         """ device (n, n) view whose lower triangle holds (K + eps)⁻¹ (TRTRI + LAUUM, 2n³/3 flop) """
+        if self._low is not None:
+            # computed alongside the factorisation on another stream: order the current stream behind it
+            cur = torch.cuda.current_stream()
+            if self._low_stream is not None and self._low_stream != cur:
+                cur.wait_stream(self._low_stream)
+                self._low.record_stream(cur)
+            return self._low
         return _ops.chol_inverse(self._st)
 
     def logdet_quad(self, r=None):

@@ -415,6 +415,44 @@ def chol_factor(K, addmat=None, adddiag=None, epsrel='auto', epsabs=0.0):
     return st
 
 
+def chol_factor_inverse(K, side, addmat=None, adddiag=None, epsrel='auto', epsabs=0.0):
+    """ factorisation on the current stream and inverse-from-factor on the torch stream `side`, overlapped inside the
+    library (lgp_chol_factor_inverse).  Returns (FactorState, Kinv view (n, n), lower triangle valid): the factor is
+    ready in current-stream order, Kinv in `side` order (wait for `side` before reading it). """
+    lib = _lib.load()
+    assert K.ndim == 2 and K.shape[0] == K.shape[1] and K.dtype == f64
+    n = K.shape[0]
+    if K.stride(1) != 1:
+        K = K.contiguous()
+    if addmat is not None and addmat.stride(1) != 1:
+        addmat = addmat.contiguous()
+    if adddiag is not None:
+        adddiag = adddiag.contiguous()
+    st = FactorState()
+    st.n = n
+    st.npad = int(lib.lgp_chol_npad(n))
+    st.device = K.device
+    st.W = torch.empty((st.npad, st.npad), dtype=f64, device=K.device)
+    st.aux = torch.empty(int(lib.lgp_chol_aux_doubles(n)), dtype=f64, device=K.device)
+    st.info = torch.empty(1, dtype=torch.int32, device=K.device)
+    main = torch.cuda.current_stream()
+    with torch.cuda.stream(side):   # the inverse buffers come from the side stream's allocator pool (kept warm there)
+        scratch = torch.empty((st.npad, st.npad), dtype=f64, device=K.device)
+        Kinv = torch.empty((st.npad, st.npad), dtype=f64, device=K.device)
+    er = -1.0 if (isinstance(epsrel, str) and epsrel == 'auto') else float(epsrel)
+    ea = 2.220446049250313e-16 if (isinstance(epsabs, str) and epsabs == 'auto') else float(epsabs)
+    check(lib.lgp_chol_factor_inverse(ctypes.c_void_p(main.cuda_stream), ctypes.c_void_p(side.cuda_stream), ptr(K),
+                                      K.stride(0), ptr(addmat), addmat.stride(0) if addmat is not None else 0,
+                                      ptr(adddiag), n, er, ea, ptr(st.W), st.W.stride(0), ptr(st.aux), ptr(st.info),
+                                      ptr(scratch), ptr(Kinv), Kinv.stride(0)), 'lgp_chol_factor_inverse')
+    # buffers of one stream's pool used by the other stream: keep the allocator from recycling them too early
+    for t in (st.W, st.aux, K):
+        t.record_stream(side)
+    scratch.record_stream(side)
+    del scratch
+    return st, Kinv[:n, :n]
+
+
 def chol_solve(st, B, trans, inplace=False):
     """ B: (n, m) device tensor -> L^-1 B (trans=False) or L^-T B (trans=True) """
     lib = _lib.load()

@@ -544,7 +544,18 @@ static cudaStream_t panel_stream(cudaStream_t caller) {
 static inline bool ev_record(cudaEvent_t e, cudaStream_t s) { return e && cudaEventRecord(e, s) == cudaSuccess; }
 static inline bool ev_wait(cudaStream_t s, cudaEvent_t e) { return e && cudaStreamWaitEvent(s, e, 0) == cudaSuccess; }
 
-static int potrf_lookahead(CholCtx &cm, int nblk, int pb) {
+// Optional hook of the factorisation loop: called once, on the host, right after the panel that makes the leading
+// `blocks` block columns of the factor final (all rows) has been enqueued; `panel_done` is the event recorded behind that
+// panel on the panel stream.  lgp_chol_factor_inverse uses it to start the inverse of the leading half while the
+// factorisation's tail (bound by the panel chain, SMs mostly idle) is still running.
+struct PanelHook {
+    int blocks;
+    void (*fn)(void *ctx, cudaEvent_t panel_done);
+    void *ctx;
+    bool fired;
+};
+
+static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = nullptr) {
     cudaStream_t ps = (nblk > pb) ? panel_stream(cm.st) : nullptr;
     if (!ps) {
         potrf_rec(cm, 0, nblk);
@@ -584,6 +595,10 @@ static int potrf_lookahead(CholCtx &cm, int nblk, int pb) {
         e_last = e_panel;
         last = j;
         if ((rc = cp.rc) != LGP_OK || rest == 0 || !ok) break;
+        if (hook && !hook->fired && jb + w >= hook->blocks) {
+            hook->fired = true;
+            hook->fn(hook->ctx, e_panel);
+        }
         // ---- main stream
         ok = ok && ev_wait(cm.st, e_panel);
         const int w2 = rest < pb ? rest : pb;
@@ -1091,6 +1106,118 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
         fprintf(stderr, "[lgp trace] inverse: trtri %.3f ms, lauum+scale %.3f ms\n", a, b);
         cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
     }
+    return LGP_OK;
+}
+
+// ---- factorisation and inverse-from-factor in one call, overlapped
+namespace lgp {
+struct EarlyInv {
+    InvCtx c;      // on the inverse stream
+    int nb, n1;    // blocks of the padded matrix, blocks of the leading half
+    bool ok;
+};
+// X11 = Lt11^-1 and Tt = X11^T L21^T: everything of the inverse that only needs the leading n1 block columns of the factor
+static void inverse_early(EarlyInv &e) {
+    InvCtx &c = e.c;
+    const int n1 = e.n1, n2 = e.nb - e.n1;
+    trtri_rec(c, 0, n1, 1, 2);
+    if (c.rc) return;
+    const double *L21 = c.W + (int64_t)n1 * NB * c.ldw;
+    double *Tt = c.X + (int64_t)n1 * NB;  // n1 x n2 scratch (upper block)
+    RC(gemm_launch(c.st, false, true, n1 * NB, n2 * NB, n1 * NB, 1.0, c.X, c.ldx, L21, c.ldw, Tt, c.ldx,
+                   GEMM_BETA0 | GEMM_A_UPPER_K));
+}
+static void inverse_early_hook(void *ctx, cudaEvent_t panel_done) {
+    EarlyInv &e = *static_cast<EarlyInv *>(ctx);
+    if (!ev_wait(e.c.st, panel_done)) {
+        e.ok = false;  // could not order the inverse stream behind the panel: the early part runs later instead
+        return;
+    }
+    inverse_early(e);
+    e.ok = true;
+}
+}  // namespace lgp
+
+int lgp_chol_factor_inverse(lgp_stream_t stream, lgp_stream_t inv_stream, const double *K, int64_t ldk,
+                            const double *addmat, int64_t ldadd, const double *adddiag, int64_t n64, double epsrel,
+                            double epsabs, double *W, int64_t ldw, double *aux, int32_t *info, double *scratch,
+                            double *Kinv, int64_t ldkinv) {
+    if (n64 < 1 || n64 > (1 << 30) || !K || !W || !aux || !info || !scratch || !Kinv) return LGP_ERR_BADARG;
+    const int n = (int)n64, npad = (int)lgp_chol_npad(n);
+    if (ldw < npad || ldk < n || (addmat && ldadd < n) || ldkinv < npad) return LGP_ERR_BADARG;
+    if ((ldw & 1) || (ldkinv & 1) || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(aux) & 15) ||
+        (reinterpret_cast<uintptr_t>(Kinv) & 15) || (reinterpret_cast<uintptr_t>(scratch) & 15))
+        return LGP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream, si = (cudaStream_t)inv_stream;
+    if (leaf_attr()) return LGP_ERR_CUDA;
+    if (epsrel < 0) epsrel = (double)n * 2.220446049250313e-16;
+    // the inverse stream starts behind whatever the caller has enqueued on the main stream (buffer reuse)
+    if (si != st) {
+        cudaEvent_t e0 = ring_event();
+        if (!(ev_record(e0, st) && ev_wait(si, e0))) return LGP_ERR_CUDA;
+    }
+    chol_diag_scale_kernel<<<(npad + 255) / 256, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, aux);
+    LGP_CUDA_CHECK_LAUNCH();
+    chol_prepare_kernel<<<(npad + 7) / 8, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, W, ldw, aux);
+    LGP_CUDA_CHECK_LAUNCH();
+    chol_jitter_kernel<<<1, 1024, 0, st>>>(n, npad, epsrel, epsabs, W, ldw, aux, info);
+    LGP_CUDA_CHECK_LAUNCH();
+    CholCtx c{st, W, ldw, aux + LGP_AUX_INVDIAG(npad), aux + LGP_AUX_DIAG(npad), info, LGP_OK};
+    const int nb = npad / NB;
+    EarlyInv early{InvCtx{si, W, ldw, aux + LGP_AUX_INVDIAG(npad), scratch, (int64_t)npad, LGP_OK}, nb, nb / 2, false};
+    PanelHook hook{early.n1, inverse_early_hook, &early, false};
+    // Early start of the inverse behind the half-way panel: OFF by default.  Measured on B200 at n = 20000 (round 2): the
+    // span of factorisation + inverse is unchanged (248.1 ms against 248.4 ms sequential) because the small, dependent
+    // kernels of the panel chain cannot get SM slots while long-K inverse GEMM CTAs saturate the GPU (the 128 x 128 leaf
+    // needs most of an SM's registers and shared memory, and freed single slots are back-filled by pending GEMM CTAs):
+    // the factorisation's tail stretches by exactly what the inverse gains.  Kept behind LGP_EARLY_INVERSE=1 for
+    // experiments; the call is otherwise the sequential composition on two streams.
+    static const bool early_on = [] {
+        const char *e = getenv("LGP_EARLY_INVERSE");
+        return e && e[0] == '1';
+    }();
+    const bool overlap = early_on && si != st && nb >= 8 * panel_blocks();
+    {
+        int rc = potrf_lookahead(c, nb, panel_blocks(), overlap ? &hook : nullptr);
+        if (rc) return rc;
+    }
+    finalize_info_kernel<<<1, 1, 0, st>>>(info, n);
+    LGP_CUDA_CHECK_LAUNCH();
+    logdet_quad_kernel<<<1, 1024, 0, st>>>(aux + LGP_AUX_DIAG(npad), aux + LGP_AUX_S(npad), nullptr, n,
+                                           aux + LGP_AUX_SCALARS(npad) + 4);
+    LGP_CUDA_CHECK_LAUNCH();
+    if (early.c.rc) return early.c.rc;
+    // ---- the rest of the inverse, behind the complete factor
+    if (si != st) {
+        cudaEvent_t e1 = ring_event();
+        if (!(ev_record(e1, st) && ev_wait(si, e1))) {
+            cudaStreamSynchronize(st);  // ordering could not be enqueued: fall back to a host-side join
+        }
+    }
+    InvCtx &ci = early.c;
+    if (nb == 1) {
+        trtri_rec(ci, 0, 1);
+    } else {
+        const int n1 = early.n1, n2 = nb - n1;
+        if (!(hook.fired && early.ok)) inverse_early(early);
+        if (ci.rc) return ci.rc;
+        trtri_rec(ci, n1, n2, 1, 3);
+        if (ci.rc) return ci.rc;
+        double *X22 = scratch + (int64_t)n1 * NB * npad + (int64_t)n1 * NB;
+        double *X21 = scratch + (int64_t)n1 * NB * npad;
+        double *Tt = scratch + (int64_t)n1 * NB;
+        // X21[i][j] = - sum_k X22[i][k] * Tt[j][k]  (k <= i)
+        int rc = gemm_launch(si, true, true, n2 * NB, n1 * NB, n2 * NB, -1.0, X22, npad, Tt, npad, X21, npad,
+                             GEMM_BETA0 | GEMM_A_LOWER_K);
+        if (rc) return rc;
+    }
+    if (ci.rc) return ci.rc;
+    int rc = gemm_launch(si, false, false, npad, npad, npad, 1.0, scratch, npad, scratch, npad, Kinv, ldkinv,
+                         GEMM_BETA0 | GEMM_LOWER | GEMM_A_UPPER_K);
+    if (rc) return rc;
+    dim3 g = rows_grid(n, n);
+    sym_scale_lower_kernel<<<g, 256, 0, si>>>(Kinv, ldkinv, n, aux + LGP_AUX_SINV(npad));
+    LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
 }
 

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "fastmath.cuh"
 #include "bessel_k.cuh"
+#include "internal.h"
 
 namespace lgp {
 
@@ -930,7 +931,8 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
 template <int KIND, int P, int MINB>
 __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __grid_constant__ FastDesc d,
                                                                   const double *__restrict__ x, int64_t ldx, int64_t n,
-                                                                  double *__restrict__ K, int64_t ldk, int vec_ok) {
+                                                                  double *__restrict__ K, int64_t ldk, int vec_ok,
+                                                                  long long ntiles) {
     extern __shared__ __align__(16) double fsm[];
     const int nd = d.nd;
     ExpTab *tab = reinterpret_cast<ExpTab *>(fsm);
@@ -940,14 +942,20 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
     double *D = rv + (d.white_raw ? nd * FT : 0);  // D[row][col], stride F2_TS
     double *T = D + FT * F2_TS;                    // T[col][row]
     const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
-    long long b = blockIdx.x;
+    if (tid < 64) tab[tid] = EXP_TAB_DEV[tid];
+    if (KIND == LGP_K_CAUCHY && tid >= 64 && tid < 128) reinterpret_cast<LogTab *>(fsm + 128)[tid - 64] = LOG_TAB_DEV[tid - 64];
+    // Persistent CTA: tiles b = blockIdx.x, blockIdx.x + gridDim.x, ...  The bulk stores of a tile are NOT waited for
+    // where they are issued: they drain while the points of the next tile are loaded and the first half of its entries
+    // is computed; the wait sits right before the staging buffers are written again.
+    bool pending = false;  // this thread has a committed bulk-store group that may still be reading D / T
+#pragma unroll 1
+    for (long long b = blockIdx.x; b < ntiles; b += gridDim.x) {
     int tm = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);  // single precision + exact integer fix-up
     while ((long long)(tm + 1) * (tm + 2) / 2 <= b) tm++;
     while ((long long)tm * (tm + 1) / 2 > b) tm--;
     const int tn = (int)(b - (long long)tm * (tm + 1) / 2);
     const int64_t i0 = (int64_t)tm * FT, j0 = (int64_t)tn * FT;
-    if (tid < 64) tab[tid] = EXP_TAB_DEV[tid];
-    if (KIND == LGP_K_CAUCHY && tid >= 64 && tid < 128) reinterpret_cast<LogTab *>(fsm + 128)[tid - 64] = LOG_TAB_DEV[tid - 64];
+    __syncthreads();  // everybody is done with the staged points (and the non-bulk reads of T) of the previous tile
     for (int idx = tid; idx < nd * FT; idx += G_THREADS) {
         const int s = idx / FT, r = idx % FT;
         const int64_t i = i0 + r, j = j0 + r;
@@ -1025,6 +1033,14 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
 #pragma unroll
                 for (int c = 0; c < 4; c++) val[a][c] = __dadd_rn(val[a][c], d.amp_const);
         }
+        if (a0 == 0) {
+            // D / T of the previous tile may still be read by its bulk stores: the issuing threads wait, then everybody
+            if (pending) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                pending = false;
+            }
+            __syncthreads();
+        }
         if (interior) {
 #pragma unroll
             for (int a = 0; a < 2; a++) {
@@ -1065,7 +1081,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(FT * 8)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            pending = true;
         }
     } else if (mirror) {
         __syncthreads();
@@ -1081,6 +1097,9 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
             }
         }
     }
+    }  // tile loop
+    // shared memory must stay valid until the last bulk stores have read it
+    if (pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // d core / d r2 for the fast path (value returned through `val`)
@@ -1178,6 +1197,22 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_vjp_kernel(const __gri
     while ((long long)tm * (tm + 1) / 2 > b) tm--;
     const int tn = (int)(b - (long long)tm * (tm + 1) / 2);
     const int64_t i0 = (int64_t)tm * FT, j0 = (int64_t)tn * FT;
+    // Tiles strictly below the diagonal and fully inside the matrix (almost all of them): the 16 entries of G this thread
+    // needs are requested FIRST, eight independent 16-byte loads in flight per thread while the points are staged and the
+    // squared distances computed (issued one by one next to their use, the loads left the kernel latency-bound: 0.87 TB/s)
+    const bool vec_ok = ((ldg & 1) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0);
+    const bool interior = vec_ok && tm > tn && i0 + FT <= n;
+    double gpre[4][4];
+    if (interior) {
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int bb = 0; bb < 2; bb++) {
+                const double2 t = __ldcs(reinterpret_cast<const double2 *>(G + (i0 + ty + 16 * a) * ldg + j0 + 2 * tx + 32 * bb));
+                gpre[a][2 * bb] = t.x;
+                gpre[a][2 * bb + 1] = t.y;
+            }
+    }
     for (int idx = tid; idx < nd * FT; idx += G_THREADS) {
         const int s = idx / FT, r = idx % FT;
         const int64_t i = i0 + r, j = j0 + r;
@@ -1240,7 +1275,28 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_vjp_kernel(const __gri
         }
     }
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    const bool vec_ok = ((ldg & 1) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0);
+    if (interior) {
+        // straight-line: every entry is valid, off the diagonal (weight 2); no White hits unless points are duplicated
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const double bi = sbi[ty + 16 * a];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int cc = 2 * tx + 32 * (c >> 1) + (c & 1);
+                const double g = 2.0 * (gpre[a][c] - bi * sbj[cc]);
+                double val, dr2, dp1 = 0.0;
+                if (P >= 0 && !fast2_out_of_range<KIND>(r2[a][c], (double)(2 * P + 1), d.par0, false))
+                    fast2_core_derivs<KIND, P>(d, r2[a][c], tab, val, dr2);
+                else
+                    fast_core_derivs<KIND>(d, r2[a][c], val, dr2, dp1);
+                acc[0] += g * val;
+                acc[1] += g * d.amp * dr2 * (-2.0 * r2[a][c]);
+                acc[2] += g * d.amp * dp1;
+                if (d.has_white && eq[a][c]) acc[3] += g;
+                acc[4] += g;
+            }
+        }
+    } else
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         const int64_t i = i0 + ty + 16 * a;
@@ -1412,8 +1468,29 @@ static int launch_fast2(cudaStream_t st, const FastDesc &d, const double *x, int
     if (sym && v3) {
         smem += (size_t)FT * F2_TS * 8;  // second staging tile
         // 3 CTAs per SM (80 registers): measured 0.745 ms against 0.846 ms with 2 CTAs x 126 registers (Matern-5/2, n = 20k)
-        cudaFuncSetAttribute(gram_fast3_kernel<KIND, P, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        gram_fast3_kernel<KIND, P, 3><<<(unsigned)grid, G_THREADS, smem, st>>>(d, x, ldx, n, K, ldk, vec_ok);
+        static DeviceOnce once;
+        static int sm_count[MAX_DEVICES];
+        const int dev = current_device();
+        if (dev < 0) return LGP_ERR_CUDA;
+        if (!once.done(dev)) {
+            if (cudaFuncSetAttribute(gram_fast3_kernel<KIND, P, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 / 3) != cudaSuccess ||
+                cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+                return LGP_ERR_CUDA;
+            once.set(dev);
+        }
+        if (smem > 227 * 1024 / 3) return LGP_ERR_UNSUPPORTED;
+        // one tile per CTA by default; LGP_GRAM_WAVES=k makes the CTAs persistent (k waves of 3 per SM walking the lower-tile
+        // list, bulk stores of a tile draining under the next tile's arithmetic): measured SLOWER on B200 at n = 20000
+        // (Matern-5/2: 0.805 ms with k = 1, 0.796 with k = 2, against 0.740 ms one tile per CTA: the hardware block scheduler
+        // balances the diagonal / edge tiles better than the static stride, and three resident CTAs already overlap the drain)
+        static const int waves = [] {  // A/B switch (experiments only): CTAs per SM-slot; 0 = one tile per CTA
+            const char *e = getenv("LGP_GRAM_WAVES");
+            return e ? atoi(e) : 0;
+        }();
+        const int64_t wave = waves > 0 ? (int64_t)3 * sm_count[dev] * waves : grid;
+        const unsigned g3 = (unsigned)(grid < wave ? grid : wave);
+        gram_fast3_kernel<KIND, P, 3><<<g3, G_THREADS, smem, st>>>(d, x, ldx, n, K, ldk, vec_ok, (long long)grid);
     } else if (sym) {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(gram_fast2_kernel<KIND, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -355,3 +355,35 @@ def test_device_resident_descriptor_entry_points():
     vs = _ops.gram_iso_vjp_dev(sym_descs, sp, x, x, Gs, b=b, symlower=True).cpu().numpy()
     vh = _ops.gram_iso_vjp(sym_descs, x, Gs, b).cpu().numpy()
     np.testing.assert_allclose(vs, vh, rtol=1e-10, atol=1e-10 * np.abs(vh).max())
+
+
+@pytest.mark.parametrize('n', [300, 1500, 5000])
+def test_fused_factor_inverse_matches_separate_calls(n):
+    """ lgp_chol_factor_inverse (factorisation and inverse-from-factor overlapped on two streams, the leading half of the
+    inverse started behind the half-way panel for n >= 4096) gives the factor and inverse of the two separate calls """
+    rng = np.random.default_rng(n)
+    x = torch.tensor(rng.uniform(0, 10, (3, n)), device='cuda')
+    descs = [dict(kind=_lib.K_MATERNP, term=0, dimmask=7, ipar=2, par0=0.0, scale_x=1.5, scale_y=1.5, amp=1.0),
+             dict(kind=_lib.K_WHITE, term=1, dimmask=7, amp=0.01)]
+    K = _ops.gram_iso(descs, x, x, symmetric=True)
+    st0 = _ops.chol_factor(K)
+    inv0 = _ops.chol_inverse(st0)
+    side = torch.cuda.Stream('cuda')
+    for _ in range(2):
+        st1, inv1 = _ops.chol_factor_inverse(K, side)
+        torch.cuda.current_stream().wait_stream(side)
+        assert int(st1.info.item()) == 0
+        assert torch.equal(torch.tril(st1.W[:n, :n]), torch.tril(st0.W[:n, :n]))
+        assert torch.equal(st1.aux[:3 * st1.npad + 8], st0.aux[:3 * st0.npad + 8])
+        assert torch.equal(torch.tril(inv1), torch.tril(inv0))
+    # same stream for both: plain sequential composition
+    st2, inv2 = _ops.chol_factor_inverse(K, torch.cuda.current_stream())
+    assert torch.equal(torch.tril(inv2), torch.tril(inv0))
+    # an independent check of the inverse itself
+    Kr = K.clone()
+    eps = float(st0.scalars()[1].item())
+    s = st0.aux[:n]
+    Kr.diagonal().add_(eps * s * s)
+    full = torch.tril(inv0) + torch.tril(inv0, -1).T
+    resid = (full @ Kr - torch.eye(n, dtype=torch.float64, device='cuda')).abs().max().item()
+    assert resid < 1e-7
