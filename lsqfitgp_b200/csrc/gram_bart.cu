@@ -17,7 +17,8 @@
 namespace lgp {
 
 constexpr int BT = 64;           // CTA tile
-constexpr int B_THREADS = 256;   // 16 x 16 threads, 4 x 4 pairs each
+constexpr int B_THREADS = 512;   // 16 x 32 threads, 2 (rows ty, ty + 32) x 4 (columns 2tx + 32b + {0,1}) pairs each
+constexpr int B_RA = 2;           // rows per thread
 constexpr int B_MAX_P = 64;
 constexpr int B_MAX_ROWS = LGP_BART_MAX_ROWS;
 constexpr int B_MAX_STAGES = LGP_BART_MAX_STAGES;
@@ -96,7 +97,7 @@ __device__ __forceinline__ void bart_stage_chunk(const BartDesc &d, const BartIO
 }
 
 template <int MODE, bool NEED2, bool NEED3>
-__global__ void __launch_bounds__(B_THREADS, NEED3 ? 1 : 2) gram_bart_kernel(const __grid_constant__ BartDesc d,
+__global__ void __launch_bounds__(B_THREADS, 1) gram_bart_kernel(const __grid_constant__ BartDesc d,
                                                                  const __grid_constant__ BartIO io) {
     extern __shared__ __align__(16) unsigned char bsm_raw[];
     BartSmem &sm = *reinterpret_cast<BartSmem *>(bsm_raw);
@@ -105,10 +106,10 @@ __global__ void __launch_bounds__(B_THREADS, NEED3 ? 1 : 2) gram_bart_kernel(con
     const bool diag_tile = io.sym && blockIdx.x == blockIdx.y;
     const int64_t i0 = (int64_t)blockIdx.y * BT, j0 = (int64_t)blockIdx.x * BT;
 
-    double S2[4][4], S3[4][4], sumi[4][4];
-    bool any0[4][4];
+    double S2[B_RA][4], S3[B_RA][4], sumi[B_RA][4];
+    bool any0[B_RA][4];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < B_RA; a++)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             S2[a][c] = 0.0;
@@ -129,9 +130,9 @@ __global__ void __launch_bounds__(B_THREADS, NEED3 ? 1 : 2) gram_bart_kernel(con
         __syncthreads();
         for (int kk = 0; kk < kc; kk++) {
             const BartDim dk = sm.dim[kk];
-            double vx[4], vy[4];
+            double vx[B_RA], vy[4];
 #pragma unroll
-            for (int a = 0; a < 4; a++) vx[a] = sm.pt[0][0][kk][ty + 16 * a];
+            for (int a = 0; a < B_RA; a++) vx[a] = sm.pt[0][0][kk][ty + 32 * a];
 #pragma unroll
             for (int b = 0; b < 2; b++) {
                 const double2 t = *reinterpret_cast<const double2 *>(&sm.pt[1][0][kk][2 * tx + 32 * b]);
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(B_THREADS, NEED3 ? 1 : 2) gram_bart_kernel(con
                 vy[2 * b + 1] = t.y;
             }
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+            for (int a = 0; a < B_RA; a++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) bart_pass1<NEED2, NEED3>(dk, vx[a], vy[c], S2[a][c], S3[a][c], any0[a][c]);
         }
@@ -155,10 +156,10 @@ __global__ void __launch_bounds__(B_THREADS, NEED3 ? 1 : 2) gram_bart_kernel(con
             }
             for (int kk = 0; kk < kc; kk++) {
                 const BartDim dk = sm.dim[kk];
-                BartPoint px[4], py[4];
+                BartPoint px[B_RA], py[4];
 #pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    const int r = ty + 16 * a;
+                for (int a = 0; a < B_RA; a++) {
+                    const int r = ty + 32 * a;
                     px[a].v = sm.pt[0][0][kk][r];
                     px[a].pa = sm.pt[0][1][kk][r];
                     px[a].pb = sm.pt[0][2][kk][r];
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(B_THREADS, NEED3 ? 1 : 2) gram_bart_kernel(con
                     py[2 * b].rp = t4.x, py[2 * b + 1].rp = t4.y;
                 }
 #pragma unroll
-                for (int a = 0; a < 4; a++)
+                for (int a = 0; a < B_RA; a++)
 #pragma unroll
                     for (int c = 0; c < 4; c++) bart_pass2(dk, d.inv_Wn, S3[a][c], px[a], py[c], sumi[a][c]);
             }
@@ -189,9 +190,9 @@ __global__ void __launch_bounds__(B_THREADS, NEED3 ? 1 : 2) gram_bart_kernel(con
 
     // ---- `repeat` scans of all stages, value (and alpha / beta duals)
     constexpr bool DUAL = MODE != BMODE_VALUE;
-    double ga[4][4], gb[4][4];
+    double ga[B_RA][4], gb[B_RA][4];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < B_RA; a++)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             double g = d.gamma, da_ = 0.0, db_ = 0.0;
@@ -211,8 +212,8 @@ __global__ void __launch_bounds__(B_THREADS, NEED3 ? 1 : 2) gram_bart_kernel(con
         // sum_ij G_ij * {corr, amp dcorr/dalpha, amp dcorr/dbeta}; symlower: G read from the lower triangle, w = 2 off it
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
 #pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const int64_t i = i0 + ty + 16 * a;
+        for (int a = 0; a < B_RA; a++) {
+            const int64_t i = i0 + ty + 32 * a;
             if (i >= io.n) continue;
             const double bi = io.b ? io.b[i] : 0.0;
 #pragma unroll
@@ -261,15 +262,15 @@ __global__ void __launch_bounds__(B_THREADS, NEED3 ? 1 : 2) gram_bart_kernel(con
         double *dst = (o == 0) ? io.K : (o == 1 ? io.dKa : io.dKb);
         const int64_t ld = (o == 0) ? io.ldk : io.ldd;
         if (!dst) continue;
-        double vals[4][4];
+        double vals[B_RA][4];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+        for (int a = 0; a < B_RA; a++)
 #pragma unroll
             for (int c = 0; c < 4; c++)
                 vals[a][c] = LGP_B_MUL(d.amp, o == 0 ? S2[a][c] : (o == 1 ? ga[a][c] : gb[a][c]));
 #pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const int64_t i = i0 + ty + 16 * a;
+        for (int a = 0; a < B_RA; a++) {
+            const int64_t i = i0 + ty + 32 * a;
             if (i >= io.n) continue;
             double *krow = dst + i * ld;
 #pragma unroll
@@ -287,10 +288,10 @@ __global__ void __launch_bounds__(B_THREADS, NEED3 ? 1 : 2) gram_bart_kernel(con
         if (io.sym && !diag_tile) {
             __syncthreads();
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+            for (int a = 0; a < B_RA; a++)
 #pragma unroll
                 for (int c = 0; c < 4; c++)
-                    tsm[(2 * tx + 32 * (c >> 1) + (c & 1)) * B_TSTRIDE + ty + 16 * a] = vals[a][c];
+                    tsm[(2 * tx + 32 * (c >> 1) + (c & 1)) * B_TSTRIDE + ty + 32 * a] = vals[a][c];
             __syncthreads();
             // row jj of the transposed tile = column jj of the tile; 64 consecutive entries per row
             for (int idx = tid; idx < BT * BT; idx += B_THREADS) {
