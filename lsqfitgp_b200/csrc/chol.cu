@@ -555,6 +555,26 @@ struct PanelHook {
     bool fired;
 };
 
+// Panel width (in 128-blocks) for a trailing matrix of `left` blocks.  Wide panels make the trailing rank-k updates
+// efficient while they dominate; once the trailing matrix is small the factorisation is bound by the chain of dependent
+// panel kernels, whose length per 128 columns grows with the recursion depth of the panel (4-block panel: 4 leaves + 17
+// small GEMMs per 512 columns; 1-block panels: 4 leaves + 8), so the tail switches to narrower panels.
+static int panel_width(int left, int pb) {
+    static int t1 = -1, t2 = -1;
+    if (t1 < 0) {
+        int a = 64, b = 24;  // thresholds in blocks (8192 and 3072 rows), tuned on B200 (n = 20000: 90.6 -> 89.0 ms, n = 10000:
+                             // 17.7 -> 16.4 ms, n = 4096: 4.72 -> 3.77 ms against fixed 4-block panels)
+        const char *e = getenv("LGP_TAIL_BLOCKS");
+        if (e) sscanf(e, "%d,%d", &a, &b);
+        t2 = b;
+        t1 = a;
+    }
+    int w = pb;
+    if (left <= t1 && w > 2) w = 2;
+    if (left <= t2) w = 1;
+    return w < left ? w : left;
+}
+
 static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = nullptr) {
     cudaStream_t ps = (nblk > pb) ? panel_stream(cm.st) : nullptr;
     if (!ps) {
@@ -564,7 +584,7 @@ static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = null
     const bool trace = trace_enabled();  // debug only: synchronises and prints a per-panel timeline
     CholCtx cp = cm;
     cp.st = ps;
-    const int np = (nblk + pb - 1) / pb;
+    const int np = nblk;  // upper bound on the number of panels (the tail uses narrower ones)
     cudaEvent_t e_fork = nullptr, e_last = nullptr;
     cudaEvent_t *t_pstart = nullptr, *t_restend = nullptr, *t_panel = nullptr, *t_col = nullptr;
     if (trace) {
@@ -581,9 +601,9 @@ static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = null
     int rc = LGP_OK;
     int last = -1;
     cudaEvent_t e_colnext = nullptr;  // recorded on the main stream when the next panel's block column is updated
-    for (int j = 0; j < np && rc == LGP_OK && ok; j++) {
-        const int jb = j * pb;
-        const int w = (nblk - jb < pb) ? nblk - jb : pb;
+    int jb = 0;
+    for (int j = 0; jb < nblk && rc == LGP_OK && ok; j++) {
+        const int w = panel_width(nblk - jb, pb);
         const int rest = nblk - jb - w;
         // ---- panel stream
         if (j > 0) ok = ok && ev_wait(ps, e_colnext);
@@ -601,7 +621,7 @@ static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = null
         }
         // ---- main stream
         ok = ok && ev_wait(cm.st, e_panel);
-        const int w2 = rest < pb ? rest : pb;
+        const int w2 = panel_width(rest, pb);  // width of the next panel
         const int rest2 = rest - w2;
         const int K = w * NB;
         // next block column (rows jb+w.., cols jb+w..jb+w+w2): one full GEMM; the part above the block
@@ -615,6 +635,7 @@ static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = null
             rc = gemm_launch(cm.st, true, true, rest2 * NB, rest2 * NB, K, -1.0, Wp(cm, jb + w + w2, jb), cm.ldw,
                              Wp(cm, jb + w + w2, jb), cm.ldw, Wp(cm, jb + w + w2, jb + w + w2), cm.ldw, GEMM_LOWER);
         if (trace) cudaEventRecord(t_restend[j], cm.st);
+        jb += w;
     }
     if (e_last) ok = ev_wait(cm.st, e_last) && ok;  // join
     if (!ok) {
