@@ -380,7 +380,8 @@ def dist_chol_measure(n, tile, dev, rank, world, dmma_peak, reps=1):
         torch.cuda.empty_cache()
     flops = n ** 3 / 3
     tf = flops / (best['factor_ms'] * 1e-3) / 1e12
-    return dict(n=n, tile=tile, grid=grid, n_gpus=world, panel_broadcast=peer_mode, factor_ms=best['factor_ms'],
+    return dict(n=n, tile=tile, grid=grid, n_gpus=world, panel_broadcast=peer_mode, storage='lower-packed tiles',
+                factor_ms=best['factor_ms'],
                 factor_TFLOPs=tf,
                 per_gpu_TFLOPs=tf / world, frac_of_dmma_peak=tf / world / dmma_peak, dmma_peak_TFLOPs=dmma_peak,
                 e2e_ms=best['e2e_ms'], e2e_TFLOPs=flops / (best['e2e_ms'] * 1e-3) / 1e12,
@@ -744,8 +745,8 @@ def run_gpu(args):
             else:
                 # 1-GPU point of the curve: the largest n that fits one B200 with the dense local layout
                 dist_chol = dist_chol_measure(args.dist_n1, args.dist_tile, dev, rank, world, dmma_peak)
-                dist_chol['note_1gpu'] = (f'n={args.dist_n1} instead of {args.dist_n}: the dense local layout of n=150000 '
-                                          'is 180 GB; same code path on a 1 x 1 grid')
+                dist_chol['note_1gpu'] = ('same code path on a 1 x 1 process grid; lower-packed tile storage (84 GiB at '
+                                          'n = 150000)')
             if args.dist_parity_n > 0:
                 dist_chol['parity'] = {f'n{args.dist_parity_n}': dist_chol_parity(args.dist_parity_n, args.dist_tile, dev,
                                                                                   rank, world)}
@@ -842,9 +843,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dist-n', type=int, default=150000,
                     help='size of the block-cyclic multi-GPU Cholesky reported under "dist_chol" at N > 1 (0 = skip)')
-    ap.add_argument('--dist-n1', type=int, default=122880,
-                    help='N = 1 only: size of the 1-GPU point of the dist_chol curve: the largest tile multiple whose dense '
-                         'local layout fits one B200 (121 GB); 0 = skip')
+    ap.add_argument('--dist-n1', type=int, default=150000,
+                    help='N = 1 only: size of the 1-GPU point of the dist_chol curve (lower-packed tiles: 84 GiB at '
+                         'n = 150000 on one B200); 0 = skip')
     ap.add_argument('--dist-parity-n', type=int, default=30000,
                     help='size of the DistChol parity block (vs single-GPU factorisation and CPU oracle; 0 = skip)')
     ap.add_argument('--dist-tile', type=int, default=1024)

@@ -380,6 +380,23 @@ int lgp_tile_trsv(lgp_stream_t stream, const double *L, int64_t ldl, const doubl
  * per local tile column. */
 int lgp_dist_trailing_update(lgp_stream_t stream, const lgp_grid_t *grid, double *A, int64_t lda, int64_t k,
                              const double *const *panel, int64_t lj_begin, int64_t lj_end);
+/* Lower-packed local storage (half the memory: n = 150000 fits ONE B200): local tile column lj (global tile column
+ * J = pcol + npcol*lj) is one contiguous panel of leading dimension t that holds only the local tile rows
+ * li >= first = #{I < J : I mod nprow == prow}, i.e. the tiles I >= J, stacked in increasing I.
+ * lgp_dist_panel_rows: first stored local tile row and number of stored tile rows of panel lj (host outputs).
+ * lgp_dist_panel_diag / _prepare / _add_diag: the per-panel forms of lgp_dist_diag / lgp_dist_prepare / lgp_dist_add_diag;
+ *   _prepare ACCUMULATES (atomicAdd) into rowsum, which the caller zero-initialises: tiles strictly below the diagonal
+ *   contribute their column sums as well (the mirrored entries are not stored), so that the sum over processes is again
+ *   the full Gershgorin row sum of eigval_bound (_decomp.py:349-354).
+ * lgp_dist_trailing_update_packed: as lgp_dist_trailing_update with colpanels[lj] (HOST array of device pointers, one per
+ *   local tile column) instead of the dense local matrix. */
+int lgp_dist_panel_rows(const lgp_grid_t *grid, int64_t lj, int64_t *first_tile_row, int64_t *tile_rows);
+int lgp_dist_panel_diag(lgp_stream_t stream, const lgp_grid_t *grid, int64_t lj, const double *panel, double *d);
+int lgp_dist_panel_prepare(lgp_stream_t stream, const lgp_grid_t *grid, int64_t lj, double *panel, const double *sinv,
+                           double *rowsum);
+int lgp_dist_panel_add_diag(lgp_stream_t stream, const lgp_grid_t *grid, int64_t lj, double *panel, const double *eps);
+int lgp_dist_trailing_update_packed(lgp_stream_t stream, const lgp_grid_t *grid, double *const *colpanels, int64_t k,
+                                    const double *const *panel, int64_t lj_begin, int64_t lj_end);
 /* y += alpha * P x (trans=0; P rows x cols, x cols, y rows) or y += alpha * P^T x (trans=1; x rows, y cols):
  * the HBM-streaming vector updates of the distributed triangular solves */
 int lgp_dgemv(lgp_stream_t stream, int trans, const double *P, int64_t ldp, int64_t rows, int64_t cols,

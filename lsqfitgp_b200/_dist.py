@@ -302,16 +302,40 @@ class CudaTileOps:
         return ctypes.c_void_p(t.data_ptr())
 
     # ---- matrix generation and preparation
-    def gram_local(self, descs, x, rows, cols, lay):
+    def gram_local(self, descs, x, rows, cols, lay, out=None):
         """ local matrix K[rows, cols] generated in place from the replicated points x (ndim, n) """
         from . import _ops
         ri = torch.as_tensor(numpy.minimum(rows, lay.n - 1), device=self.device)
         ci = torch.as_tensor(numpy.minimum(cols, lay.n - 1), device=self.device)
-        ld = max(len(cols) + (len(cols) & 1), 2)
-        A = self.empty(max(len(rows), 1), ld)[:len(rows), :len(cols)]  # never a null pointer, even leading dimension
+        if out is None:
+            ld = max(len(cols) + (len(cols) & 1), 2)
+            out = self.empty(max(len(rows), 1), ld)[:len(rows), :len(cols)]  # never a null pointer, even leading dimension
         if len(rows) and len(cols):
-            _ops.gram_iso(descs, x.index_select(1, ri).contiguous(), x.index_select(1, ci).contiguous(), out=A)
-        return A
+            _ops.gram_iso(descs, x.index_select(1, ri).contiguous(), x.index_select(1, ci).contiguous(), out=out)
+        return out
+
+    # ---- lower-packed storage: one panel per local tile column (see lgp_dist_panel_* in include/lgp_b200.h)
+    def panel_diag(self, lay, lj, panel, d):
+        g = self._grid(lay)
+        self._ck(self.lib.lgp_dist_panel_diag(self._sp(), ctypes.byref(g), lj, self._p(panel), self._p(d)),
+                 'lgp_dist_panel_diag')
+
+    def panel_prepare(self, lay, lj, panel, sinv, rowsum):
+        g = self._grid(lay)
+        self._ck(self.lib.lgp_dist_panel_prepare(self._sp(), ctypes.byref(g), lj, self._p(panel), self._p(sinv),
+                                                 self._p(rowsum)), 'lgp_dist_panel_prepare')
+
+    def panel_add_diag(self, lay, lj, panel, eps):
+        g = self._grid(lay)
+        self._ck(self.lib.lgp_dist_panel_add_diag(self._sp(), ctypes.byref(g), lj, self._p(panel), self._p(eps)),
+                 'lgp_dist_panel_add_diag')
+
+    def trailing_update_packed(self, lay, colpanels, k, panel, lj_begin, lj_end):
+        g = self._grid(lay)
+        cols = (ctypes.c_void_p * max(len(colpanels), 1))(*[p.data_ptr() if p.numel() else None for p in colpanels])
+        arr = (ctypes.c_void_p * lay.Pr)(*[p.data_ptr() for p in panel])
+        self._ck(self.lib.lgp_dist_trailing_update_packed(self._sp(), ctypes.byref(g), cols, k, arr, lj_begin, lj_end),
+                 'lgp_dist_trailing_update_packed')
 
     def diag(self, lay, A, d):
         g = self._grid(lay)
@@ -475,7 +499,7 @@ class DistChol:
     """
 
     def __init__(self, descs, x, *, tile=512, grid=None, group=None, epsrel='auto', epsabs=0.0, ops=None,
-                 check=True, timers=None, peer='auto'):
+                 check=True, timers=None, peer='auto', storage='lower'):
         if dist.is_available() and dist.is_initialized():
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         else:
@@ -492,23 +516,60 @@ class DistChol:
         self._peer_opt = peer
         self._descs, self._x = descs, x  # kept for matvec(): K is regenerated strip-wise, never stored
 
-        # ---- Gram matrix, generated in place by the owner of each tile
+        # ---- Gram matrix, generated in place by the owner of each tile.  storage='lower' (default): only the tiles on or
+        # below the diagonal, one contiguous panel per local tile column (half the memory: n = 150000 fits one B200);
+        # 'dense': the whole local matrix as one row-major array (the round-1 layout, kept for comparison)
+        if storage not in ('lower', 'dense'):
+            raise ValueError(f'storage must be "lower" or "dense", found {storage!r}')
+        self.storage = storage
         self._mark('start')
-        self.A = A = ops.gram_local(descs, x, lay.global_rows(), lay.global_cols(), lay)
+        T = lay.T
+        if storage == 'dense':
+            self.A = A = ops.gram_local(descs, x, lay.global_rows(), lay.global_cols(), lay)
+            self._panels = None
+        else:
+            self.A = None
+            grows = lay.global_rows()
+            self._first = [tiles_before(lay.pc + lay.Pc * lj, lay.pr, lay.Pr) for lj in range(lay.LC)]
+            sizes = [max(lay.LR - f, 0) * T * T for f in self._first]
+            buf = ops.empty(max(sum(sizes), 2))
+            self._panels, off = [], 0
+            for lj, (f, sz) in enumerate(zip(self._first, sizes)):
+                panel = buf[off:off + sz].view(-1, T)
+                off += sz
+                self._panels.append(panel)
+                if sz:
+                    J = lay.pc + lay.Pc * lj
+                    ops.gram_local(descs, x, grows[f * T:], numpy.arange(J * T, (J + 1) * T), lay, out=panel)
         self._mark('gram')
 
         # ---- equilibration and jitter
         d = ops.zeros(lay.npad)
-        ops.diag(lay, A, d)
+        if storage == 'dense':
+            ops.diag(lay, A, d)
+        else:
+            for lj, panel in enumerate(self._panels):
+                if panel.numel():
+                    ops.panel_diag(lay, lj, panel, d)
         self._allreduce(d)
         self.s, self.sinv = ops.scale_from_diag(lay, d)
         rowsum = ops.zeros(lay.n)
-        ops.prepare(lay, A, self.sinv, rowsum)
+        if storage == 'dense':
+            ops.prepare(lay, A, self.sinv, rowsum)
+        else:
+            for lj, panel in enumerate(self._panels):
+                if panel.numel():
+                    ops.panel_prepare(lay, lj, panel, self.sinv, rowsum)
         self._allreduce(rowsum)
         er = -1.0 if (isinstance(epsrel, str) and epsrel == 'auto') else float(epsrel)
         ea = 2.220446049250313e-16 if (isinstance(epsabs, str) and epsabs == 'auto') else float(epsabs)
         self._epsout = ops.eps(lay, rowsum, er, ea)
-        ops.add_diag(lay, A, self._epsout[1:2])
+        if storage == 'dense':
+            ops.add_diag(lay, A, self._epsout[1:2])
+        else:
+            for lj, panel in enumerate(self._panels):
+                if panel.numel():
+                    ops.panel_add_diag(lay, lj, panel, self._epsout[1:2])
         del d, rowsum
         self._mark('prepare')
 
@@ -530,6 +591,28 @@ class DistChol:
         if check and self._info != INT_MAX and self._info <= lay.n:
             raise numpy.linalg.LinAlgError('cholesky decomposition not finite, probably matrix not pos def numerically')
 
+    # ---- local storage access (dense local matrix or lower-packed panels)
+    def _tile(self, li, lj):
+        """ local tile (li, lj) as a T x T view """
+        T = self.lay.T
+        if self._panels is None:
+            return self.A[li * T:(li + 1) * T, lj * T:(lj + 1) * T]
+        o = (li - self._first[lj]) * T
+        return self._panels[lj][o:o + T]
+
+    def _below(self, li0, lj):
+        """ the local tiles (li >= li0, lj) stacked: ((LR - li0) T) x T view """
+        T = self.lay.T
+        if self._panels is None:
+            return self.A[li0 * T:, lj * T:(lj + 1) * T]
+        return self._panels[lj][(li0 - self._first[lj]) * T:]
+
+    def _trailing(self, k, slabs, lj_begin, lj_end):
+        if self._panels is None:
+            self.ops.trailing_update(self.lay, self.A, k, slabs, lj_begin, lj_end)
+        else:
+            self.ops.trailing_update_packed(self.lay, self._panels, k, slabs, lj_begin, lj_end)
+
     # ---- collectives (no-ops in a single process)
     def _mark(self, name):
         if self._timers is not None:
@@ -548,7 +631,7 @@ class DistChol:
 
     # ---- right-looking factorisation with one-panel look-ahead
     def _factor(self):
-        lay, ops, A = self.lay, self.ops, self.A
+        lay, ops = self.lay, self.ops
         T, NT, Pr, Pc, pr, pc = lay.T, lay.NT, lay.Pr, lay.Pc, lay.pr, lay.pc
         nb = T // 128
         # diagonal tiles owned here: inverted 128x128 diagonal blocks kept for the solves
@@ -595,7 +678,7 @@ class DistChol:
                     buf_free[set_].wait()
                 Lkk = invd_k = None
                 if own_diag:
-                    tile = A[lkr * T:(lkr + 1) * T, lkc * T:(lkc + 1) * T]
+                    tile = self._tile(lkr, lkc)
                     invd_k = self.invd[self._mydiag[k]]
                     ops.potrf_tile(tile, invd_k, self.dvec, self.info, k * T)
                     Lkk = tile
@@ -635,18 +718,18 @@ class DistChol:
                         off = soff(set_, pr)
                         dst = [pb.data_addr('mc', off)] if self._multimem else \
                             [pb.data_addr(q, off) for q in range(self.world)]
-                        ops.trsm_right_bcast(Lkk, invd_k, A[li0 * T:, lkc * T:(lkc + 1) * T], dst, T, self._multimem)
+                        ops.trsm_right_bcast(Lkk, invd_k, self._below(li0, lkc), dst, T, self._multimem)
                         ops.flag_signal([pb.flag_addr(q, READY + pr) for q in range(self.world)], k + 1)
                 else:
                     if in_col and cnt > 0:
-                        ops.trsm_right(Lkk, invd_k, A[li0 * T:, lkc * T:(lkc + 1) * T])
+                        ops.trsm_right(Lkk, invd_k, self._below(li0, lkc))
                     for r in range(Pr):
                         c_r = lay.panel_count(k, r)
                         if c_r == 0:
                             continue
                         buf = slab[set_][r][:c_r * TT]
                         if in_col and pr == r:
-                            ops.copy2d(A[li0 * T:, lkc * T:(lkc + 1) * T], buf.view(c_r * T, T))
+                            ops.copy2d(self._below(li0, lkc), buf.view(c_r * T, T))
                         self._bcast(buf, lay.rank_of(r, pcol))
                 panel_done = ops.event()
                 panel_done.record()
@@ -663,13 +746,13 @@ class DistChol:
                     lj_next = (k + 1) // Pc
                     if pc == nxt_c:
                         # look-ahead: the next panel's tile column first, then release the panel stream
-                        ops.trailing_update(lay, A, k, panels, lj_next, lj_next + 1)
+                        self._trailing(k, panels, lj_next, lj_next + 1)
                         ev = ops.event()
                         ev.record()
                         col_ready[k + 1] = ev
-                        ops.trailing_update(lay, A, k, panels, lj_next + 1, lay.LC)
+                        self._trailing(k, panels, lj_next + 1, lay.LC)
                     else:
-                        ops.trailing_update(lay, A, k, panels, 0, lay.LC)
+                        self._trailing(k, panels, 0, lay.LC)
                 ev = ops.event()
                 ev.record()
                 buf_free[set_] = ev
@@ -774,12 +857,12 @@ class DistChol:
             yk = ops.zeros(T)
             if lay.owner(k, k) == self.rank:
                 yk.copy_(z[k * T:(k + 1) * T] - part)
-                ops.trsv_tile(A[lkr * T:(lkr + 1) * T, lkc * T:(lkc + 1) * T], self.invd[self._mydiag[k]], yk, False)
+                ops.trsv_tile(self._tile(lkr, lkc), self.invd[self._mydiag[k]], yk, False)
             self._bcast(yk, lay.owner(k, k))
             y[k * T:(k + 1) * T] = yk
             li0 = lay.panel_first(k)
             if pc == pcol and lay.LR > li0:
-                ops.gemv(A[li0 * T:, lkc * T:(lkc + 1) * T], yk, acc[li0 * T:], 1.0, False)
+                ops.gemv(self._below(li0, lkc), yk, acc[li0 * T:], 1.0, False)
         return y if _padded else y[:lay.n]
 
     def _back(self, y):
@@ -795,12 +878,12 @@ class DistChol:
             li0 = lay.panel_first(k)
             if k < NT - 1:
                 if pc == pcol and lay.LR > li0:
-                    ops.gemv(A[li0 * T:, lkc * T:(lkc + 1) * T], xloc[li0 * T:], part, 1.0, True)
+                    ops.gemv(self._below(li0, lkc), xloc[li0 * T:], part, 1.0, True)
                 self._allreduce(part)
             xk = ops.zeros(T)
             if lay.owner(k, k) == self.rank:
                 xk.copy_(y[k * T:(k + 1) * T] - part)
-                ops.trsv_tile(A[lkr * T:(lkr + 1) * T, lkc * T:(lkc + 1) * T], self.invd[self._mydiag[k]], xk, True)
+                ops.trsv_tile(self._tile(lkr, lkc), self.invd[self._mydiag[k]], xk, True)
             self._bcast(xk, lay.owner(k, k))
             x[k * T:(k + 1) * T] = xk
             if pr == prow:
@@ -838,10 +921,10 @@ class DistChol:
             li0 = lay.panel_first(J)
             seg = out[J * T:(J + 1) * T]
             if lay.LR > li0:
-                ops.gemv(A[li0 * T:, lj * T:(lj + 1) * T], uloc[li0 * T:], seg, 1.0, True)
+                ops.gemv(self._below(li0, lj), uloc[li0 * T:], seg, 1.0, True)
             if lay.owner(J, J) == self.rank:
                 lkr = J // Pr
-                ops.trmv_tile(A[lkr * T:(lkr + 1) * T, lj * T:(lj + 1) * T], u[J * T:(J + 1) * T], seg, True)
+                ops.trmv_tile(self._tile(lkr, lj), u[J * T:(J + 1) * T], seg, True)
         self._allreduce(out)
         return out[:lay.n]
 
@@ -856,10 +939,10 @@ class DistChol:
             li0 = lay.panel_first(J)
             wj = wv[J * T:(J + 1) * T]
             if lay.LR > li0:
-                ops.gemv(A[li0 * T:, lj * T:(lj + 1) * T], wj, acc[li0 * T:], 1.0, False)
+                ops.gemv(self._below(li0, lj), wj, acc[li0 * T:], 1.0, False)
             if lay.owner(J, J) == self.rank:
                 lkr = J // Pr
-                ops.trmv_tile(A[lkr * T:(lkr + 1) * T, lj * T:(lj + 1) * T], wj, acc[lkr * T:(lkr + 1) * T], False)
+                ops.trmv_tile(self._tile(lkr, lj), wj, acc[lkr * T:(lkr + 1) * T], False)
         out = ops.zeros(lay.npad)
         if lay.LR:
             out.index_copy_(0, self._local_rows_index(), acc[:lay.LR * T])
@@ -902,11 +985,11 @@ class _MatrixTileOps(CudaTileOps):
         super().__init__(device)
         self._K, self._add = K, addmat
 
-    def gram_local(self, descs, x, rows, cols, lay):
+    def gram_local(self, descs, x, rows, cols, lay, out=None):
         ri = torch.as_tensor(numpy.minimum(rows, lay.n - 1), device=self.device)
         ci = torch.as_tensor(numpy.minimum(cols, lay.n - 1), device=self.device)
         ld = max(len(cols) + (len(cols) & 1), 2)
-        A = self.empty(max(len(rows), 1), ld)[:len(rows), :len(cols)]
+        A = out if out is not None else self.empty(max(len(rows), 1), ld)[:len(rows), :len(cols)]
         if len(rows) and len(cols):
             A.copy_(self._K.index_select(0, ri).index_select(1, ci))
             if self._add is not None:

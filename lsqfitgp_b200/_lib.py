@@ -121,6 +121,12 @@ SIGNATURES = {
     'lgp_flag_wait': (_int, [_vp, _vp, _int, ctypes.c_uint64, _i64, _vp]),
     'lgp_tile_trsv': (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _int]),
     'lgp_dist_trailing_update': (_int, [_vp, ctypes.POINTER(Grid), _vp, _i64, _i64, ctypes.POINTER(_vp), _i64, _i64]),
+    'lgp_dist_panel_rows': (_int, [ctypes.POINTER(Grid), _i64, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    'lgp_dist_panel_diag': (_int, [_vp, ctypes.POINTER(Grid), _i64, _vp, _vp]),
+    'lgp_dist_panel_prepare': (_int, [_vp, ctypes.POINTER(Grid), _i64, _vp, _vp, _vp]),
+    'lgp_dist_panel_add_diag': (_int, [_vp, ctypes.POINTER(Grid), _i64, _vp, _vp]),
+    'lgp_dist_trailing_update_packed': (_int, [_vp, ctypes.POINTER(Grid), ctypes.POINTER(_vp), _i64, ctypes.POINTER(_vp),
+                                               _i64, _i64]),
     'lgp_dgemv': (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _vp, _dbl]),
     'lgp_copy2d': (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64]),
 }

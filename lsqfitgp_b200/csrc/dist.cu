@@ -89,6 +89,75 @@ __global__ void __launch_bounds__(256) dist_prepare_kernel(double *__restrict__ 
     if (lane == 0 && gi < g.n) rowsum[gi] = sum;
 }
 
+// ---- lower-packed local storage: local tile column lj (global tile column J = pc + Pc lj) is ONE contiguous panel
+// (rows x T, leading dimension T) holding only the local tile rows li >= first = tiles_before(J, pr, Pr), i.e. the tiles
+// I >= J.  Half the memory of the dense local matrix: n = 150000 fits one B200 (84 GiB), SURVEY.md section 8(e).
+struct PanelGeom {
+    int64_t n;
+    int T, Pr, pr, J, first, rows_t;  // rows_t: number of tile rows stored in the panel
+};
+__device__ __forceinline__ int64_t panel_grow(const PanelGeom &p, int64_t r) {
+    return ((int64_t)p.pr + (int64_t)p.Pr * (p.first + r / p.T)) * p.T + r % p.T;
+}
+
+// d[gi] = A_ii for the diagonal entries of the panel's first tile, if that tile is the diagonal tile (J, J)
+__global__ void panel_diag_kernel(const double *__restrict__ P, PanelGeom p, double *__restrict__ d) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.T) return;
+    const int64_t gi = (int64_t)p.J * p.T + t;
+    if (gi < p.n) d[gi] = P[(int64_t)t * p.T + t];
+}
+__global__ void panel_add_diag_kernel(double *__restrict__ P, PanelGeom p, const double *__restrict__ eps) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.T) return;
+    const int64_t gi = (int64_t)p.J * p.T + t;
+    if (gi < p.n) P[(int64_t)t * p.T + t] += eps[0];
+}
+
+// P <- P / s_i / s_j (identity in the padding); rowsum[gi] += sum_j |P_ij| and, for tiles strictly below the diagonal,
+// rowsum[gj] += sum_i |P_ij| (the mirrored entries that are not stored).  CTA = 64 rows x T columns, thread = 4+ columns.
+constexpr int PP_ROWS = 64;
+__global__ void __launch_bounds__(256) panel_prepare_kernel(double *__restrict__ P, PanelGeom p,
+                                                            const double *__restrict__ sinv,
+                                                            double *__restrict__ rowsum) {
+    __shared__ double rs[PP_ROWS];
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * PP_ROWS;
+    const int64_t nrows = (int64_t)p.rows_t * p.T;
+    if (tid < PP_ROWS) rs[tid] = 0.0;
+    __syncthreads();
+    const bool diag_tile = (p.pr + p.Pr * (p.first + (int)(r0 / p.T))) == p.J;  // a CTA never straddles tiles (T % 64 == 0)
+    for (int c = tid; c < p.T; c += 256) {
+        const int64_t gj = (int64_t)p.J * p.T + c;
+        const double sj = gj < p.n ? sinv[gj] : 1.0;
+        double colsum = 0.0;
+        for (int q = 0; q < PP_ROWS; q++) {
+            const int64_t r = r0 + q;
+            if (r >= nrows) break;
+            const int64_t gi = panel_grow(p, r);
+            double v;
+            if (gi >= p.n || gj >= p.n) {
+                v = (gi == gj) ? 1.0 : 0.0;
+            } else {
+                v = (P[r * p.T + c] * sj) * sinv[gi];  // exact: powers of two
+                const double a = fabs(v);
+                colsum += a;
+                atomicAdd(&rs[q], a);
+            }
+            P[r * p.T + c] = v;
+        }
+        if (!diag_tile && gj < p.n && colsum != 0.0) atomicAdd(rowsum + gj, colsum);
+    }
+    __syncthreads();
+    if (tid < PP_ROWS) {
+        const int64_t r = r0 + tid;
+        if (r < nrows) {
+            const int64_t gi = panel_grow(p, r);
+            if (gi < p.n) atomicAdd(rowsum + gi, rs[tid]);
+        }
+    }
+}
+
 // out[0] = max_i rowsum_i, out[1] = eps = epsrel*max + epsabs  (eigval_bound + _parseeps, _decomp.py:245-255,349-354)
 __global__ void __launch_bounds__(1024) dist_eps_kernel(const double *__restrict__ rowsum, int64_t n, double epsrel,
                                                         double epsabs, double *__restrict__ out) {
@@ -325,6 +394,88 @@ int lgp_copy2d_bcast(lgp_stream_t stream, const double *src, int64_t lds, int64_
               (unsigned)((rows + 65534) / 65535));
     copy2d_bcast_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, lds, mir, rows, (int)cols);
     LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+// ---- lower-packed panels (see PanelGeom)
+static bool panel_geom(const lgp_grid_t *grid, int64_t lj, Grid &g, PanelGeom &p) {
+    if (!grid_ok(grid, g) || lj < 0 || lj >= g.LC) return false;
+    p.n = g.n;
+    p.T = g.T;
+    p.Pr = g.Pr;
+    p.pr = g.pr;
+    p.J = g.pc + g.Pc * (int)lj;
+    p.first = tiles_before(p.J, g.pr, g.Pr);
+    p.rows_t = g.LR - p.first;
+    return true;
+}
+
+int lgp_dist_panel_rows(const lgp_grid_t *grid, int64_t lj, int64_t *first_tile_row, int64_t *tile_rows) {
+    Grid g;
+    PanelGeom p;
+    if (!panel_geom(grid, lj, g, p) || !first_tile_row || !tile_rows) return LGP_ERR_BADARG;
+    *first_tile_row = p.first;
+    *tile_rows = p.rows_t > 0 ? p.rows_t : 0;
+    return LGP_OK;
+}
+
+int lgp_dist_panel_diag(lgp_stream_t stream, const lgp_grid_t *grid, int64_t lj, const double *panel, double *d) {
+    Grid g;
+    PanelGeom p;
+    if (!panel_geom(grid, lj, g, p) || !d) return LGP_ERR_BADARG;
+    if (p.rows_t <= 0 || p.J % g.Pr != g.pr) return LGP_OK;  // the diagonal tile (J, J) is not stored here
+    if (!panel) return LGP_ERR_BADARG;
+    panel_diag_kernel<<<(g.T + 255) / 256, 256, 0, (cudaStream_t)stream>>>(panel, p, d);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+int lgp_dist_panel_prepare(lgp_stream_t stream, const lgp_grid_t *grid, int64_t lj, double *panel, const double *sinv,
+                           double *rowsum) {
+    Grid g;
+    PanelGeom p;
+    if (!panel_geom(grid, lj, g, p) || !sinv || !rowsum) return LGP_ERR_BADARG;
+    if (p.rows_t <= 0) return LGP_OK;
+    if (!panel) return LGP_ERR_BADARG;
+    const int64_t nrows = (int64_t)p.rows_t * p.T;
+    panel_prepare_kernel<<<(unsigned)((nrows + PP_ROWS - 1) / PP_ROWS), 256, 0, (cudaStream_t)stream>>>(panel, p, sinv,
+                                                                                                      rowsum);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+int lgp_dist_panel_add_diag(lgp_stream_t stream, const lgp_grid_t *grid, int64_t lj, double *panel, const double *eps) {
+    Grid g;
+    PanelGeom p;
+    if (!panel_geom(grid, lj, g, p) || !eps) return LGP_ERR_BADARG;
+    if (p.rows_t <= 0 || p.J % g.Pr != g.pr) return LGP_OK;
+    if (!panel) return LGP_ERR_BADARG;
+    panel_add_diag_kernel<<<(g.T + 255) / 256, 256, 0, (cudaStream_t)stream>>>(panel, p, eps);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+int lgp_dist_trailing_update_packed(lgp_stream_t stream, const lgp_grid_t *grid, double *const *colpanels, int64_t k,
+                                    const double *const *panel, int64_t lj_begin, int64_t lj_end) {
+    Grid g;
+    if (!grid_ok(grid, g) || !colpanels || !panel || k < 0 || k >= g.NT) return LGP_ERR_BADARG;
+    if (lj_begin < 0) lj_begin = 0;
+    if (lj_end > g.LC) lj_end = g.LC;
+    const int64_t TT = (int64_t)g.T * g.T;
+    const int li0_mine = tiles_before((int)k + 1, g.pr, g.Pr);
+    for (int64_t lj = lj_begin; lj < lj_end; lj++) {
+        const int J = g.pc + g.Pc * (int)lj;
+        if (J <= k) continue;
+        const int li_s = tiles_before(J, g.pr, g.Pr);  // first local tile row with I >= J = first stored row of the panel
+        if (li_s >= g.LR) continue;
+        if (!colpanels[lj]) return LGP_ERR_BADARG;
+        const int rJ = J % g.Pr;
+        const double *Aop = panel[g.pr] + (int64_t)(li_s - li0_mine) * TT;
+        const double *Bop = panel[rJ] + (int64_t)(J / g.Pr - tiles_before((int)k + 1, rJ, g.Pr)) * TT;
+        int rc = gemm_launch((cudaStream_t)stream, true, true, (g.LR - li_s) * g.T, g.T, g.T, -1.0, Aop, g.T, Bop, g.T,
+                             colpanels[lj], g.T, 0);
+        if (rc) return rc;
+    }
     return LGP_OK;
 }
 

@@ -43,11 +43,75 @@ class NumpyTileOps:
     def synchronize(self):
         pass
 
-    def gram_local(self, descs, x, rows, cols, lay):
+    def gram_local(self, descs, x, rows, cols, lay, out=None):
         n = lay.n
         r = np.minimum(rows, n - 1)
         c = np.minimum(cols, n - 1)
-        return torch.from_numpy(np.ascontiguousarray(self.K[np.ix_(r, c)]))
+        blk = torch.from_numpy(np.ascontiguousarray(self.K[np.ix_(r, c)]))
+        if out is not None:
+            out.copy_(blk)
+            return out
+        return blk
+
+    # ---- lower-packed storage (lgp_dist_panel_* of include/lgp_b200.h)
+    @staticmethod
+    def _panel_geom(lay, lj):
+        from lsqfitgp_b200._dist import tiles_before
+        J = lay.pc + lay.Pc * lj
+        first = tiles_before(J, lay.pr, lay.Pr)
+        gi = lay.global_rows()[first * lay.T:]
+        gj = np.arange(J * lay.T, (J + 1) * lay.T)
+        return J, first, gi, gj
+
+    def panel_diag(self, lay, lj, panel, d):
+        J, first, gi, gj = self._panel_geom(lay, lj)
+        if J % lay.Pr != lay.pr or panel.numel() == 0:
+            return
+        t = np.arange(lay.T)
+        ok = gj < lay.n
+        d.numpy()[gj[ok]] = panel.numpy()[t[ok], t[ok]]
+
+    def panel_prepare(self, lay, lj, panel, sinv, rowsum):
+        J, first, gi, gj = self._panel_geom(lay, lj)
+        a = panel.numpy()
+        si = sinv.numpy()
+        a *= si[gi][:, None]
+        a *= si[gj][None, :]
+        pad = (gi[:, None] >= lay.n) | (gj[None, :] >= lay.n)
+        a[pad] = 0
+        a[(gi[:, None] == gj[None, :]) & pad] = 1
+        absa = np.abs(np.where(pad, 0, a))
+        rs = rowsum.numpy()
+        ok = gi < lay.n
+        np.add.at(rs, gi[ok], absa.sum(axis=1)[ok])
+        # tiles strictly below the diagonal also stand for their mirror images
+        offdiag = (gi // lay.T) != J
+        okc = gj < lay.n
+        np.add.at(rs, gj[okc], absa[offdiag].sum(axis=0)[okc])
+
+    def panel_add_diag(self, lay, lj, panel, eps):
+        J, first, gi, gj = self._panel_geom(lay, lj)
+        if J % lay.Pr != lay.pr or panel.numel() == 0:
+            return
+        t = np.arange(lay.T)[gj < lay.n]
+        panel.numpy()[t, t] += float(eps[0])
+
+    def trailing_update_packed(self, lay, colpanels, k, panel, lj_begin, lj_end):
+        from lsqfitgp_b200._dist import tiles_before
+        T = lay.T
+        li0 = tiles_before(k + 1, lay.pr, lay.Pr)
+        for lj in range(max(lj_begin, 0), min(lj_end, lay.LC)):
+            J = lay.pc + lay.Pc * lj
+            if J <= k:
+                continue
+            li_s = tiles_before(J, lay.pr, lay.Pr)
+            if li_s >= lay.LR:
+                continue
+            rJ = J % lay.Pr
+            Aop = panel[lay.pr].numpy().reshape(-1, T)[(li_s - li0) * T:(lay.LR - li0) * T]
+            off = J // lay.Pr - tiles_before(k + 1, rJ, lay.Pr)
+            Bop = panel[rJ].numpy().reshape(-1, T)[off * T:(off + 1) * T]
+            colpanels[lj].numpy()[...] -= Aop @ Bop.T
 
     @staticmethod
     def _owned_diag(lay):

@@ -91,13 +91,14 @@ def _check_against_oracle(dc, K, b):
     np.testing.assert_allclose(kv, K @ b + float(dc._epsout[1]) * s ** 2 * b, rtol=1e-12, atol=1e-13 * np.abs(kv).max())
 
 
+@pytest.mark.parametrize('storage', ['lower', 'dense'])
 @pytest.mark.parametrize('n,T', [(300, 128), (700, 256), (128, 128), (1, 128)])
-def test_single_process_orchestration(n, T):
+def test_single_process_orchestration(n, T, storage):
     from _numpy_tile_ops import NumpyTileOps
     K = _matrix(n)
     b = np.random.default_rng(1).standard_normal(n)
     x = torch.zeros(1, n, dtype=torch.float64)
-    dc = _dist.DistChol(None, x, tile=T, ops=NumpyTileOps(K))
+    dc = _dist.DistChol(None, x, tile=T, ops=NumpyTileOps(K), storage=storage)
     _check_against_oracle(dc, K, b)
 
 
@@ -116,7 +117,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, T, grid, q):
+def _worker(rank, world, port, n, T, grid, q, storage='lower'):
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from _numpy_tile_ops import NumpyTileOps
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -126,7 +127,7 @@ def _worker(rank, world, port, n, T, grid, q):
         K = _matrix(n)
         b = np.random.default_rng(1).standard_normal(n)
         x = torch.zeros(1, n, dtype=torch.float64)
-        dc = _dist.DistChol(None, x, tile=T, grid=grid, ops=NumpyTileOps(K))
+        dc = _dist.DistChol(None, x, tile=T, grid=grid, ops=NumpyTileOps(K), storage=storage)
         try:
             _check_against_oracle(dc, K, b)
             q.put((rank, 'ok', dc.logdet()))
@@ -136,12 +137,13 @@ def _worker(rank, world, port, n, T, grid, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n,T,grid', [(700, 128, (2, 1)), (700, 128, (1, 2)), (520, 256, (2, 1))])
-def test_two_ranks_gloo(n, T, grid):
+@pytest.mark.parametrize('n,T,grid,storage', [(700, 128, (2, 1), 'lower'), (700, 128, (1, 2), 'lower'),
+                                              (520, 256, (2, 1), 'lower'), (700, 128, (2, 1), 'dense')])
+def test_two_ranks_gloo(n, T, grid, storage):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, T, grid, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, T, grid, q, storage)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]

@@ -28,12 +28,13 @@ def _problem(n, seed=5005):
     return X, b, descs, terms
 
 
+@pytest.mark.parametrize('storage', ['lower', 'dense'])
 @pytest.mark.parametrize('n,T', [(1500, 256), (1000, 128), (513, 512), (2048, 512), (77, 128)])
-def test_distchol_single_rank_vs_oracle(n, T):
+def test_distchol_single_rank_vs_oracle(n, T, storage):
     X, b, descs, terms = _problem(n)
     dev = torch.device('cuda:0')
     x = torch.tensor(np.ascontiguousarray(X.T)).to(dev)
-    dc = _dist.DistChol(descs, x, tile=T)
+    dc = _dist.DistChol(descs, x, tile=T, storage=storage)
     K = ogp.gram(terms, X.T.copy(), X.T.copy())
     ref = odecomp.Chol(K)
     ld_ref = 2 * np.sum(np.log(np.diag(ref._L)))
@@ -48,6 +49,12 @@ def test_distchol_single_rank_vs_oracle(n, T):
     st = _ops.chol_factor(torch.tensor(K).to(dev))
     ld1 = 2 * float(st.scalars()[4].item())
     assert abs(dc.logdet() - ld1) <= 1e-12 * abs(ld1)
+    # products with the factor and the size-independent check L (L^T v) = (K + eps S^2) v
+    np.testing.assert_allclose(dc.correlate(b).cpu().numpy(), ref.correlate(b), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(dc.back_correlate(b).cpu().numpy(), ref.back_correlate(b), rtol=1e-10, atol=1e-12)
+    bd = torch.tensor(b).to(dev)
+    kv = dc.matvec(bd)
+    assert float(((dc.correlate(dc.back_correlate(bd)) - kv).norm() / kv.norm()).item()) <= 1e-12
 
 
 def test_distchol_not_posdef():
@@ -67,12 +74,15 @@ def _torchrun(nproc, *args, timeout=600):
 
 
 @pytest.mark.parametrize('nproc,grid', [(2, '2x1'), (2, '1x2'), (4, '2x2'), (8, '2x4')])
-@pytest.mark.parametrize('peer', ['off', 'on'])
-def test_distchol_multi_rank_vs_oracle(nproc, grid, peer):
-    """ peer=off: NCCL panel broadcasts; peer=on: fused TRSM -> peer-memory stores (multimem / NVLink) with counters """
+@pytest.mark.parametrize('peer,storage', [('off', 'lower'), ('on', 'lower'), ('on', 'dense')])
+def test_distchol_multi_rank_vs_oracle(nproc, grid, peer, storage):
+    """ peer=off: NCCL panel broadcasts; peer=on: fused TRSM -> peer-memory stores (multimem / NVLink) with counters;
+    storage: lower-packed panels (default) or the dense local matrix.  Also drives the operator API on the same ranks
+    (GP(..., solver='chol-dist'), GP.decompose) and the L (L^T v) = K v check (tools/dist_check.py --oracle). """
     if torch.cuda.device_count() < nproc:
         pytest.skip(f'needs {nproc} GPUs')
-    res = _torchrun(nproc, '--size', '3000', '--tile', '256', '--grid', grid, '--oracle', '--peer', peer)
+    res = _torchrun(nproc, '--size', '3000', '--tile', '256', '--grid', grid, '--oracle', '--peer', peer, '--storage',
+                    storage)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert 'DIST_CHECK_OK' in res.stdout
 

@@ -30,6 +30,7 @@ def main():
     ap.add_argument('--out', default=None)
     ap.add_argument('--peer', default='auto', choices=['auto', 'on', 'off'],
                     help='panel broadcast: fused TRSM -> peer-memory stores (on), NCCL broadcasts (off), or auto')
+    ap.add_argument('--storage', default='lower', choices=['lower', 'dense'])
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -72,7 +73,7 @@ def main():
         timers = []
         t0 = time.perf_counter()
         dc = _dist.DistChol(descs, x, tile=args.tile, grid=grid, timers=timers,
-                            peer={'auto': 'auto', 'on': True, 'off': False}[args.peer])
+                            peer={'auto': 'auto', 'on': True, 'off': False}[args.peer], storage=args.storage)
         sync()
         t1 = time.perf_counter()
         ph = {timers[i][0]: timers[i][1] - timers[i - 1][1] for i in range(1, len(timers))}
@@ -101,7 +102,7 @@ def main():
 
     ok = resid <= 1e-10
     out = dict(n=n, tile=args.tile, world=world, grid=[dc.lay.Pr, dc.lay.Pc], logdet=logdet, resid=resid,
-               t_solve=t_solve, times=times, info=dc._info, peer_mode=getattr(dc, 'peer_mode', 'nccl'),
+               t_solve=t_solve, times=times, info=dc._info, peer_mode=getattr(dc, 'peer_mode', 'nccl'), storage=args.storage,
                factor_ms_device=dc.factor_ms(),
                factor_tflops=[n ** 3 / 3 / t['factor'] / 1e12 for t in times])
     if args.oracle:
