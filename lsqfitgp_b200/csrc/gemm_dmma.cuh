@@ -254,9 +254,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS) gemm_dmma_kernel
         while ((long long)R * tm * (tm + 1) / 2 > b) tm--;
         tn = (int)(b - (long long)R * tm * (tm + 1) / 2);
     } else {
-        // column-of-tiles fastest so that consecutive CTAs share the B tile stream in L2
-        tm = blockIdx.x % p.tiles_m;
-        tn = blockIdx.x / p.tiles_m;
+        // Grouped rasterisation: the CTAs in flight at any time (one wave = 3 per SM) cover GROUP row tiles x ~wave/GROUP
+        // column tiles, so that both operand streams are re-used out of L2.  (With the plain column-of-tiles-fastest
+        // order a wave spans ~440 row tiles of ONE tile column: every CTA streams its own A strip and all of A is re-read
+        // from HBM once per tile column: 62 GB of DRAM reads for an 8192^3 product, profiles/gemm_dmma_ncu_r1.txt.)
+        constexpr int GROUP = 16;
+        const long long b = blockIdx.x;
+        const long long per_group = (long long)GROUP * p.tiles_n;
+        const int first_m = (int)(b / per_group) * GROUP;
+        const int gsz = min(GROUP, p.tiles_m - first_m);
+        const int rem = (int)(b % per_group);
+        tm = first_m + rem % gsz;
+        tn = rem / gsz;
     }
     const int m0 = tm * BM, n0 = tn * BN;
 

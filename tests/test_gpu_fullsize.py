@@ -152,3 +152,26 @@ def test_matern_real_order_full_size_sampled_rows():
     Kg = K[torch.as_tensor(rows, device=dev)].cpu().numpy()
     assert np.max(np.abs(Kg - Ko) / np.abs(Ko)) < 2e-13
     assert torch.equal(K[:2048, :2048], K[:2048, :2048].T)
+
+
+def test_logml_value_against_oracle_at_full_size(state):
+    """ the VALUE of logML at n = 20000 against the CPU oracle (round-1 verdict: only logdet / residual / finite-difference
+    checks existed at this size).  The oracle evaluates the Gram matrix with the closed half-integer form Maternp(p=2)
+    (equal to the reference's kv-based Matern(nu=2.5) to 1e-15, tests/test_oracle_special.py, and 20x cheaper than 4e8 calls
+    of scipy.special.kv) into ONE host buffer and factors it in place with LAPACK (oracle.gp.logml_value_lean); the sampled
+    rows of test_gram_sampled_rows_and_symmetry pin the device Gram to the kv form.  Tolerance 1e-9 (north_star). """
+    import psutil
+    if psutil.virtual_memory().available < 2.5 * 8 * N * N:
+        pytest.skip('host RAM')
+    X, y, st, dev = state['X'], state['y'], state['st'], state['dev']
+    terms = [(1.0, [dict(kind='maternp', p=2, scale=1.5)]), (0.01, [dict(kind='white')])]
+    val_o, L, eps_o = ogp.logml_value_lean(terms, X.T.copy(), y)
+    ld_o = float(np.sum(np.log(np.diagonal(L))))
+    del L
+    a = _ops.chol_solve(st, torch.tensor(y, device=dev)[:, None], False)
+    ld, q = _ops.chol_logdet_quad(st, a[:, 0].contiguous()).cpu().numpy()
+    val = 0.5 * (N * np.log(2 * np.pi) + 2 * ld + q)
+    assert abs(ld - ld_o) <= 1e-11 * abs(ld_o)
+    assert abs(val - val_o) <= 1e-9 * abs(val_o)
+    s = st.scalars().cpu().numpy()
+    assert abs(s[1] * s[3] - eps_o) <= 1e-12 * eps_o

@@ -2,7 +2,9 @@
 //   - DMMA m8n8k4 (mma.sync f64) register-resident loop
 //   - DFMA register-resident loop
 //   - exp() fp64 throughput
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o peaks_fp64 peaks_fp64.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --cudart shared -o peaks_fp64 peaks_fp64.cu
+// (shared runtime: a statically linked binary carries the runtime's whole symbol table into the tree that is shipped to
+// the GPU box).  The same loops are part of the library as lgp_peak_probe, which bench.py times in every run.
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
