@@ -735,6 +735,61 @@ def run_gpu(args):
                   workload='BASELINE configs[0]: GP(ExpQuad(scale=3)) n=1000, marginal_likelihood + predfromdata on 500 '
                            'points, host arrays in / out (reference docs: 4.8 ms jitted on a laptop CPU)')
 
+    # ---- c4_bart (extra key, N = 1): BASELINE configs[3], lgp.BART kernel at n = 5000, p = 10 (8 continuous + 2 binary
+    # covariates): Gram build, Cholesky, and one objective + gradient evaluation of the bayestree.bart recipe
+    # (lambda^2 BART(alpha, beta) + sigma^2 I + k^2 11', epsrel = 0; derivatives w.r.t. alpha, beta, lambda, sigma^2)
+    c4 = None
+    if world == 1 and args.c4:
+        rng = np.random.default_rng(4004)
+        n4 = 5000
+        X4 = np.concatenate([rng.standard_normal((n4, 8)), rng.integers(0, 2, (n4, 2)).astype(float)], axis=1)
+        y4 = rng.standard_normal(n4)
+        splits = lgp.BART.splits_from_coord(X4)
+        idx = lgp.BART.indices_from_coord(X4, splits)
+        xi = lgp.unstructured_to_structured(idx.astype(np.int32), names=[f'c{i}' for i in range(10)])
+        kb = lgp.BART(splits=splits, indices=True, alpha=0.95, beta=2, maxd=10, reset=[2, 4, 6, 8], gamma=1)
+        ixd = torch.tensor(np.ascontiguousarray(idx.T.astype(np.float64)), device=dev)
+
+        def dev_ms(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1) / reps
+        gram_ms = dev_ms(lambda: kb._gram_device(ixd, ixd, None, symmetric=True))
+        Kb = kb._gram_device(ixd, ixd, None, symmetric=True)
+        Kb.diagonal().add_(0.1)
+        chol_ms = dev_ms(lambda: _ops.chol_factor(Kb))
+        del Kb
+
+        def fit_step():
+            th = torch.tensor([0.95, 2.0, 1.1, 0.5], dtype=torch.float64, requires_grad=True)
+            k4 = th[2] ** 2 * lgp.BART(splits=splits, indices=True, alpha=th[0], beta=th[1], maxd=10, reset=[2, 4, 6, 8])
+            gp4 = (lgp.GP(k4, checkpos=False, checksym=False, checkfinite=False, epsrel=0).addx(xi, 'trainmean')
+                   .addcov(torch.diag((th[3] * torch.ones(n4, dtype=torch.float64)).to(dev)), 'trainnoise')
+                   .addcov(0.49, 'mean').addtransf({'trainmean': 1, 'trainnoise': 1, 'mean': 1}, 'train'))
+            ml = gp4.marginal_likelihood({'train': y4})
+            g, = torch.autograd.grad(ml, th)
+            return float(ml.detach()), g.numpy()
+        fit_step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            fit_step()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        c4 = dict(n=n4, p=10, gram_ms=gram_ms, gram_Gpairs_per_s=n4 * n4 / (gram_ms * 1e-3) / 1e9, chol_ms=chol_ms,
+                  chol_TFLOPs=n4 ** 3 / 3 / (chol_ms * 1e-3) / 1e12, recipe_value_and_gradient_ms=min(ts) * 1e3,
+                  workload='BASELINE configs[3]: lgp.BART(maxd=10, reset=[2,4,6,8]) n=5000 p=10: symmetric Gram build, '
+                           'Cholesky, and one bayestree.bart objective+gradient evaluation (alpha, beta, lambda, sigma^2) '
+                           'through the public API, wall clock')
+        torch.cuda.empty_cache()
+
     sampler.join(timeout=2)
 
     dist_chol = None
@@ -807,6 +862,8 @@ def run_gpu(args):
             line['c3_batch'] = c3
         if c1 is not None:
             line['c1_latency'] = c1
+        if c4 is not None:
+            line['c4_bart'] = c4
         if dist_chol is not None:
             line['dist_chol'] = dist_chol
             par = dist_chol.get('parity') or {}
@@ -853,6 +910,7 @@ def main():
                     help='extra key batch_throughput: the same evaluations with this many in flight per GPU (0: skip)')
     ap.add_argument('--c3-per-gpu', type=int, default=8, help='extra key c3_batch: points per GPU (0: skip)')
     ap.add_argument('--c1', type=int, default=1, help='extra key c1_latency at N = 1 (0: skip)')
+    ap.add_argument('--c4', type=int, default=1, help='extra key c4_bart at N = 1 (0: skip)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

@@ -684,20 +684,28 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 // Hot path: no branches, no range checks: the caller tracks the smallest and largest r2 of the thread (as unsigned high
 // words, which order like the non-negative doubles) and redoes out-of-range entries on the slow path.
+// Interleaved copies of the exp table in shared memory (see fm_exp_neg_fast).  Measured on B200, n = 20000, symmetric build:
+// ExpQuad 0.632 -> 0.610 ms with 4 copies (the lookups' bank conflicts were on its critical path), Matern-5/2 0.740 -> 0.783 ms
+// (issue-bound: the extra address arithmetic costs more than the conflicts), so only ExpQuad replicates.
+template <int KIND>
+struct FTabRep {
+    static constexpr int value = KIND == LGP_K_EXPQUAD ? 4 : 1;
+};
+
 template <int KIND, int P>
 __device__ __forceinline__ double fast2_core(double r2, double nu2, double par0, double c0, double c1, double c2,
                                              const ExpTab *tab, const LogTab *ltab) {
-    if (KIND == LGP_K_EXPQUAD) return fm_exp_neg_fast(__dmul_rn(-0.5, r2), tab);
+    if (KIND == LGP_K_EXPQUAD) return fm_exp_neg_fast<FTabRep<KIND>::value>(__dmul_rn(-0.5, r2), tab);
     if (KIND == LGP_K_CAUCHY) {
         // rational quadratic (alpha = 2): (1 + r2/beta)^(-beta/2) (_basic.py:339-343); here nu2 = beta, par0 = RN(1/beta),
         // c0 = -beta/2.  Division and sum rounded as in the reference, the power as exp(c0 log x) with the short log / exp
         const double x = __dadd_rn(1.0, fm_div_recip(r2, nu2, par0));
-        return fm_exp_neg_fast(__dmul_rn(c0, fm_log_ge1_fast(x, ltab)), tab);
+        return fm_exp_neg_fast<FTabRep<KIND>::value>(__dmul_rn(c0, fm_log_ge1_fast(x, ltab)), tab);
     }
     // Maternp: x = sqrt((2p+1) r2 + par0); exp(-x) * poly_p(2x)   (_matern.py:48-49, _bessel.py:103-110)
     const double z = __dadd_rn(__dmul_rn(nu2, r2), par0);
     const double x = fm_sqrt_fast(z);
-    const double ex = fm_exp_neg_fast(-x, tab);
+    const double ex = fm_exp_neg_fast<FTabRep<KIND>::value>(-x, tab);
     if (P == 0) return ex;
     // Horner in the reference's order poly = 1 + ((poly*c_k)*2)*x, the last product-sum fused
     double poly = 1.0;
@@ -738,6 +746,23 @@ __device__ __noinline__ double fast2_slow_entry(const FastDesc &d, double r2, co
     return v;
 }
 
+// The same for the symmetric version-3 kernel, which does not stage raw coordinates: the White comparison of the (rare)
+// entries with r2 == 0 reads them from global memory (keeps 3 KB of shared memory per CTA for the replicated exp table)
+template <int KIND>
+__device__ __noinline__ double fast3_slow_entry(const FastDesc &d, double r2, const double *su, const double *sv,
+                                                const double *__restrict__ x, int64_t ldx, int64_t i, int64_t j, int row,
+                                                int col) {
+    double v = __dmul_rn(d.amp, fast_core<KIND>(d, r2));
+    if (d.has_white) {
+        bool eq = (r2 == 0.0);
+        for (int s = 0; s < d.nd && eq; s++)
+            eq = d.white_raw ? (x[(int64_t)d.dims[s] * ldx + i] == x[(int64_t)d.dims[s] * ldx + j])
+                             : (su[s * FT + row] == sv[s * FT + col]);
+        v = __dadd_rn(v, eq ? d.amp_white : 0.0);
+    }
+    return v;
+}
+
 constexpr int F2_TS = FT + 2;  // row stride of the transpose buffer: 16-byte aligned rows for the bulk stores
 
 template <int KIND, int P, bool SYM>
@@ -750,9 +775,11 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
     // layout: exp table (64 x 16 B), su[nd][64], sv[nd][64], raw copies ru, rv (White with a rescaled main factor),
     // transpose buffer T[64][66] in symmetric mode
     const int nd = d.nd;
-    ExpTab *tab = reinterpret_cast<ExpTab *>(fsm);
-    const LogTab *ltab = reinterpret_cast<const LogTab *>(fsm + 128);  // rational quadratic only
-    double *su = fsm + 128 + (KIND == LGP_K_CAUCHY ? 256 : 0), *sv = su + nd * FT;
+    constexpr int F_TABREP = FTabRep<KIND>::value;
+    ExpTab *tab0 = reinterpret_cast<ExpTab *>(fsm);      // F_TABREP interleaved copies: entry j of copy c at [j * F_TABREP + c]
+    const ExpTab *tab = tab0 + (threadIdx.x & (F_TABREP - 1));  // this lane's copy
+    const LogTab *ltab = reinterpret_cast<const LogTab *>(fsm + 128 * F_TABREP);  // rational quadratic only
+    double *su = fsm + 128 * F_TABREP + (KIND == LGP_K_CAUCHY ? 256 : 0), *sv = su + nd * FT;
     double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
     double *T = rv + (d.white_raw ? nd * FT : 0);
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -768,8 +795,8 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
         tn = blockIdx.x % tiles_n;
     }
     const int64_t i0 = (int64_t)tm * FT, j0 = (int64_t)tn * FT;
-    if (tid < 64) tab[tid] = EXP_TAB_DEV[tid];
-    if (KIND == LGP_K_CAUCHY && tid >= 64 && tid < 128) reinterpret_cast<LogTab *>(fsm + 128)[tid - 64] = LOG_TAB_DEV[tid - 64];
+    if (tid < 64 * F_TABREP) tab0[tid] = EXP_TAB_DEV[tid / F_TABREP];
+    if (KIND == LGP_K_CAUCHY && tid < 64) reinterpret_cast<LogTab *>(fsm + 128 * F_TABREP)[tid] = LOG_TAB_DEV[tid];
     for (int idx = tid; idx < nd * FT; idx += G_THREADS) {
         const int s = idx / FT, r = idx % FT;
         const int64_t i = i0 + r, j = j0 + r;
@@ -935,15 +962,20 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
                                                                   long long ntiles) {
     extern __shared__ __align__(16) double fsm[];
     const int nd = d.nd;
-    ExpTab *tab = reinterpret_cast<ExpTab *>(fsm);
-    const LogTab *ltab = reinterpret_cast<const LogTab *>(fsm + 128);  // rational quadratic only
-    double *su = fsm + 128 + (KIND == LGP_K_CAUCHY ? 256 : 0), *sv = su + nd * FT;
-    double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
-    double *D = rv + (d.white_raw ? nd * FT : 0);  // D[row][col], stride F2_TS
+    constexpr int F_TABREP = FTabRep<KIND>::value;
+    ExpTab *tab0 = reinterpret_cast<ExpTab *>(fsm);      // F_TABREP interleaved copies: entry j of copy c at [j * F_TABREP + c]
+    const ExpTab *tab = tab0 + (threadIdx.x & (F_TABREP - 1));  // this lane's copy
+    const LogTab *ltab = reinterpret_cast<const LogTab *>(fsm + 128 * F_TABREP);  // rational quadratic only
+    double *su = fsm + 128 * F_TABREP + (KIND == LGP_K_CAUCHY ? 256 : 0), *sv = su + nd * FT;
+    // raw coordinates for the White comparison are staged only where the 1 KB table leaves room for them (3 CTAs per SM);
+    // the ExpQuad instantiation, with its 4 KB replicated table, reads them from global memory on the rare slow path
+    constexpr bool RAWSM = F_TABREP == 1;
+    double *ru = sv + nd * FT, *rv = ru + ((RAWSM && d.white_raw) ? nd * FT : 0);
+    double *D = rv + ((RAWSM && d.white_raw) ? nd * FT : 0);  // D[row][col], stride F2_TS
     double *T = D + FT * F2_TS;                    // T[col][row]
     const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
-    if (tid < 64) tab[tid] = EXP_TAB_DEV[tid];
-    if (KIND == LGP_K_CAUCHY && tid >= 64 && tid < 128) reinterpret_cast<LogTab *>(fsm + 128)[tid - 64] = LOG_TAB_DEV[tid - 64];
+    if (tid < 64 * F_TABREP) tab0[tid] = EXP_TAB_DEV[tid / F_TABREP];
+    if (KIND == LGP_K_CAUCHY && tid < 64) reinterpret_cast<LogTab *>(fsm + 128 * F_TABREP)[tid] = LOG_TAB_DEV[tid];
     // Persistent CTA: tiles b = blockIdx.x, blockIdx.x + gridDim.x, ...  The bulk stores of a tile are NOT waited for
     // where they are issued: they drain while the points of the next tile are loaded and the first half of its entries
     // is computed; the wait sits right before the staging buffers are written again.
@@ -963,7 +995,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
         double yr = (j < n) ? x[(int64_t)d.dims[s] * ldx + j] : 0.0;
         su[idx] = fast_scale_point(d, xr);
         sv[idx] = fast_scale_point(d, yr);
-        if (d.white_raw) {
+        if (RAWSM && d.white_raw) {
             ru[idx] = xr;
             rv[idx] = yr;
         }
@@ -976,7 +1008,6 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
     const double par0 = KIND == LGP_K_CAUCHY ? d.rpar1 : d.par0, amp = d.amp;
     const double c0 = KIND == LGP_K_CAUCHY ? d.cexp : d.coef2[0], c1 = d.coef2[1], c2 = d.coef2[2];
     const double rng0 = KIND == LGP_K_CAUCHY ? d.r2max : nu2;
-    const double *wu = d.white_raw ? ru : su, *wv = d.white_raw ? rv : sv;
     const bool white = d.has_white != 0;
     const bool mirror = tm != tn;
     const bool interior = vec_ok && i0 + FT <= n && j0 + FT <= n;
@@ -1024,8 +1055,11 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
 #pragma unroll
                 for (int c = 0; c < 4; c++)
                     if (fast2_out_of_range<KIND>(r2[a][c], rng0, par0, white))
-                        val[a][c] = fast2_slow_entry<KIND>(d, r2[a][c], wu, wv, ty + 16 * (a0 + a),
-                                                           2 * tx + 32 * (c >> 1) + (c & 1));
+                        val[a][c] = RAWSM ? fast2_slow_entry<KIND>(d, r2[a][c], d.white_raw ? ru : su, d.white_raw ? rv : sv,
+                                                                   ty + 16 * (a0 + a), 2 * tx + 32 * (c >> 1) + (c & 1))
+                                          : fast3_slow_entry<KIND>(d, r2[a][c], su, sv, x, ldx, i0 + ty + 16 * (a0 + a),
+                                                                   j0 + 2 * tx + 32 * (c >> 1) + (c & 1),
+                                                                   ty + 16 * (a0 + a), 2 * tx + 32 * (c >> 1) + (c & 1));
         }
         if (d.has_const) {
 #pragma unroll
@@ -1143,11 +1177,12 @@ __device__ __forceinline__ void fast_core_derivs(const FastDesc &d, double r2, d
 
 // Fast-math value and d core / d r2 (ExpQuad, Maternp with compile-time P), arguments inside the range accepted by
 // fast2_out_of_range; same formulas as fast_core_derivs.
+constexpr int V_TABREP = 1;  // replicated tables measured slower here (1.14 -> 1.18 ms with 8 copies): the kernel is issue-bound
 template <int KIND, int P>
 __device__ __forceinline__ void fast2_core_derivs(const FastDesc &d, double r2, const ExpTab *tab, double &val,
                                                   double &dr2) {
     if (KIND == LGP_K_EXPQUAD) {
-        val = fm_exp_neg_fast(-0.5 * r2, tab);
+        val = fm_exp_neg_fast<V_TABREP>(-0.5 * r2, tab);
         dr2 = -0.5 * val;
         return;
     }
@@ -1155,7 +1190,7 @@ __device__ __forceinline__ void fast2_core_derivs(const FastDesc &d, double r2, 
     constexpr double nu2 = (double)(2 * PP + 1);
     const double z = nu2 * r2 + d.par0;
     const double x = fm_sqrt_fast(z);
-    const double ex = fm_exp_neg_fast(-x, tab);
+    const double ex = fm_exp_neg_fast<V_TABREP>(-x, tab);
     if (PP == 0) {
         val = ex;
         dr2 = -nu2 * ex / (2.0 * x);
@@ -1188,9 +1223,11 @@ __global__ void __launch_bounds__(G_THREADS, 2) gram_fast_vjp_kernel(const __gri
     double *ru = sv + nd * FT, *rv = ru + (d.white_raw ? nd * FT : 0);
     __shared__ double sbi[FT], sbj[FT];
     __shared__ double red[G_THREADS / 32][5];
-    __shared__ ExpTab tab[64];
+    __shared__ ExpTab tab0[64 * V_TABREP];   // V_TABREP interleaved copies (bank-private lookups, see fm_exp_neg_fast)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    if (P >= 0 && tid < 64) tab[tid] = EXP_TAB_DEV[tid];
+    const ExpTab *tab = tab0 + (tid & (V_TABREP - 1));
+    if (P >= 0)
+        for (int i = tid; i < 64 * V_TABREP; i += G_THREADS) tab0[i] = EXP_TAB_DEV[i / V_TABREP];
     long long b = blockIdx.x;
     int tm = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
     while ((long long)(tm + 1) * (tm + 2) / 2 <= b) tm++;
@@ -1458,15 +1495,18 @@ static int launch_fast(cudaStream_t st, const FastDesc &d, const double *x, int6
 template <int KIND, int P>
 static int launch_fast2(cudaStream_t st, const FastDesc &d, const double *x, int64_t ldx, int64_t n, const double *y,
                         int64_t ldy, int64_t m, double *K, int64_t ldk, bool sym) {
-    size_t smem = 1024 + (KIND == LGP_K_CAUCHY ? 2048 : 0) + (size_t)(2 + (d.white_raw ? 2 : 0)) * d.nd * FT * sizeof(double) +
+    size_t smem = 1024 * FTabRep<KIND>::value + (KIND == LGP_K_CAUCHY ? 2048 : 0) + (size_t)(2 + (d.white_raw ? 2 : 0)) * d.nd * FT * sizeof(double) +
                   (sym ? FT * F2_TS * 8 : 0);
     int64_t tm = (n + FT - 1) / FT, tn = (m + FT - 1) / FT;
     int64_t grid = sym ? tm * (tm + 1) / 2 : tm * tn;
     if (grid > 2147483647LL) return LGP_ERR_UNSUPPORTED;
     int vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
     static const bool v3 = !(getenv("LGP_GRAM_V3") && getenv("LGP_GRAM_V3")[0] == '0');  // A/B switch (experiments only)
-    if (sym && v3) {
-        smem += (size_t)FT * F2_TS * 8;  // second staging tile
+    // version 3 stages both the tile and its mirror image and no raw coordinates; it needs 3 CTAs per SM to pay off
+    const size_t smem3 = smem + (size_t)FT * F2_TS * 8 -
+                         ((d.white_raw && FTabRep<KIND>::value != 1) ? (size_t)2 * d.nd * FT * sizeof(double) : 0);
+    if (sym && v3 && smem3 <= 77400) {
+        smem = smem3;
         // 3 CTAs per SM (80 registers): measured 0.745 ms against 0.846 ms with 2 CTAs x 126 registers (Matern-5/2, n = 20k)
         static DeviceOnce once;
         static int sm_count[MAX_DEVICES];
@@ -1474,12 +1514,12 @@ static int launch_fast2(cudaStream_t st, const FastDesc &d, const double *x, int
         if (dev < 0) return LGP_ERR_CUDA;
         if (!once.done(dev)) {
             if (cudaFuncSetAttribute(gram_fast3_kernel<KIND, P, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024 / 3) != cudaSuccess ||
+                                     77400) != cudaSuccess ||
                 cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
                 return LGP_ERR_CUDA;
             once.set(dev);
         }
-        if (smem > 227 * 1024 / 3) return LGP_ERR_UNSUPPORTED;
+        // (3 CTAs per SM: 3 * (76800 + 1024 reserved) = 228 KB; many-field inputs that need more go through version 2)
         // one tile per CTA by default; LGP_GRAM_WAVES=k makes the CTAs persistent (k waves of 3 per SM walking the lower-tile
         // list, bulk stores of a tile draining under the next tile's arithmetic): measured SLOWER on B200 at n = 20000
         // (Matern-5/2: 0.805 ms with k = 1, 0.796 with k = 2, against 0.740 ms one tile per CTA: the hardware block scheduler
