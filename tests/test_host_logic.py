@@ -71,21 +71,32 @@ def test_structured_array():
         _array.columns_of(np.array(['a', 'b']))
 
 
-@pytest.mark.parametrize('maxd,reset', [(2, None), (4, 2), (10, [2, 4, 6, 8]), (1, None), (0, None), (6, [2, 4])])
+@pytest.mark.parametrize('maxd,reset', [(2, None), (4, 2), (10, [2, 4, 6, 8]), (1, None), (0, None), (6, [2, 4]),
+                                        (3, [1]), (6, [1, 2, 4]), (7, [2, 3, 5])])
 def test_bart_bracket_folding_matches_oracle(maxd, reset):
+    """ stages (including reset patterns that do not fold into one `repeat` sequence: chained stages) against the
+    oracle's restatement of the reference's bracket folding, and the derivative rows against finite differences """
     spec = _BartSpec(1.0, (np.array([3]), None), True, 0.95, 2, maxd, 1, None, True, None, reset)
-    stages, gamma = spec.rows()
+    widths, nrows, rows, drows, gamma = spec.stages()
     ref = obart.fold_brackets(obart.make_pnt(0.95, 2, maxd), reset)
-    assert len(stages) == len(ref)
-    for rows, (probs, repeat) in zip(stages, ref):
-        np.testing.assert_array_equal(rows.ravel(), probs)
-        assert rows.shape[0] == (repeat or 1)
+    assert len(widths) == len(ref) and gamma == 1.0
+    r = 0
+    for w, nr, (probs, repeat) in zip(widths, nrows, ref):
+        assert nr == (repeat or 1) and w * nr == probs.size
+        np.testing.assert_array_equal(rows[r:r + nr, :w].ravel(), probs)
+        r += nr
+    assert r == len(rows) and drows.shape == (2,) + rows.shape
+    h = 1e-6
+    for q, (da, db) in enumerate([(h, 0.0), (0.0, h)]):
+        up = _BartSpec(1.0, (np.array([3]), None), True, 0.95 + da, 2 + db, maxd, 1, None, True, None, reset).stages()[2]
+        dn = _BartSpec(1.0, (np.array([3]), None), True, 0.95 - da, 2 - db, maxd, 1, None, True, None, reset).stages()[2]
+        np.testing.assert_allclose(drows[q], (up - dn) / (2 * h), atol=1e-8)
 
 
 def test_bart_unsupported_depth():
     spec = _BartSpec(1.0, (np.array([3]), None), True, 0.95, 2, 4, 1, None, True, None, None)
     with pytest.raises(NotImplementedError):
-        spec.rows()
+        spec.stages()
 
 
 def test_bart_preprocessing_matches_oracle(rng):
