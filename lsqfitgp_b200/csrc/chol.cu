@@ -560,16 +560,24 @@ struct PanelHook {
 // panel kernels, whose length per 128 columns grows with the recursion depth of the panel (4-block panel: 4 leaves + 17
 // small GEMMs per 512 columns; 1-block panels: 4 leaves + 8), so the tail switches to narrower panels.
 static int panel_width(int left, int pb) {
-    static int t1 = -1, t2 = -1;
-    if (t1 < 0) {
-        int a = 64, b = 24;  // thresholds in blocks (8192 and 3072 rows), tuned on B200 (n = 20000: 90.6 -> 89.0 ms, n = 10000:
-                             // 17.7 -> 16.4 ms, n = 4096: 4.72 -> 3.77 ms against fixed 4-block panels)
+    static int t0 = -1, t1 = -1, t2 = -1;
+    if (t0 < 0) {
+        // thresholds in blocks of remaining rows: above a -> 2 * pb (rank-1024 trailing updates run at 35.4 instead of
+        // 34.4 TFLOP/s), above b -> pb, above c -> 2 blocks, else 1 block.  Tuned on B200.
+        int a = 96, b = 64, c = 24;
         const char *e = getenv("LGP_TAIL_BLOCKS");
-        if (e) sscanf(e, "%d,%d", &a, &b);
-        t2 = b;
-        t1 = a;
+        if (e) {
+            int x = 0, y = 0, z = 0;
+            const int got = sscanf(e, "%d,%d,%d", &x, &y, &z);
+            if (got == 3) a = x, b = y, c = z;
+            if (got == 2) b = x, c = y;
+        }
+        t1 = b;
+        t2 = c;
+        t0 = a;
     }
     int w = pb;
+    if (left > t0) w = 2 * pb;
     if (left <= t1 && w > 2) w = 2;
     if (left <= t2) w = 1;
     return w < left ? w : left;
