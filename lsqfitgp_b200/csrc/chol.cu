@@ -14,6 +14,7 @@
 #include "gemm_dmma.cuh"
 #include "internal.h"
 #include "chol_leaf2.cuh"
+#include "chol_leaf3.cuh"
 
 namespace lgp {
 
@@ -385,14 +386,22 @@ __global__ void finalize_info_kernel(int32_t *info, int n) {
 static int leaf_version() {
     static const int v = [] {
         const char *e = getenv("LGP_LEAF");
-        return (e && e[0] == '2') ? 2 : 1;
+        return e ? atoi(e) : 31;
     }();
     return v;
 }
 static cudaError_t leaf_set_attrs() {
     cudaError_t e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(potrf_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM_BYTES);
+    e = cudaFuncSetAttribute(potrf_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(potrf_leaf3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(potrf_leaf3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(potrf_leaf3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(potrf_leaf3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
 }
 // the > 48 KB shared-memory opt-in is a per-device attribute: once per device, not once per process
 static int leaf_attr() {
@@ -419,7 +428,16 @@ static int panel_blocks() {
 }
 static void leaf_launch(cudaStream_t st, double *Wblk, int64_t ld, double *invd, double *dvec, int32_t *info, int j0,
                         int version = 0) {
-    if ((version ? version : leaf_version()) == 2)
+    const int v = version ? version : leaf_version();
+    if (v == 3)
+        potrf_leaf3_kernel<0><<<1, L3_THREADS, L3_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
+    else if (v == 31)
+        potrf_leaf3_kernel<1><<<1, L3_THREADS, L3_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
+    else if (v == 32)
+        potrf_leaf3_kernel<2><<<1, L3_THREADS, L3_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
+    else if (v == 33)
+        potrf_leaf3_kernel<3><<<1, L3_THREADS, L3_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
+    else if (v == 2)
         potrf_leaf2_kernel<<<1, L2_THREADS, L2_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
     else
         potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
@@ -564,7 +582,7 @@ static int panel_width(int left, int pb) {
     if (t0 < 0) {
         // thresholds in blocks of remaining rows: above a -> 2 * pb (rank-1024 trailing updates run at 35.4 instead of
         // 34.4 TFLOP/s), above b -> pb, above c -> 2 blocks, else 1 block.  Tuned on B200.
-        int a = 96, b = 64, c = 24;
+        int a = 96, b = 64, c = 32;
         const char *e = getenv("LGP_TAIL_BLOCKS");
         if (e) {
             int x = 0, y = 0, z = 0;
@@ -581,6 +599,14 @@ static int panel_width(int left, int pb) {
     if (left <= t1 && w > 2) w = 2;
     if (left <= t2) w = 1;
     return w < left ? w : left;
+}
+
+static int first_blocks() {
+    static const int v = [] {
+        const char *e = getenv("LGP_FIRST_BLOCKS");
+        return (e && atoi(e) > 0) ? atoi(e) : 2;
+    }();
+    return v;
 }
 
 static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = nullptr) {
@@ -611,7 +637,9 @@ static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = null
     cudaEvent_t e_colnext = nullptr;  // recorded on the main stream when the next panel's block column is updated
     int jb = 0;
     for (int j = 0; jb < nblk && rc == LGP_OK && ok; j++) {
-        const int w = panel_width(nblk - jb, pb);
+        int w = panel_width(nblk - jb, pb);
+        // nothing overlaps the very first panel: keep it narrow (the second one hides behind its trailing update)
+        if (j == 0 && w > first_blocks()) w = first_blocks();
         const int rest = nblk - jb - w;
         // ---- panel stream
         if (j > 0) ok = ok && ev_wait(ps, e_colnext);
@@ -1041,6 +1069,10 @@ int lgp_debug_leaf(lgp_stream_t stream, double *Wblk, int64_t ld, double *invd, 
 // debug hook: phase timestamps (SM clock cycles) of the last leaf-2 launch
 int lgp_debug_leaf2_clocks(long long *out32) {
     return cudaMemcpyFromSymbol(out32, l2_dbg, 32 * sizeof(long long)) == cudaSuccess ? LGP_OK : LGP_ERR_CUDA;
+}
+
+int lgp_debug_leaf3_clocks(long long *out32) {
+    return cudaMemcpyFromSymbol(out32, l3_dbg, 32 * sizeof(long long)) == cudaSuccess ? LGP_OK : LGP_ERR_CUDA;
 }
 
 int lgp_chol_solve(lgp_stream_t stream, const double *W, int64_t ldw, const double *aux, int64_t n64, double *B,

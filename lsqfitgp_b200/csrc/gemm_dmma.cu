@@ -1,6 +1,7 @@
 // Launcher for the FP64 DMMA GEMM (see gemm_dmma.cuh).
 #include "gemm_dmma.cuh"
 #include "internal.h"
+#include <stdlib.h>
 #include <string.h>
 
 namespace lgp {
@@ -23,6 +24,27 @@ static int launch_cfg(cudaStream_t stream, GemmParams &p) {
     gemm_dmma_kernel<Cfg, AK, BK_><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
     LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
+}
+
+// number of SMs of the current device (cached per device)
+static int sm_count() {
+    static int cached[MAX_DEVICES];
+    const int dev = current_device();
+    if (dev < 0 || dev >= MAX_DEVICES) return 148;
+    if (!cached[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev] = v;
+    }
+    return cached[dev];
+}
+// experiment switch (read once): LGP_GEMM_SMALL=0 keeps the throughput tiles everywhere
+static bool gemm_small_disabled() {
+    static const bool v = [] {
+        const char *e = getenv("LGP_GEMM_SMALL");
+        return e && e[0] == '0';
+    }();
+    return v;
 }
 
 template <class Cfg>
@@ -56,16 +78,27 @@ int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int
         p.mir = *mir;
     else
         memset(&p.mir, 0, sizeof(p.mir));
-    // tile configuration: the in-place products need the aliased dimension inside one tile
+    // tile configuration: the in-place products need the aliased dimension inside one tile; grids that would leave SMs
+    // idle with the throughput tiles use the latency tiles (4x the CTAs)
+    const int sms = sm_count();
     if (flags & GEMM_INPLACE_B) {
-        if (a_kmaj && !b_kmaj) return launch_cfg<GemmWide, true, false>(stream, p);
-        if (!a_kmaj && !b_kmaj) return launch_cfg<GemmWide, false, false>(stream, p);
+        const bool small = (N + 63) / 64 < sms && !gemm_small_disabled();
+        if (a_kmaj && !b_kmaj)
+            return small ? launch_cfg<GemmWideSmall, true, false>(stream, p) : launch_cfg<GemmWide, true, false>(stream, p);
+        if (!a_kmaj && !b_kmaj)
+            return small ? launch_cfg<GemmWideSmall, false, false>(stream, p)
+                         : launch_cfg<GemmWide, false, false>(stream, p);
         return LGP_ERR_UNSUPPORTED;
     }
     if (flags & GEMM_INPLACE_A) {
-        if (a_kmaj && b_kmaj) return launch_cfg<GemmTall, true, true>(stream, p);
+        const bool small = (M + 63) / 64 < sms && !gemm_small_disabled();
+        if (a_kmaj && b_kmaj)
+            return small ? launch_cfg<GemmTallSmall, true, true>(stream, p) : launch_cfg<GemmTall, true, true>(stream, p);
         return LGP_ERR_UNSUPPORTED;
     }
+    const int64_t tm = (M + 63) / 64, tn = (N + 63) / 64;
+    const int64_t tiles = (flags & GEMM_LOWER) ? tm * (tm + 1) / 2 : tm * tn;
+    if (tiles < sms && !gemm_small_disabled()) return launch_layout<GemmSmall>(stream, a_kmaj, b_kmaj, p);
     return launch_layout<GemmBig>(stream, a_kmaj, b_kmaj, p);
 }
 

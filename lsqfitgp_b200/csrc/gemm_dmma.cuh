@@ -102,6 +102,13 @@ struct GemmCfg {
 using GemmBig = GemmCfg<64, 64, 2, 2, 4, 3>;
 using GemmTall = GemmCfg<64, 128, 2, 4, 4, 2>;  // C aliases A (right-TRSM leaf): all N <= 128 columns in one tile
 using GemmWide = GemmCfg<128, 64, 4, 2, 4, 2>;  // C aliases B (left-solve leaf): all M <= 128 rows in one tile
+// Latency configurations for products whose grid would not even fill the SMs once (the panel chain of the factorisation's
+// tail, small matrices): a quarter of the tile area, so 4x the CTAs and a quarter of the dependent k-loop time per CTA
+// (a 64x64x128 tile is 8 k-tiles x 1024 cycles of DMMA issue on ONE SM = 4.2 us; 32x32: 1 us).  Small footprints (35 /
+// 57 KB, 128 threads) also fit into the slot a finishing GemmBig CTA frees.
+using GemmSmall = GemmCfg<32, 32, 2, 2, 4, 4>;
+using GemmTallSmall = GemmCfg<16, 128, 1, 4, 3, 3>;
+using GemmWideSmall = GemmCfg<128, 16, 4, 1, 3, 3>;
 
 template <bool KMAJ, int ROWS, int THREADS>
 __device__ __forceinline__ void gemm_load_tile(uint32_t smem_tile, const double *__restrict__ G, int64_t ld,

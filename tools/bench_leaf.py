@@ -13,7 +13,7 @@ A = torch.randn(128, 128, dtype=torch.float64, device=dev)
 K = A @ A.T + 128 * torch.eye(128, dtype=torch.float64, device=dev)
 L = torch.linalg.cholesky(K)
 Linv = torch.linalg.inv(L)
-for variant in (1, 2):
+for variant in (1, 2, 3):
     invd = torch.full((128, 128), 7.0, dtype=torch.float64, device=dev)
     dvec = torch.empty(128, dtype=torch.float64, device=dev)
     info = torch.full((1,), 2**31 - 1, dtype=torch.int32, device=dev)
@@ -30,6 +30,7 @@ for variant in (1, 2):
     print(f'   bad pivot reported at {int(info.item())} (expect 71)')
     reps = 50
     W = K.clone()
+    Ws = [K.clone() for _ in range(20)]
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -48,3 +49,23 @@ c = np.array(list(clk)[:18], dtype=np.int64)
 names = ['load', 'sync'] + sum([[f'potrf{J}', f'trtri/trsm{J}', f'update{J}'] for J in range(4)], []) + ['X d=1', 'X d=2', 'X d=3', 'store']
 d = np.diff(c)
 print('leaf2 phases (cycles):', ', '.join(f'{n} {v}' for n, v in zip(names[1:], d)), '| total', c[-1] - c[0])
+
+lib.lgp_debug_leaf3_clocks.argtypes = [ctypes.c_void_p]
+for rep in range(3):
+    W = K.clone()
+    lib.lgp_debug_leaf(_lib.stream_ptr(), _lib.ptr(W), 128, _lib.ptr(invd), _lib.ptr(dvec), _lib.ptr(info), 1, 3)
+    torch.cuda.synchronize()
+    lib.lgp_debug_leaf3_clocks(clk)
+    c = np.array(list(clk)[:10], dtype=np.int64)
+    names3 = ['load'] + sum([[f'panel{J}', f'colupd{J}'] for J in range(4)], [])[:-1] + ['store']
+    print('leaf3 phases (cycles):', ', '.join(f'{n} {v}' for n, v in zip(names3, np.diff(c))), '| total', c[-1] - c[0])
+# fresh (valid) input for every launch: time 20 leaves on 20 different matrices
+for variant in (1, 3):
+    Ws = [K.clone() for _ in range(20)]
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for Wi in Ws:
+        lib.lgp_debug_leaf(_lib.stream_ptr(), _lib.ptr(Wi), 128, _lib.ptr(invd), _lib.ptr(dvec), _lib.ptr(info), 1, variant)
+    e1.record(); torch.cuda.synchronize()
+    print(f'variant={variant}: {e0.elapsed_time(e1)*1e3/20:.1f} us per leaf (fresh inputs), L err {float((Ws[-1] - L).abs().max() / L.abs().max()):.2e}')
