@@ -13,7 +13,6 @@
 #include "common.cuh"
 #include "gemm_dmma.cuh"
 #include "internal.h"
-#include "chol_leaf2.cuh"
 #include "chol_leaf3.cuh"
 
 namespace lgp {
@@ -380,28 +379,19 @@ __global__ void finalize_info_kernel(int32_t *info, int n) {
 // ------------------------------------------------------------------------------------------------
 // 4. host-side recursion (all sizes in 128-blocks of the padded matrix)
 // ------------------------------------------------------------------------------------------------
-// Leaf selection: version 1 (register-resident, unblocked; above) is the product path.  Version 2 (chol_leaf2.cuh, blocked
-// 4 x 32) is bit-for-bit as accurate but measured no faster (67 us both; its phase breakdown is in DESIGN.md section 3):
-// kept selectable with LGP_LEAF=2 for kernel experiments only.
+// Leaf selection: version 3 (chol_leaf3.cuh) is the product path; version 1 (unblocked, register-resident; above) stays
+// selectable with LGP_LEAF=1 for A/B measurements.
 static int leaf_version() {
     static const int v = [] {
         const char *e = getenv("LGP_LEAF");
-        return e ? atoi(e) : 31;
+        return (e && e[0] == '1') ? 1 : 3;
     }();
     return v;
 }
 static cudaError_t leaf_set_attrs() {
     cudaError_t e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(potrf_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(potrf_leaf3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(potrf_leaf3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(potrf_leaf3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(potrf_leaf3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
+    return cudaFuncSetAttribute(potrf_leaf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
 }
 // the > 48 KB shared-memory opt-in is a per-device attribute: once per device, not once per process
 static int leaf_attr() {
@@ -428,17 +418,8 @@ static int panel_blocks() {
 }
 static void leaf_launch(cudaStream_t st, double *Wblk, int64_t ld, double *invd, double *dvec, int32_t *info, int j0,
                         int version = 0) {
-    const int v = version ? version : leaf_version();
-    if (v == 3)
-        potrf_leaf3_kernel<0><<<1, L3_THREADS, L3_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
-    else if (v == 31)
-        potrf_leaf3_kernel<1><<<1, L3_THREADS, L3_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
-    else if (v == 32)
-        potrf_leaf3_kernel<2><<<1, L3_THREADS, L3_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
-    else if (v == 33)
-        potrf_leaf3_kernel<3><<<1, L3_THREADS, L3_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
-    else if (v == 2)
-        potrf_leaf2_kernel<<<1, L2_THREADS, L2_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
+    if ((version ? version : leaf_version()) == 3)
+        potrf_leaf3_kernel<<<1, L3_THREADS, L3_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
     else
         potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(Wblk, ld, invd, dvec, info, j0);
 }
@@ -1066,11 +1047,7 @@ int lgp_debug_leaf(lgp_stream_t stream, double *Wblk, int64_t ld, double *invd, 
     return LGP_OK;
 }
 
-// debug hook: phase timestamps (SM clock cycles) of the last leaf-2 launch
-int lgp_debug_leaf2_clocks(long long *out32) {
-    return cudaMemcpyFromSymbol(out32, l2_dbg, 32 * sizeof(long long)) == cudaSuccess ? LGP_OK : LGP_ERR_CUDA;
-}
-
+// debug hook: phase timestamps (SM clock cycles) of the last leaf-3 launch
 int lgp_debug_leaf3_clocks(long long *out32) {
     return cudaMemcpyFromSymbol(out32, l3_dbg, 32 * sizeof(long long)) == cudaSuccess ? LGP_OK : LGP_ERR_CUDA;
 }

@@ -12,8 +12,8 @@
 //  * Augmented elimination: the combined array S holds A/L on and below the diagonal and Y = L^-T above it
 //    (S[r][c] = X[c][r] for r < c).  Eliminating the columns of [A; I] turns the bottom block into L^-T, so one sweep of
 //    four 32-column panels produces the factor and its inverse, and every row block of a panel is treated alike.
-//  * Inside a panel the column steps run in LDL^T form: a step needs 1/pivot (hardware estimate + two Newton steps, 5
-//    dependent DP instructions), not 1/sqrt(pivot) (~12); the square roots of the 32 pivots are taken once, in
+//  * Inside a panel the column steps run in LDL^T form: a step needs 1/pivot (hardware estimate + one third-order
+//    step, 3 dependent DFMAs), not 1/sqrt(pivot) (~12); the square roots of the 32 pivots are taken once, in
 //    parallel, after the last step, and every row is scaled then.  Step j of the chain warp (lane r = row r of the
 //    diagonal block): publish a_rj to shared memory, read column j back (broadcast 16-byte loads), t_r = a_rj / a_jj,
 //    a_rc -= t_r a_cj.  The entry of the next column is updated and published FIRST, the other 30 - j FMAs follow.
@@ -21,9 +21,11 @@
 //    L_JJ^-T) are four FOLLOWER warps, one row per lane, in lockstep with the chain warp: the chain warp publishes
 //    t_cj = a_cj / a_jj per step behind a shared-memory mbarrier, a follower does p_rc -= p_rj t_cj.  The triangular
 //    solves of the panel therefore cost nothing after the last column step.
-//  * Rank-32 updates on the FP64 tensor pipe (DMMA 8x8x4 from shared memory, two accumulator sets per unit).  Only the
-//    next panel's block column (4 blocks) is updated between two panels; the remaining blocks and the global stores of
-//    the finished block column are done by the three spare warps WHILE the next panel's chain runs.
+//  * Rank-32 updates on the FP64 tensor pipe (DMMA 8x8x4 from shared memory, 16 independent accumulator tiles per warp).
+//    Only the next panel's block column (4 blocks) is updated between two panels; the remaining blocks are done by the
+//    three spare warps WHILE the next panel's chain runs.
+//  * Measured on B200 (phase clocks, tools/bench_leaf.py): load 3.5k cycles, panels 7.0-8.7k each (~220 cycles per
+//    column step), block-column updates 3.3k each (DMMA issue bound is 2k), stores 10k: 55k cycles = 28 us + launch.
 #pragma once
 #include "common.cuh"
 
@@ -41,9 +43,7 @@ constexpr int L3_OFF_TS = L3_OFF_RAW + L3_B * L3_B;
 constexpr int L3_OFF_XD = L3_OFF_TS + L3_B * L3_B;
 constexpr int L3_OFF_RL = L3_OFF_XD + 2 * L3_B * L3_XS;
 constexpr int L3_OFF_BAR = L3_OFF_RL + 128;
-constexpr int L3_OFF_STG = L3_OFF_BAR + 32;  // 4096 doubles: staging of one half of a block column's outputs (bulk stores)
-constexpr int L3_SMEM_BYTES = (L3_OFF_STG + 4096) * 8;
-static_assert(L3_OFF_STG % 2 == 0, "16-byte alignment of the bulk-store staging buffer");
+constexpr int L3_SMEM_BYTES = (L3_OFF_BAR + 32) * 8;
 static_assert(L3_OFF_RAW % 2 == 0 && L3_OFF_TS % 2 == 0, "16-byte alignment of the broadcast buffers");
 
 __device__ __forceinline__ void l3_mbar_init(uint32_t a, int count) {
@@ -223,99 +223,56 @@ __device__ __forceinline__ void l3_update_unit(double *__restrict__ S, const dou
         l3_unit(S + (I * L3_B) * L3_S + Js * L3_B, L3_S, pb, L3_S, pc, L3_S, lane);
 }
 
-// global stores of the finished block column Jp: L[:, Jp] (zeros above the diagonal) and rows Jp of X = L^-1; eight
-// independent shared-memory loads in flight per thread
-template <int NT>
+// Global stores of block column Jp: L[:, Jp] (zeros above the diagonal) and rows Jp of X = L^-1.  16-byte stores, two
+// adjacent output entries per thread read from S with two 8-byte loads (odd row stride), eight in flight.  One SM moves
+// ~25 bytes per cycle towards L2, so the 256 KB of output cost ~10 000 cycles whatever the instruction mix, and stores
+// issued EARLY (block column J-1 during panel J, by the spare warps or by the bulk-copy engine) slowed the shared-memory
+// traffic of the following update phase by more than they saved (measured: 39.7 / 45.3 us per leaf against 31.0): all
+// outputs leave at the end.
+template <int NT, bool VEC>
 __device__ __forceinline__ void l3_store_colblock(const double *__restrict__ S, const double *__restrict__ RL,
-                                                  double *__restrict__ Wblk, int64_t ld, double *__restrict__ invd, int Jp,
-                                                  int t) {
+                                                     double *__restrict__ Wblk, int64_t ld, double *__restrict__ invd,
+                                                     int Jp, int t) {
     const int c0 = Jp * L3_B;
-    constexpr int NEL = 128 * L3_B;
-    for (int base = t; base < NEL; base += 8 * NT) {
-        double v[8];
+    constexpr int NEL2 = 128 * L3_B / 2;
+    for (int base = t; base < NEL2; base += 8 * NT) {
+        double2 v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int idx = base + k * NT;
-            const int r = idx >> 5, c = c0 + (idx & 31);
-            v[k] = (idx < NEL && r >= c) ? S[r * L3_S + c] : 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int idx = base + k * NT;
-            if (idx < NEL) Wblk[(int64_t)(idx >> 5) * ld + c0 + (idx & 31)] = v[k];
-        }
-    }
-    for (int base = t; base < NEL; base += 8 * NT) {
-        double v[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int idx = base + k * NT;
-            const int i = c0 + (idx >> 7), r = idx & 127;  // X[i][r]
-            v[k] = (idx < NEL) ? ((r < i) ? S[r * L3_S + i] : ((r == i) ? RL[i] : 0.0)) : 0.0;
+            const int r = idx >> 4, c = c0 + 2 * (idx & 15);
+            v[k].x = (idx < NEL2 && r >= c) ? S[r * L3_S + c] : 0.0;
+            v[k].y = (idx < NEL2 && r >= c + 1) ? S[r * L3_S + c + 1] : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int idx = base + k * NT;
-            if (idx < NEL) invd[(c0 + (idx >> 7)) * 128 + (idx & 127)] = v[k];
+            if (idx < NEL2) {
+                double *dst = Wblk + (int64_t)(idx >> 4) * ld + c0 + 2 * (idx & 15);
+                if (VEC) {
+                    *reinterpret_cast<double2 *>(dst) = v[k];
+                } else {
+                    dst[0] = v[k].x;
+                    dst[1] = v[k].y;
+                }
+            }
         }
     }
-}
-
-// Same through the bulk-copy engine: the outputs are staged row by row in a contiguous, 16-byte aligned buffer (the
-// rows of S have an odd stride; the rows of X are columns of S) and leave as cp.async.bulk copies of 256 / 1024 bytes.
-template <int NT, int BARID>
-__device__ __forceinline__ void l3_group_sync() {
-    if (NT == L3_THREADS)
-        __syncthreads();
-    else
-        asm volatile("bar.sync %0, %1;" ::"n"(BARID), "n"(NT) : "memory");
-}
-__device__ __forceinline__ void l3_bulk_store(double *dst, const double *src, int bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
-                 : "memory");
-}
-template <int NT, int BARID>
-__device__ __forceinline__ void l3_store_colblock_bulk(const double *__restrict__ S, const double *__restrict__ RL,
-                                                       double *__restrict__ STG, double *__restrict__ Wblk, int64_t ld,
-                                                       double *__restrict__ invd, int Jp, int t) {
-    const int c0 = Jp * L3_B;
-    constexpr int NEL = 128 * L3_B;
-    for (int base = t; base < NEL; base += 4 * NT) {
-        double v[4];
+    for (int base = t; base < NEL2; base += 8 * NT) {
+        double2 v[8];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 8; k++) {
             const int idx = base + k * NT;
-            const int r = idx >> 5, c = c0 + (idx & 31);
-            v[k] = (idx < NEL && r >= c) ? S[r * L3_S + c] : 0.0;
+            const int i = c0 + (idx >> 6), r = 2 * (idx & 63);  // X[i][r], X[i][r + 1]
+            v[k].x = (idx < NEL2) ? ((r < i) ? S[r * L3_S + i] : ((r == i) ? RL[i] : 0.0)) : 0.0;
+            v[k].y = (idx < NEL2) ? ((r + 1 < i) ? S[(r + 1) * L3_S + i] : ((r + 1 == i) ? RL[i] : 0.0)) : 0.0;
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (base + k * NT < NEL) STG[base + k * NT] = v[k];
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    l3_group_sync<NT, BARID>();
-    for (int r = t; r < 128; r += NT) l3_bulk_store(Wblk + (int64_t)r * ld + c0, STG + r * L3_B, L3_B * 8);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    l3_group_sync<NT, BARID>();
-    for (int base = t; base < NEL; base += 4 * NT) {
-        double v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 8; k++) {
             const int idx = base + k * NT;
-            const int i = c0 + (idx >> 7), r = idx & 127;  // X[i][r]
-            v[k] = (idx < NEL) ? ((r < i) ? S[r * L3_S + i] : ((r == i) ? RL[i] : 0.0)) : 0.0;
+            if (idx < NEL2) *reinterpret_cast<double2 *>(invd + (c0 + (idx >> 6)) * 128 + 2 * (idx & 63)) = v[k];
         }
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (base + k * NT < NEL) STG[base + k * NT] = v[k];
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    l3_group_sync<NT, BARID>();
-    for (int i = t; i < L3_B; i += NT) l3_bulk_store(invd + (c0 + i) * 128, STG + i * 128, 128 * 8);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    l3_group_sync<NT, BARID>();
 }
 
 __device__ long long l3_dbg[32];  // phase timestamps of the last launch (clock64 of thread 0): lgp_debug_leaf3_clocks
@@ -324,9 +281,6 @@ __device__ long long l3_dbg[32];  // phase timestamps of the last launch (clock6
         if (tid == 0) l3_dbg[i] = clock64(); \
     } while (0)
 
-// MODE (experiments): 0 thread stores, block column J-1 during panel J; 1 thread stores, everything at the end; 2 no
-// global stores at all (timing only); 3 bulk stores, block column J-1 during panel J
-template <int MODE>
 __global__ void __launch_bounds__(L3_THREADS, 1) potrf_leaf3_kernel(double *__restrict__ Wblk, int64_t ld,
                                                                    double *__restrict__ invd,
                                                                    double *__restrict__ dvec,
@@ -337,31 +291,40 @@ __global__ void __launch_bounds__(L3_THREADS, 1) potrf_leaf3_kernel(double *__re
     double *TS = S + L3_OFF_TS;
     double *XD = S + L3_OFF_XD;
     double *RL = S + L3_OFF_RL;
-    double *STG = S + L3_OFF_STG;
     const uint32_t bar0 = smem_u32(S + L3_OFF_BAR);
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
 
     L3_STAMP(0);
     if (tid < 32) l3_mbar_init(bar0 + 8 * tid, 1);
-    // lower triangle in (cp.async, everything in flight at once): block column 0 first, the panel-0 chain starts on it
-    // while the other three block columns are still arriving
-    for (int idx = tid; idx < 128 * L3_B; idx += L3_THREADS) {
-        const int r = idx >> 5, c = idx & 31;
-        if (r >= c)
-            cp_async8(smem_u32(S + r * L3_S + c), Wblk + (int64_t)r * ld + c);
-        else
-            S[r * L3_S + c] = 0.0;
+    // lower triangle in, 16-byte loads with eight in flight per thread: block column 0 by everybody (the panel-0 chain
+    // starts on it), the other three block columns by the spare warps while panel 0 runs
+    const bool vec = !((ld & 1) | (int64_t)(reinterpret_cast<uintptr_t>(Wblk) & 15));
+    {
+        double2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int idx = tid + k * L3_THREADS, r = idx >> 4, c = 2 * (idx & 15);
+            v[k] = make_double2(0.0, 0.0);
+            if (vec) {
+                if (r >= c) v[k] = *reinterpret_cast<const double2 *>(Wblk + (int64_t)r * ld + c);
+            } else {
+                if (r >= c) v[k].x = Wblk[(int64_t)r * ld + c];
+                if (r >= c + 1) v[k].y = Wblk[(int64_t)r * ld + c + 1];
+            }
+        }
+        // block columns 1..3 (rows 32..127): asynchronous copies queued behind the loads above, waited for after panel 0
+        for (int idx = tid; idx < 96 * 96; idx += L3_THREADS) {
+            const int r = 32 + idx / 96, c = 32 + idx % 96;
+            if (r >= c) cp_async8(smem_u32(S + r * L3_S + c), Wblk + (int64_t)r * ld + c);
+        }
+        cp_async_commit();
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int idx = tid + k * L3_THREADS, r = idx >> 4, c = 2 * (idx & 15);
+            S[r * L3_S + c] = v[k].x;
+            S[r * L3_S + c + 1] = (r >= c + 1) ? v[k].y : 0.0;
+        }
     }
-    cp_async_commit();
-    for (int idx = tid; idx < 128 * 96; idx += L3_THREADS) {
-        const int r = idx / 96, c = L3_B + idx % 96;
-        if (r >= c)
-            cp_async8(smem_u32(S + r * L3_S + c), Wblk + (int64_t)r * ld + c);
-        else
-            S[r * L3_S + c] = 0.0;
-    }
-    cp_async_commit();
-    cp_async_wait<1>();
     __syncthreads();
     L3_STAMP(1);
 
@@ -409,7 +372,15 @@ __global__ void __launch_bounds__(L3_THREADS, 1) potrf_leaf3_kernel(double *__re
             l3_follow(p, ts_s, rl_s, bar0, parity);
 #pragma unroll
             for (int c = 0; c < L3_B; c++) row[c] = p[c];
-        } else if (J > 0) {
+        } else if (J == 0) {
+            // spare warps during panel 0: zeros into the blocks above the block diagonal (Y starts as the identity, whose
+            // diagonal blocks the identity-row warp supplies)
+            const int t = (w - 5) * 32 + lane;
+            for (int idx = t; idx < 96 * 96; idx += L3_NSPARE * 32) {
+                const int r = idx / 96, c = 32 + idx % 96;
+                if ((r >> 5) < (c >> 5)) S[r * L3_S + c] = 0.0;
+            }
+        } else {
             // spare warps: blocks of the previous panel's update that the current panel does not touch, then the global
             // stores of the previous block column
             const int sw = w - 5, Js = J - 1;
@@ -420,8 +391,6 @@ __global__ void __launch_bounds__(L3_THREADS, 1) potrf_leaf3_kernel(double *__re
                     for (int hf = 0; hf < 2; hf++, cnt++)
                         if (cnt % L3_NSPARE == sw) l3_update_unit(S, XD, I, K, hf, Js, lane);
                 }
-            if (MODE == 0) l3_store_colblock<L3_NSPARE * 32>(S, RL, Wblk, ld, invd, Js, sw * 32 + lane);
-            if (MODE == 3) l3_store_colblock_bulk<L3_NSPARE * 32, 2>(S, RL, STG, Wblk, ld, invd, Js, sw * 32 + lane);
         }
         if (J == 0) cp_async_wait<0>();
         __syncthreads();
@@ -432,10 +401,10 @@ __global__ void __launch_bounds__(L3_THREADS, 1) potrf_leaf3_kernel(double *__re
         __syncthreads();
         L3_STAMP(3 + 2 * J);
     }
-    if (MODE == 0) l3_store_colblock<L3_THREADS>(S, RL, Wblk, ld, invd, 3, tid);
-    if (MODE == 1)
-        for (int Jp = 0; Jp < 4; Jp++) l3_store_colblock<L3_THREADS>(S, RL, Wblk, ld, invd, Jp, tid);
-    if (MODE == 3) l3_store_colblock_bulk<L3_THREADS, 0>(S, RL, STG, Wblk, ld, invd, 3, tid);
+    if (vec)
+        for (int Jp = 0; Jp < 4; Jp++) l3_store_colblock<L3_THREADS, true>(S, RL, Wblk, ld, invd, Jp, tid);
+    else
+        for (int Jp = 0; Jp < 4; Jp++) l3_store_colblock<L3_THREADS, false>(S, RL, Wblk, ld, invd, Jp, tid);
     L3_STAMP(9);
 }
 

@@ -19,8 +19,9 @@ def relerr(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
+# (grids below one CTA per SM run the 32x32 latency tiles, larger ones the 64x64 throughput tiles: both are covered)
 @pytest.mark.parametrize('M,N,K', [(128, 128, 128), (300, 200, 150), (257, 129, 77), (1, 1, 1), (64, 640, 33),
-                                   (1024, 512, 2048)])
+                                   (1024, 512, 2048), (1100, 900, 130), (1537, 1025, 50)])
 @pytest.mark.parametrize('akm', [True, False])
 @pytest.mark.parametrize('bkm', [True, False])
 def test_dgemm_layouts(M, N, K, akm, bkm):
@@ -57,6 +58,53 @@ def test_dgemm_flags():
     _ops.dgemm(_ops.as_aligned(L), _ops.as_aligned(X), Y, a_kmajor=False, b_kmajor=False, M=M, N=130, K=M,
                flags=_lib.GEMM_BETA0 | _lib.GEMM_A_UPPER_K)
     assert relerr(Y, L.T @ X) < 1e-13
+
+
+@pytest.mark.parametrize('M', [384, 1500])  # latency tiles / throughput tiles of the lower-triangular enumeration
+def test_dgemm_lower_both_tile_configurations(M):
+    K = 136
+    g = torch.Generator(device='cpu').manual_seed(M)
+    Aop = torch.randn(M, K, generator=g, dtype=torch.float64).to(dev())
+    C0 = torch.randn(M, M, generator=g, dtype=torch.float64).to(dev())
+    C = _ops.as_aligned(C0.clone())
+    _ops.dgemm(_ops.as_aligned(Aop), _ops.as_aligned(Aop), C, a_kmajor=True, b_kmajor=True, M=M, N=M, K=K, alpha=-1.0,
+               flags=_lib.GEMM_LOWER)
+    assert relerr(torch.tril(C), torch.tril(C0 - Aop @ Aop.T)) < 1e-13
+    assert torch.equal(torch.triu(C, 1), torch.triu(C0, 1))
+
+
+@pytest.mark.parametrize('t', [128, 256, 1024])
+def test_tile_potrf_leaf_against_torch(t):
+    """The 128x128 leaf (Cholesky factor + its inverse in one CTA, csrc/chol_leaf3.cuh) through lgp_tile_potrf: factor,
+    inverted diagonal blocks, diagonal, zeros above the diagonal, failure index.  The strict upper triangle of the input
+    is scratch and must be ignored."""
+    lib = _lib.load()
+    K = spd(t, 11 + t).to(dev())
+    L = torch.linalg.cholesky(K)
+    A = _ops.as_aligned(K + torch.triu(torch.full_like(K, 3.0), 1))
+    invd = torch.full((t // 128, 128, 128), 7.0, dtype=torch.float64, device=dev())
+    dvec = torch.zeros(t + 5, dtype=torch.float64, device=dev())
+    info = torch.full((1,), 2**31 - 1, dtype=torch.int32, device=dev())
+    rc = lib.lgp_tile_potrf(_lib.stream_ptr(), _lib.ptr(A), A.stride(0), t, _lib.ptr(invd), _lib.ptr(dvec), _lib.ptr(info), 5)
+    torch.cuda.synchronize()
+    assert rc == 0 and int(info.item()) == 2**31 - 1
+    assert relerr(torch.tril(A), L) < 1e-12
+    assert relerr(dvec[5:], torch.diagonal(L)) < 1e-13
+    for b in range(t // 128):
+        blk = slice(128 * b, 128 * (b + 1))
+        assert torch.equal(torch.triu(A[blk, blk], 1), torch.zeros(128, 128, dtype=torch.float64, device=dev()))
+        Xb = torch.linalg.inv(L[blk, blk])
+        assert relerr(invd[b], Xb) < 1e-11
+        assert torch.equal(torch.triu(invd[b], 1), torch.zeros(128, 128, dtype=torch.float64, device=dev()))
+    # first failing pivot (global, 1-based): column 70 of the second block if there is one
+    j = 70 + (128 if t > 128 else 0)
+    Kb = K.clone()
+    Kb[j, j] = -1.0
+    A = _ops.as_aligned(Kb)
+    info.fill_(2**31 - 1)
+    lib.lgp_tile_potrf(_lib.stream_ptr(), _lib.ptr(A), A.stride(0), t, _lib.ptr(invd), _lib.ptr(dvec), _lib.ptr(info), 5)
+    torch.cuda.synchronize()
+    assert int(info.item()) == 5 + j + 1
 
 
 def test_dgemm_rejects_misaligned():
