@@ -748,166 +748,299 @@ static void solve_upper_rec(SolveCtx &c, int jb, int nb) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// vector triangular solves (m == 1): one launch per 128-block, HBM-streaming GEMV updates
+// vector triangular solves (m == 1): ONE kernel per sweep, block rows chained by flags (decoupled look-back)
 // ------------------------------------------------------------------------------------------------
-__global__ void vec_scale_store_kernel(const double *src, double *dst, int64_t stride, int n,
-                                       const double *__restrict__ f);
-
-constexpr int TRSV_THREADS = 256;
-constexpr int TRSV_DIAG_THREADS = 1024;
-constexpr int TRSV_ROWS_PER_CTA = 64;  // forward update: 8 warps x 8 rows, all loads of a warp in flight at once
-
-// In-place blocked TRSV, two launches per 128-block:
-//   diag kernel  : b_j <- op(invd_j) b_j                        (one CTA of 32 warps, every load independent)
-//   update kernel: b[rest] -= op(L)[rest, j] b_j                (forward: rows below; backward: columns before)
+// In-place blocked TRSV.  Round 1 used two launches per 128-block (628 dependent launches for the two sweeps at n =
+// 20 000: 4.2 ms for 3.2 GB of traffic).  Here a sweep is one kernel of one CTA per 128-block row:
+//   forward  (L x = b):   CTA i:  x_i = invd_i (b_i / s_i - sum_{j < i} L_ij x_j)
+//   backward (L^T x = y): CTA i:  x_i = invd_i^T (y_i - sum_{j > i} L_ji^T x_j) / s_i
+// CTA i streams its block row (column) of L as the x_j become available, so that when x_{i-1} (x_{i+1}) is published
+// only one 128 x 128 product, prefetched into shared memory, and the product with the inverted diagonal block, prefetched
+// into registers, remain on the chain.  Block rows are handed out through an atomic ticket in dependency order, so a CTA
+// only ever waits for CTAs that are already running: no co-residency requirement, no cooperative launch.  Flags carry
+// the epoch of the launch and the ticket counter is never reset: nothing to clear between launches.
 // `stride` is the element stride of the vector (a column of a row-major n x m matrix).
+constexpr int TRSV_THREADS = 256;
+constexpr int TRSV_SMEM_BYTES = NB * NB * 8 + (8 * NB + 2 * NB + 8) * 8;
+
+__device__ __forceinline__ unsigned trsv_ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void trsv_st_release(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct TrsvArgs {
+    const double *W;
+    int64_t ldw;
+    const double *invd;
+    const double *sinv;  // 1/s (nullptr: no scaling)
+    const double *svec;  // s: the backward sweep publishes x = z / s and its consumers need z = x s (exact: powers of two)
+    double *b;
+    int64_t stride;
+    int n, nblk;
+    unsigned long long *counter;
+    unsigned long long base;
+    unsigned *flags;
+    unsigned epoch;
+};
+
 template <bool TRANS>
-__global__ void __launch_bounds__(TRSV_DIAG_THREADS) trsv_diag_kernel(const double *__restrict__ invd,
-                                                                      double *__restrict__ b, int64_t stride, int j0,
-                                                                      int n) {
-    __shared__ double bj[NB], xs[NB];
-    __shared__ double part[8][NB];
+__global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_sweep_kernel(const TrsvArgs a) {
+    extern __shared__ __align__(16) double tsm[];
+    double *Lbuf = tsm;                 // the last block of the chain: L_{i,i-1} (forward) / L_{i+1,i} (backward)
+    double *part = Lbuf + NB * NB;      // [8][128] partial sums
+    double *rhs = part + 8 * NB;        // [128]
+    double *xs = rhs + NB;              // [128]
+    int *ish = reinterpret_cast<int *>(xs + NB);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < NB) bj[tid] = (j0 + tid < n) ? b[(int64_t)(j0 + tid) * stride] : 0.0;
+    if (tid == 0) ish[0] = (int)(atomicAdd(a.counter, 1ULL) - a.base);
     __syncthreads();
+    const int ticket = ish[0];
+    const int i = TRANS ? a.nblk - 1 - ticket : ticket;
+    const int i0 = i * NB;
+    const double *invd = a.invd + (int64_t)i * NB * NB;
+    const int nchain = TRANS ? a.nblk - 1 - i : i;  // number of blocks x_j this CTA consumes
+
+    // ---- prefetch: the chain's last block into shared memory, the inverted diagonal block into registers
+    if (nchain > 0) {
+        const double *Lp = TRANS ? a.W + (int64_t)(i0 + NB) * a.ldw + i0 : a.W + (int64_t)i0 * a.ldw + (i0 - NB);
+        for (int ch = tid; ch < NB * NB / 2; ch += TRSV_THREADS) {
+            const int r = ch >> 6, c2 = ch & 63;
+            cp_async16(smem_u32(Lbuf + r * NB + 2 * c2), Lp + (int64_t)r * a.ldw + 2 * c2, 16);
+        }
+    }
+    cp_async_commit();
+    // forward: warp w owns rows 16w..16w+15, lanes along k (k = lane + 32 q); backward: thread (c4 = 4 lane, g = warp)
+    // owns columns c4..c4+3 and rows 16g..16g+15 of every block
+    double dv[16][4];
     if (!TRANS) {
-        // x[r] = sum_{k <= r} invd[r][k] b[k]: warp w owns rows 4w..4w+3, lanes along k
-        double v[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int r = 0; r < 16; r++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) v[i][q] = invd[(4 * warp + i) * NB + lane + 32 * q];
+            for (int q = 0; q < 4; q++) dv[r][q] = invd[(16 * warp + r) * NB + lane + 32 * q];
+    } else {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            double acc = 0.0;
+        for (int r = 0; r < 16; r++) {
+            const double4 v = *reinterpret_cast<const double4 *>(invd + (16 * warp + r) * NB + 4 * lane);
+            dv[r][0] = v.x, dv[r][1] = v.y, dv[r][2] = v.z, dv[r][3] = v.w;
+        }
+    }
+    // own right-hand side (forward: scaled by 1/s)
+    if (tid < NB) {
+        const int g = i0 + tid;
+        double v = (g < a.n) ? a.b[(int64_t)g * a.stride] : 0.0;
+        if (!TRANS && a.sinv && g < a.n) v *= a.sinv[g];
+        rhs[tid] = v;
+    }
+
+    double acc[16];
 #pragma unroll
-            for (int q = 0; q < 4; q++) acc += v[i][q] * bj[lane + 32 * q];  // invd is zero above the diagonal
-            acc = warp_sum(acc);
-            if (lane == 0) xs[4 * warp + i] = acc;
+    for (int r = 0; r < 16; r++) acc[r] = 0.0;
+    // one block of the chain: forward acc[r] (row 16 warp + r, partial over this lane's 4 columns) += L[r][4 lane..] . x;
+    // backward acc[0..3] (columns 4 lane.., partial over rows 16 warp..) += L[r][c] x[r]
+    auto block_product = [&](const double *Lp, int64_t ldl, int j0) {
+        if (!TRANS) {
+            double xv[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int g = j0 + 4 * lane + q;
+                xv[q] = (g < a.n) ? __ldcg(a.b + (int64_t)g * a.stride) : 0.0;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {  // eight 32-byte loads in flight
+                double4 l[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    l[r] = *reinterpret_cast<const double4 *>(Lp + (int64_t)(16 * warp + 8 * h + r) * ldl + 4 * lane);
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    acc[8 * h + r] += l[r].x * xv[0] + l[r].y * xv[1] + l[r].z * xv[2] + l[r].w * xv[3];
+            }
+        } else {
+            double xv[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int g = j0 + 16 * warp + r;
+                xv[r] = (g < a.n) ? __ldcg(a.b + (int64_t)g * a.stride) : 0.0;
+                if (a.svec && g < a.n) xv[r] *= a.svec[g];
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                double4 l[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    l[r] = *reinterpret_cast<const double4 *>(Lp + (int64_t)(16 * warp + 8 * h + r) * ldl + 4 * lane);
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    acc[0] += l[r].x * xv[8 * h + r];
+                    acc[1] += l[r].y * xv[8 * h + r];
+                    acc[2] += l[r].z * xv[8 * h + r];
+                    acc[3] += l[r].w * xv[8 * h + r];
+                }
+            }
+        }
+    };
+
+    // ---- the chain: blocks in dependency order (forward j = 0..i-1, backward j = nblk-1..i+1), the last one from Lbuf
+    int done = 0;  // blocks consumed; `ready` of them are known to be published
+    int ready = 0;
+    while (done < nchain) {
+        if (ready == done) {
+            if (tid == 0) {
+                int k = done;
+                // wait for the next one, then take every further one that is already there
+                while (trsv_ld_acquire(a.flags + (TRANS ? a.nblk - 1 - k : k)) != a.epoch) __nanosleep(32);
+                k++;
+                while (k < nchain && trsv_ld_acquire(a.flags + (TRANS ? a.nblk - 1 - k : k)) == a.epoch) k++;
+                ish[1] = k;
+            }
+            __syncthreads();
+            ready = ish[1];
+            __syncthreads();
+        }
+        for (; done < ready; done++) {
+            const int j = TRANS ? a.nblk - 1 - done : done;
+            if (done == nchain - 1) {
+                cp_async_wait<0>();
+                __syncthreads();
+                block_product(Lbuf, NB, j * NB);
+            } else {
+                const double *Lp = TRANS ? a.W + (int64_t)j * NB * a.ldw + i0 : a.W + (int64_t)i0 * a.ldw + (int64_t)j * NB;
+                block_product(Lp, a.ldw, j * NB);
+            }
+        }
+    }
+
+    // ---- rhs - sum, then the product with the inverted diagonal block
+    if (!TRANS) {
+        double mine = 0.0;  // lane r keeps the sum of row 16 warp + r
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const double s = warp_sum(acc[r]);
+            if (lane == r) mine = s;
+        }
+        __syncthreads();  // rhs is complete
+        if (lane < 16) rhs[16 * warp + lane] -= mine;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) s += dv[r][q] * rhs[lane + 32 * q];  // invd is zero above the diagonal
+            s = warp_sum(s);
+            if (lane == r) mine = s;
+        }
+        if (lane < 16) {
+            const int g = i0 + 16 * warp + lane;
+            if (g < a.n) a.b[(int64_t)g * a.stride] = mine;
         }
     } else {
-        // x[c] = sum_{k >= c} invd[k][c] b[k]: 8 threads per column, 16 k-values each
-        const int c = tid & 127, part_id = tid >> 7;
-        double v[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = invd[(part_id * 16 + i) * NB + c];
-        double acc = 0.0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) acc += v[i] * bj[part_id * 16 + i];
-        part[part_id][c] = acc;
+        for (int q = 0; q < 4; q++) part[warp * NB + 4 * lane + q] = acc[q];
         __syncthreads();
         if (tid < NB) {
-            double t = 0.0;
+            double s = 0.0;
 #pragma unroll
-            for (int q = 0; q < 8; q++) t += part[q][tid];
-            xs[tid] = t;
+            for (int g = 0; g < 8; g++) s += part[g * NB + tid];
+            rhs[tid] -= s;
+        }
+        __syncthreads();
+        // x[c] = sum_k invd[k][c] rhs[k]  (invd is zero above the diagonal)
+        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const double y = rhs[16 * warp + r];
+#pragma unroll
+            for (int q = 0; q < 4; q++) s4[q] += dv[r][q] * y;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) part[warp * NB + 4 * lane + q] = s4[q];
+        __syncthreads();
+        if (tid < NB) {
+            double s = 0.0;
+#pragma unroll
+            for (int g = 0; g < 8; g++) s += part[g * NB + tid];
+            const int g = i0 + tid;
+            if (g < a.n) a.b[(int64_t)g * a.stride] = a.sinv ? s * a.sinv[g] : s;
         }
     }
     __syncthreads();
-    if (tid < NB && j0 + tid < n) b[(int64_t)(j0 + tid) * stride] = xs[tid];
-}
-
-// forward: rows r >= j0+128: b[r] -= L[r][j0..j0+127] . x_j   (x_j = b_j, already solved)
-__global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_update_kernel(const double *__restrict__ W, int64_t ldw,
-                                                                       double *__restrict__ b, int64_t stride,
-                                                                       int j0, int n) {
-    __shared__ double xs[NB];
-    const int tid = threadIdx.x;
-    if (tid < NB) xs[tid] = b[(int64_t)(j0 + tid) * stride];
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    const int r0 = j0 + NB + TRSV_ROWS_PER_CTA * blockIdx.x + 8 * warp;
-    double xv[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) xv[q] = xs[4 * lane + q];
-    double4 l[8];
-    double old[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int r = r0 + i;
-        if (r < n) {
-            l[i] = *reinterpret_cast<const double4 *>(W + (int64_t)r * ldw + j0 + 4 * lane);
-            old[i] = (lane == 0) ? b[(int64_t)r * stride] : 0.0;
-        } else {
-            l[i] = make_double4(0.0, 0.0, 0.0, 0.0);
-            old[i] = 0.0;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        double acc = l[i].x * xv[0] + l[i].y * xv[1] + l[i].z * xv[2] + l[i].w * xv[3];
-        acc = warp_sum(acc);
-        if (lane == 0 && r0 + i < n) b[(int64_t)(r0 + i) * stride] = old[i] - acc;
+    if (tid == 0) {
+        __threadfence();
+        trsv_st_release(a.flags + i, a.epoch);
     }
 }
 
-// backward: columns c < j0: b[c] -= sum_{r < rows} L[j0+r][c] * x_j[r]; 2 threads per column (64 rows each)
-__global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_update_kernel(const double *__restrict__ W, int64_t ldw,
-                                                                       double *__restrict__ b, int64_t stride,
-                                                                       int j0, int n) {
-    __shared__ double xs[NB];
-    __shared__ double part[TRSV_THREADS / 2];
-    const int tid = threadIdx.x;
-    const int rows = min(NB, n - j0);
-    if (tid < NB) xs[tid] = (tid < rows) ? b[(int64_t)(j0 + tid) * stride] : 0.0;
-    __syncthreads();
-    const int cl = tid & 127, half = tid >> 7;
-    const int col = blockIdx.x * (TRSV_THREADS / 2) + cl;
-    double acc = 0.0;
-    if (col < j0) {
-        const double *Lp = W + (int64_t)(j0 + half * 64) * ldw + col;
-#pragma unroll
-        for (int r8 = 0; r8 < 64; r8 += 16) {
-            double v[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) v[i] = Lp[(int64_t)(r8 + i) * ldw];  // rows beyond n are identity padding
-#pragma unroll
-            for (int i = 0; i < 16; i++) acc += v[i] * xs[half * 64 + r8 + i];
-        }
-    }
-    if (half) part[cl] = acc;
-    __syncthreads();
-    if (!half && col < j0) b[(int64_t)col * stride] -= acc + part[cl];
-}
+// Flag workspace of the sweeps: one slot per (device, caller stream), allocated once; the host side hands out epochs and
+// ticket bases under the lock that also covers the launch, so that they follow the stream order of the launches.
+struct TrsvSlot {
+    cudaStream_t caller;
+    bool used;
+    unsigned long long *counter;
+    unsigned *flags;
+    unsigned long long base;
+    unsigned epoch;
+};
+constexpr int TRSV_SLOTS = 32;
+constexpr int TRSV_MAX_BLOCKS = 1 << 16;  // n up to 8.4 million
 
-static int trsv_inplace(cudaStream_t st, const double *W, int64_t ldw, const double *invd, const double *sinv, int n,
-                        double *b, int64_t stride, int trans) {
+static int trsv_inplace(cudaStream_t st, const double *W, int64_t ldw, const double *invd, const double *sinv,
+                        const double *svec, int n, double *b, int64_t stride, int trans) {
+    static std::mutex mu;
+    static TrsvSlot pools[MAX_DEVICES][TRSV_SLOTS];
+    static DeviceOnce attr;
     const int nblk = (n + NB - 1) / NB;
-    if (!trans) {
-        // L^-1 b = Lt^-1 (b / s): the scaling is applied when a block is first read.  Rows below the current
-        // block are updated before they are scaled, so scale the whole vector first (one tiny pass).
-        if (sinv) {
-            vec_scale_store_kernel<<<(n + 255) / 256, 256, 0, st>>>(b, b, stride, n, sinv);
-            LGP_CUDA_CHECK_LAUNCH();
-        }
-        for (int jb = 0; jb < nblk; jb++) {
-            const int j0 = jb * NB;
-            trsv_diag_kernel<false><<<1, TRSV_DIAG_THREADS, 0, st>>>(invd + (int64_t)jb * NB * NB, b, stride, j0, n);
-            LGP_CUDA_CHECK_LAUNCH();
-            const int rest = n - j0 - NB;
-            if (rest > 0) {
-                trsv_fwd_update_kernel<<<(rest + TRSV_ROWS_PER_CTA - 1) / TRSV_ROWS_PER_CTA, TRSV_THREADS, 0, st>>>(
-                    W, ldw, b, stride, j0, n);
-                LGP_CUDA_CHECK_LAUNCH();
-            }
-        }
-    } else {
-        // L^-T b = S^-1 Lt^-T b: scale each block by 1/s as it is finished
-        for (int jb = nblk - 1; jb >= 0; jb--) {
-            const int j0 = jb * NB;
-            trsv_diag_kernel<true><<<1, TRSV_DIAG_THREADS, 0, st>>>(invd + (int64_t)jb * NB * NB, b, stride, j0, n);
-            LGP_CUDA_CHECK_LAUNCH();
-            if (j0 > 0) {
-                trsv_bwd_update_kernel<<<(j0 + TRSV_THREADS / 2 - 1) / (TRSV_THREADS / 2), TRSV_THREADS, 0, st>>>(
-                    W, ldw, b, stride, j0, n);
-                LGP_CUDA_CHECK_LAUNCH();
-            }
-        }
-        if (sinv) {
-            vec_scale_store_kernel<<<(n + 255) / 256, 256, 0, st>>>(b, b, stride, n, sinv);
-            LGP_CUDA_CHECK_LAUNCH();
-        }
+    if (nblk > TRSV_MAX_BLOCKS) return LGP_ERR_UNSUPPORTED;
+    if ((ldw & 1) || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(invd) & 15)) return LGP_ERR_ALIGN;
+    const int dev = current_device();
+    if (dev < 0 || dev >= MAX_DEVICES) return LGP_ERR_CUDA;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!attr.done(dev)) {
+        if (cudaFuncSetAttribute(trsv_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM_BYTES) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(trsv_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM_BYTES) !=
+                cudaSuccess)
+            return LGP_ERR_CUDA;
+        attr.set(dev);
     }
+    TrsvSlot *slot = nullptr, *free_slot = nullptr;
+    for (int k = 0; k < TRSV_SLOTS; k++) {
+        TrsvSlot &s = pools[dev][k];
+        if (s.used && s.caller == st) {
+            slot = &s;
+            break;
+        }
+        if (!s.used && !free_slot) free_slot = &s;
+    }
+    if (!slot) {
+        if (!free_slot) return LGP_ERR_UNSUPPORTED;  // more than 32 distinct caller streams on one device
+        void *p = nullptr;
+        const size_t bytes = 256 + (size_t)TRSV_MAX_BLOCKS * sizeof(unsigned);
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return LGP_ERR_CUDA;
+        if (cudaMemset(p, 0, bytes) != cudaSuccess) return LGP_ERR_CUDA;
+        slot = free_slot;
+        slot->caller = st;
+        slot->used = true;
+        slot->counter = static_cast<unsigned long long *>(p);
+        slot->flags = reinterpret_cast<unsigned *>(static_cast<char *>(p) + 256);
+        slot->base = 0;
+        slot->epoch = 0;
+    }
+    if (++slot->epoch == 0) {
+        // the 32-bit epoch wrapped: flags of 2^32 launches ago could alias; clear them (stream-ordered)
+        if (cudaMemsetAsync(slot->flags, 0, (size_t)TRSV_MAX_BLOCKS * sizeof(unsigned), st) != cudaSuccess) return LGP_ERR_CUDA;
+        slot->epoch = 1;
+    }
+    TrsvArgs a{W, ldw, invd, sinv, svec, b, stride, n, nblk, slot->counter, slot->base, slot->flags, slot->epoch};
+    slot->base += (unsigned long long)nblk;
+    if (trans)
+        trsv_sweep_kernel<true><<<nblk, TRSV_THREADS, TRSV_SMEM_BYTES, st>>>(a);
+    else
+        trsv_sweep_kernel<false><<<nblk, TRSV_THREADS, TRSV_SMEM_BYTES, st>>>(a);
+    LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
 }
 
@@ -915,11 +1048,6 @@ __global__ void vec_scale_copy_kernel(const double *__restrict__ src, int64_t st
                                       const double *__restrict__ f) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[(int64_t)i * stride] * (f ? f[i] : 1.0);
-}
-__global__ void vec_scale_store_kernel(const double *src, double *dst, int64_t stride, int n,
-                                       const double *__restrict__ f) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[(int64_t)i * stride] = src[(int64_t)i * stride] * (f ? f[i] : 1.0);
 }
 
 // X = Lt^-1 (lower) out of place into X (ld = ldx); the strict upper triangle of X is scratch.
@@ -1060,7 +1188,7 @@ int lgp_chol_solve(lgp_stream_t stream, const double *W, int64_t ldw, const doub
     cudaStream_t st = (cudaStream_t)stream;
     const double *sinv = aux + LGP_AUX_SINV(npad);
     int64_t total = (int64_t)n * m;
-    if (m == 1) return trsv_inplace(st, W, ldw, aux + LGP_AUX_INVDIAG(npad), sinv, n, B, ldb, trans);
+    if (m == 1) return trsv_inplace(st, W, ldw, aux + LGP_AUX_INVDIAG(npad), sinv, aux + LGP_AUX_S(npad), n, B, ldb, trans);
     SolveCtx c{st, W, ldw, aux + LGP_AUX_INVDIAG(npad), n, B, ldb, m, LGP_OK};
     if (!trans) {
         row_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, ldb, n, m, sinv);
@@ -1354,7 +1482,7 @@ int lgp_flag_wait(lgp_stream_t stream, const uint64_t *flags, int n, uint64_t va
 int lgp_tile_trsv(lgp_stream_t stream, const double *L, int64_t ldl, const double *invd, int64_t t, double *b,
                   int trans) {
     if (t < NB || t % NB || !L || !invd || !b) return LGP_ERR_BADARG;
-    return trsv_inplace((cudaStream_t)stream, L, ldl, invd, nullptr, (int)t, b, 1, trans);
+    return trsv_inplace((cudaStream_t)stream, L, ldl, invd, nullptr, nullptr, (int)t, b, 1, trans);
 }
 
 int lgp_chol_logdet_quad(lgp_stream_t stream, const double *aux, int64_t n64, const double *a, double *out) {

@@ -170,6 +170,41 @@ def test_chol_unequal_scales_and_addmat():
     assert abs(sc[1] * sc[3] - do.eps) / do.eps < 1e-14
 
 
+@pytest.mark.parametrize('n', [1, 100, 128, 129, 333, 400, 1000, 2500])
+def test_vector_solves_match_matrix_solves(n):
+    """ m = 1 goes through the single-kernel look-back TRSV sweeps, m > 1 through the GEMM recursion: same results, with
+    unequal equilibration scales, for both sweeps, and against the oracle's factor """
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    K = A @ A.T / n + np.eye(n)
+    d = 2.0 ** rng.integers(-6, 6, n)
+    K = K * d[:, None] * d[None, :]
+    st = _ops.chol_factor(torch.tensor(K).to(dev()))
+    L = odecomp.Chol(K)._L
+    B = rng.standard_normal((n, 3))
+    Bd = torch.tensor(B).to(dev())
+    for trans in (False, True):
+        ref = sl.solve_triangular(L, B, lower=True, trans='T' if trans else 'N')
+        Xm = _ops.chol_solve(st, Bd, trans).cpu().numpy()[:, :3]
+        X1 = _ops.chol_solve(st, Bd[:, :1].contiguous(), trans).cpu().numpy()[:, 0]
+        scale = np.abs(ref).max()
+        assert np.abs(Xm - ref).max() / scale < 1e-10
+        assert np.abs(X1 - ref[:, 0]).max() / scale < 1e-10
+    # both sweeps in place on a strided vector (a column of a wider matrix), twice in a row on the same stream
+    wide = _ops.aligned_empty(n, 4, dev())
+    for rep in range(2):
+        wide.copy_(torch.tensor(np.concatenate([B, B[:, :1]], axis=1)).to(dev()))
+        col = wide[:, 2:3]  # (16-byte aligned: the C ABI requires it)
+        lib = _lib.load()
+        for trans in (0, 1):
+            _ops.check(lib.lgp_chol_solve(_lib.stream_ptr(), _lib.ptr(st.W), st.W.stride(0), _lib.ptr(st.aux), st.n,
+                                          col.data_ptr(), wide.stride(0), 1, trans), 'lgp_chol_solve')
+        ref = sl.cho_solve((L, True), B[:, 2])
+        got = wide.cpu().numpy()
+        assert np.abs(got[:, 2] - ref).max() / np.abs(ref).max() < 1e-9
+        assert np.array_equal(got[:, 1], B[:, 1]) and np.array_equal(got[:, 3], B[:, 0])  # neighbours untouched
+
+
 def test_chol_failure_reporting():
     K = torch.eye(200, dtype=torch.float64, device=dev())
     K[150, 150] = 1e-30
