@@ -47,7 +47,7 @@ UNIT = 'evals/s'
 FP64_DMMA_PEAK_FALLBACK = 37.0   # round-1 measurement (profiles/peaks_fp64_r1.log); the line reports the live probe
 
 # DRAM traffic of one lgp_chol_factor call at n=20000 comes from an ncu capture (it cannot be measured in this process)
-CHOL_TRAFFIC_BYTES_N20000 = 62.88e9
+CHOL_TRAFFIC_BYTES_N20000 = 82.90e9   # profiles/traffic_chol20k_r2.txt (68.9 GB read + 14.0 GB written)
 
 
 def make_data(n, seed=2002):
@@ -834,7 +834,7 @@ def run_gpu(args):
                           frac=chol_tflops / dmma_peak,
                           traffic=CHOL_TRAFFIC_BYTES_N20000 if n == 20000 else None,
                           traffic_source='ncu dram__bytes_read.sum + dram__bytes_write.sum over the kernels of one '
-                                         'lgp_chol_factor call at n=20000 (profiles/traffic_chol20k_r1.txt; ncu cannot run '
+                                         'lgp_chol_factor call at n=20000 (profiles/traffic_chol20k_r2.txt; ncu cannot run '
                                          'inside this process): 42.8 GB read + 20.1 GB written; the rank-512 right-looking '
                                          'update re-reads the trailing matrix once per panel (~43 GB); tensor-bound',
                           peak_source='measured in THIS run: register-resident DMMA.8x8x4 loop of the library '
