@@ -582,6 +582,13 @@ static int panel_width(int left, int pb) {
     return w < left ? w : left;
 }
 
+static int chain_blocks() {
+    static const int v = [] {
+        const char *e = getenv("LGP_CHAIN_BLOCKS");
+        return e ? atoi(e) : 32;
+    }();
+    return v;
+}
 static int first_blocks() {
     static const int v = [] {
         const char *e = getenv("LGP_FIRST_BLOCKS");
@@ -616,6 +623,7 @@ static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = null
     int rc = LGP_OK;
     int last = -1;
     cudaEvent_t e_colnext = nullptr;  // recorded on the main stream when the next panel's block column is updated
+    cudaEvent_t e_rest = nullptr;     // recorded on the main stream behind the rest of the previous trailing update
     int jb = 0;
     for (int j = 0; jb < nblk && rc == LGP_OK && ok; j++) {
         int w = panel_width(nblk - jb, pb);
@@ -623,7 +631,8 @@ static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = null
         if (j == 0 && w > first_blocks()) w = first_blocks();
         const int rest = nblk - jb - w;
         // ---- panel stream
-        if (j > 0) ok = ok && ev_wait(ps, e_colnext);
+        if (e_colnext) ok = ok && ev_wait(ps, e_colnext);
+        e_colnext = nullptr;
         if (trace) cudaEventRecord(t_pstart[j], ps);
         potrf_rec(cp, jb, w);
         if (rest > 0) trsm_right_rec(cp, jb + w, rest * NB, jb, w);
@@ -636,22 +645,47 @@ static int potrf_lookahead(CholCtx &cm, int nblk, int pb, PanelHook *hook = null
             hook->fired = true;
             hook->fn(hook->ctx, e_panel);
         }
-        // ---- main stream
-        ok = ok && ev_wait(cm.st, e_panel);
         const int w2 = panel_width(rest, pb);  // width of the next panel
         const int rest2 = rest - w2;
         const int K = w * NB;
-        // next block column (rows jb+w.., cols jb+w..jb+w+w2): one full GEMM; the part above the block
-        // diagonal is scratch (never read: leaves and LOWER kernels only touch r >= c)
-        rc = gemm_launch(cm.st, true, true, rest * NB, w2 * NB, K, -1.0, Wp(cm, jb + w, jb), cm.ldw, Wp(cm, jb + w, jb),
-                         cm.ldw, Wp(cm, jb + w, jb + w), cm.ldw, 0);
-        e_colnext = trace ? t_col[j] : ring_event();
-        ok = ok && ev_record(e_colnext, cm.st);
+        // Update of the next block column (rows jb+w.., cols jb+w..jb+w+w2): one full GEMM; the part above the block
+        // diagonal is scratch (never read: leaves and LOWER kernels only touch r >= c).  While the trailing matrix is
+        // large it runs on the main stream, in order behind the rest of the previous update.  In the chain-bound tail it
+        // stays on the panel stream: leaf -> TRSM -> column update -> next leaf then are launches of ONE stream, without
+        // the two cross-stream event hops per panel (it still waits for the previous rest update, which has long
+        // finished there).
+        // (measured on B200: at n <= 12 800 the whole factorisation is faster this way, 14.06 -> 13.68 ms at n = 10 000; at
+        // n = 20 000 only the last 32 blocks are)
+        const bool chain_on_ps = rest <= (nblk <= 100 ? nblk : chain_blocks());
+        if (chain_on_ps) {
+            if (e_rest) ok = ok && ev_wait(ps, e_rest);
+            rc = gemm_launch(ps, true, true, rest * NB, w2 * NB, K, -1.0, Wp(cm, jb + w, jb), cm.ldw, Wp(cm, jb + w, jb),
+                             cm.ldw, Wp(cm, jb + w, jb + w), cm.ldw, 0);
+            if (trace) cudaEventRecord(t_col[j], ps);
+            ok = ok && ev_wait(cm.st, e_panel);
+        } else {
+            ok = ok && ev_wait(cm.st, e_panel);
+            rc = gemm_launch(cm.st, true, true, rest * NB, w2 * NB, K, -1.0, Wp(cm, jb + w, jb), cm.ldw,
+                             Wp(cm, jb + w, jb), cm.ldw, Wp(cm, jb + w, jb + w), cm.ldw, 0);
+            e_colnext = trace ? t_col[j] : ring_event();
+            ok = ok && ev_record(e_colnext, cm.st);
+        }
         // rest of the trailing matrix
         if (rc == LGP_OK && rest2 > 0)
             rc = gemm_launch(cm.st, true, true, rest2 * NB, rest2 * NB, K, -1.0, Wp(cm, jb + w + w2, jb), cm.ldw,
                              Wp(cm, jb + w + w2, jb), cm.ldw, Wp(cm, jb + w + w2, jb + w + w2), cm.ldw, GEMM_LOWER);
-        if (trace) cudaEventRecord(t_restend[j], cm.st);
+        if (trace) {
+            cudaEventRecord(t_restend[j], cm.st);
+            e_rest = t_restend[j];
+        } else {
+            e_rest = ring_event();
+            ok = ok && ev_record(e_rest, cm.st);
+        }
+        if (chain_on_ps) {
+            // the join below must see the column update as well
+            e_last = ring_event();
+            ok = ok && ev_record(e_last, ps);
+        }
         jb += w;
     }
     if (e_last) ok = ev_wait(cm.st, e_last) && ok;  // join

@@ -252,14 +252,39 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS) gemm_dmma_kernel
 
     int tm, tn;
     if (p.flags & GEMM_LOWER) {
-        // blockIdx.x enumerates the tiles that touch the lower triangle, row by row: with BM = R*BN row tm
-        // has R*(tm+1) column tiles, so rows 0..tm-1 hold R*tm*(tm+1)/2 tiles
+        // blockIdx.x enumerates the tiles that touch the lower triangle: with BM = R*BN row tm has R*(tm+1) column
+        // tiles, so rows 0..tm-1 hold R*tm*(tm+1)/2 tiles
         constexpr int R = BM >= BN ? BM / BN : 1;  // (BM < BN configurations are never launched with LOWER)
         long long b = blockIdx.x;
         tm = (int)((sqrt(8.0 * (double)b / R + 1.0) - 1.0) * 0.5);
         while ((long long)R * (tm + 1) * (tm + 2) / 2 <= b) tm++;
         while ((long long)R * tm * (tm + 1) / 2 > b) tm--;
         tn = (int)(b - (long long)R * tm * (tm + 1) / 2);
+        if (R == 1) {
+            // Grouped rasterisation of the triangle: bands of GROUP tile rows, inside a band column by column (rows
+            // max(tn, r0)..r1 of column tn), so that a wave of CTAs shares GROUP row strips of A and ~wave/GROUP column
+            // strips of B out of L2.  Row by row, a wave spans one or two tile rows and streams EVERY column strip of B:
+            // with K = 1024 that is 160 MB per tile row at n = 20 000, more than L2 (the trailing updates of one
+            // factorisation read 64 GB from DRAM, profiles/traffic_chol20k_r2.txt).  Rows 0..r0-1 hold r0 (r0+1)/2
+            // tiles, so the band of tile b is the band of its row in the row-by-row order.
+            constexpr int GROUP = 16;
+            const int r0 = (tm / GROUP) * GROUP;
+            const int gs = min(GROUP, p.tiles_m - r0);
+            int local = (int)(b - (long long)r0 * (r0 + 1) / 2);
+            if (local < r0 * gs) {
+                tn = local / gs;
+                tm = r0 + local % gs;
+            } else {
+                local -= r0 * gs;
+                int c = 0;
+                while (local >= gs - c) {
+                    local -= gs - c;
+                    c++;
+                }
+                tn = r0 + c;
+                tm = r0 + c + local;
+            }
+        }
     } else {
         // Grouped rasterisation: the CTAs in flight at any time (one wave = 3 per SM) cover GROUP row tiles x ~wave/GROUP
         // column tiles, so that both operand streams are re-used out of L2.  (With the plain column-of-tiles-fastest
