@@ -12,13 +12,16 @@
  *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it and never synchronise
  *   - return value: 0 = launched ok; <0 = argument/launch error (LGP_ERR_*).  Numerical failure of the
  *     factorisation is reported in the device-side `info` word (LAPACK convention, 1-based pivot index)
- *   - no device memory is allocated inside the library (it creates a few CUDA streams and events on first use: one
- *     high-priority panel stream per caller stream, side streams for the inverse recursion)
+ *   - every matrix and vector the library works on is the caller's: nothing is allocated on the data path.  On first use
+ *     per device it creates a few CUDA streams and events (one high-priority panel stream per caller stream, side streams
+ *     for the inverse recursion) and, per caller stream that issues vector solves (lgp_chol_solve with m = 1,
+ *     lgp_tile_trsv), one 256 KiB flag workspace (cudaMalloc once: that first call synchronises the device)
  *   - thread safety: entry points may be called concurrently from several host threads on different streams
  *
  * Environment switches, for kernel experiments only (the product path needs none): LGP_TRACE (per-panel timeline of the
  * factorisation, synchronises), LGP_PANEL_BLOCKS (panel width in 128-blocks, default 4), LGP_GRAM_V3=0 (symmetric Gram
- * through the version-2 kernel), LGP_LEAF=2 (blocked 128x128 leaf of chol_leaf2.cuh).
+ * through the version-2 kernel), LGP_LEAF=1 (unblocked register-resident 128x128 leaf instead of chol_leaf3.cuh),
+ * LGP_TAIL_BLOCKS / LGP_FIRST_BLOCKS / LGP_CHAIN_BLOCKS (panel schedule), LGP_GEMM_SMALL=0 (no latency tiles).
  */
 #ifndef LGP_B200_H
 #define LGP_B200_H
@@ -270,7 +273,9 @@ int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const dou
                     double *aux, int32_t *info);
 
 /* B (n x m, ldb even, 16-byte aligned) <- L^-1 B (trans=0) or L^-T B (trans=1), L = diag(s) Lt.
- * Replaces jax.scipy.linalg.solve_triangular in _decomp.py:402-403,407-408,419,426,439,467-469. */
+ * Replaces jax.scipy.linalg.solve_triangular in _decomp.py:402-403,407-408,419,426,439,467-469.
+ * m = 1: ONE kernel per sweep (block rows chained by device flags in ticket order; up to 32 distinct caller streams per
+ * device, LGP_ERR_UNSUPPORTED beyond); m > 1: recursion over DMMA GEMMs with the inverted diagonal blocks. */
 int lgp_chol_solve(lgp_stream_t stream, const double *W, int64_t ldw, const double *aux, int64_t n, double *B,
                    int64_t ldb, int64_t m, int trans);
 

@@ -1054,7 +1054,8 @@ static int trsv_inplace(cudaStream_t st, const double *W, int64_t ldw, const dou
         void *p = nullptr;
         const size_t bytes = 256 + (size_t)TRSV_MAX_BLOCKS * sizeof(unsigned);
         if (cudaMalloc(&p, bytes) != cudaSuccess) return LGP_ERR_CUDA;
-        if (cudaMemset(p, 0, bytes) != cudaSuccess) return LGP_ERR_CUDA;
+        // cleared in stream order: cudaMemset runs on the NULL stream, which a non-blocking caller stream does not wait for
+        if (cudaMemsetAsync(p, 0, bytes, st) != cudaSuccess) return LGP_ERR_CUDA;
         slot = free_slot;
         slot->caller = st;
         slot->used = true;

@@ -205,6 +205,39 @@ def test_vector_solves_match_matrix_solves(n):
         assert np.array_equal(got[:, 1], B[:, 1]) and np.array_equal(got[:, 3], B[:, 0])  # neighbours untouched
 
 
+def test_vector_solves_on_fresh_streams():
+    """ first use of a caller stream allocates and clears the flag workspace of the TRSV sweeps IN STREAM ORDER (a
+    cudaMemset on the NULL stream raced with the first sweep on a non-blocking stream): several new streams, solved
+    right after their creation, from several host threads """
+    import threading
+    n = 1500
+    K = spd(n, 3).to(dev())
+    st = _ops.chol_factor(K)
+    y = torch.randn(n, 1, dtype=torch.float64, device=dev())
+    ref = _ops.chol_solve(st, _ops.chol_solve(st, y, False), True)
+    torch.cuda.synchronize()
+    outs, errs = {}, []
+
+    def work(k):
+        try:
+            s = torch.cuda.Stream(dev())
+            s.wait_stream(torch.cuda.default_stream(dev()))
+            with torch.cuda.stream(s):
+                for rep in range(3):
+                    outs[k, rep] = _ops.chol_solve(st, _ops.chol_solve(st, y, False), True)
+            s.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs
+    for v in outs.values():
+        assert torch.equal(v, ref)  # the sweeps are deterministic
+
+
 def test_chol_failure_reporting():
     K = torch.eye(200, dtype=torch.float64, device=dev())
     K[150, 150] = 1e-30
