@@ -835,8 +835,10 @@ def run_gpu(args):
                           traffic=CHOL_TRAFFIC_BYTES_N20000 if n == 20000 else None,
                           traffic_source='ncu dram__bytes_read.sum + dram__bytes_write.sum over the kernels of one '
                                          'lgp_chol_factor call at n=20000 (profiles/traffic_chol20k_r2.txt; ncu cannot run '
-                                         'inside this process): 42.8 GB read + 20.1 GB written; the rank-512 right-looking '
-                                         'update re-reads the trailing matrix once per panel (~43 GB); tensor-bound',
+                                         'inside this process): 68.9 GB read + 14.0 GB written, captured before the grouped '
+                                         'rasterisation of the lower-triangular tile enumeration; the right-looking updates '
+                                         're-read the trailing matrix once per panel and stream the panel strips; '
+                                         'tensor-bound (0.97 TB/s average)',
                           peak_source='measured in THIS run: register-resident DMMA.8x8x4 loop of the library '
                                       '(lgp_peak_probe), sustained over %.1f s; burst %.2f; MEASURED_PEAKS.json has no '
                                       'FP64 entry' % (peaks['dmma_sustained_seconds'], peaks['dmma_burst_TFLOPs']),
