@@ -1002,10 +1002,8 @@ __global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_sweep_kernel(const TrsvA
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        trsv_st_release(a.flags + i, a.epoch);
-    }
+    // (st.release.gpu orders the stores of the whole CTA, which thread 0 has observed through the barrier, before the flag)
+    if (tid == 0) trsv_st_release(a.flags + i, a.epoch);
 }
 
 // Flag workspace of the sweeps: one slot per (device, caller stream), allocated once; the host side hands out epochs and
