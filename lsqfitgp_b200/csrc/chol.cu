@@ -326,13 +326,6 @@ __global__ void get_factor_kernel(const double *__restrict__ W, int64_t ldw, con
 }
 
 // Kinv_ij *= sinv_i * sinv_j on the lower triangle (undo the equilibration of the inverse)
-__global__ void sym_scale_lower_kernel(double *__restrict__ A, int64_t lda, int n, const double *__restrict__ f) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = blockIdx.y + GRID_Y_MAX * blockIdx.z;
-    if (j > i || i >= n) return;
-    A[(int64_t)i * lda + j] = (A[(int64_t)i * lda + j] * f[j]) * f[i];
-}
-
 __global__ void copy_block_kernel(const double *__restrict__ src, int64_t lds, double *__restrict__ dst, int64_t ldd,
                                   int rows, int cols) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1289,13 +1282,11 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
     trtri_rec(c, 0, npad / NB);
     if (c.rc) return c.rc;
     if (trace) cudaEventRecord(t1, st);
-    // Kinv[i][j] = sum_{k >= i} X[k][i] X[k][j], j <= i   (LAUUM as one triangular-K SYRK launch)
+    // Kinv[i][j] = sum_{k >= i} X[k][i] X[k][j] / (s_i s_j), j <= i   (LAUUM as one triangular-K SYRK launch; the
+    // equilibration scales are applied in its epilogue: exact, powers of two)
     int rc = gemm_launch(st, false, false, npad, npad, npad, 1.0, scratch, npad, scratch, npad, Kinv, ldk,
-                         GEMM_BETA0 | GEMM_LOWER | GEMM_A_UPPER_K);
+                         GEMM_BETA0 | GEMM_LOWER | GEMM_A_UPPER_K, nullptr, aux + LGP_AUX_SINV(npad));
     if (rc) return rc;
-    dim3 g = rows_grid(n, n);
-    sym_scale_lower_kernel<<<g, 256, 0, st>>>(Kinv, ldk, n, aux + LGP_AUX_SINV(npad));
-    LGP_CUDA_CHECK_LAUNCH();
     if (trace) {
         cudaEventRecord(t2, st);
         cudaEventSynchronize(t2);
@@ -1412,11 +1403,8 @@ int lgp_chol_factor_inverse(lgp_stream_t stream, lgp_stream_t inv_stream, const 
     }
     if (ci.rc) return ci.rc;
     int rc = gemm_launch(si, false, false, npad, npad, npad, 1.0, scratch, npad, scratch, npad, Kinv, ldkinv,
-                         GEMM_BETA0 | GEMM_LOWER | GEMM_A_UPPER_K);
+                         GEMM_BETA0 | GEMM_LOWER | GEMM_A_UPPER_K, nullptr, aux + LGP_AUX_SINV(npad));
     if (rc) return rc;
-    dim3 g = rows_grid(n, n);
-    sym_scale_lower_kernel<<<g, 256, 0, si>>>(Kinv, ldkinv, n, aux + LGP_AUX_SINV(npad));
-    LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
 }
 

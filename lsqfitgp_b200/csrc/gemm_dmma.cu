@@ -57,7 +57,8 @@ static int launch_layout(cudaStream_t stream, bool a_kmaj, bool b_kmaj, GemmPara
 
 // Host-side launcher (internal; the C ABI wrapper is lgp_dgemm in capi.cu).
 int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int K, double alpha, const double *A,
-                int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int flags, const GemmMirror *mir) {
+                int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int flags, const GemmMirror *mir,
+                const double *scale) {
     if (M <= 0 || N <= 0) return LGP_OK;
     if (mir && (mir->n < 0 || mir->n > GEMM_MAX_MIRRORS || (mir->multimem && mir->n != 1))) return LGP_ERR_BADARG;
     if (mir)
@@ -74,6 +75,7 @@ int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.alpha = alpha;
     p.flags = flags;
+    p.scale = scale;
     if (mir)
         p.mir = *mir;
     else

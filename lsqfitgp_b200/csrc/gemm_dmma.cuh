@@ -55,6 +55,8 @@ struct GemmParams {
     double alpha;
     int flags;
     int tiles_m, tiles_n;
+    const double *scale;  // optional: C[i][j] = (alpha acc[i][j] * scale[j]) * scale[i] (+ C): the equilibration scales of the
+                          // inverse applied in the epilogue instead of a separate pass over the matrix; needs N entries
     GemmMirror mir;
 };
 
@@ -396,6 +398,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS) gemm_dmma_kernel
         const int cmax = lower ? min(p.N, row + 1) : p.N;  // exclusive bound on valid columns
         if (col >= cmax) return;
         double v0 = p.alpha * a0, v1 = p.alpha * a1;
+        if (p.scale) {
+            const double sr = p.scale[row];
+            v0 = (v0 * p.scale[col]) * sr;
+            if (col + 1 < cmax) v1 = (v1 * p.scale[col + 1]) * sr;
+        }
         if (vec_ok && col + 1 < cmax) {
             double2 *cp = reinterpret_cast<double2 *>(crow + col);
             if (!beta0) {

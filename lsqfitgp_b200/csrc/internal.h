@@ -11,7 +11,7 @@ constexpr int NB = 128;  // Cholesky leaf / distribution block
 struct GemmMirror;  // gemm_dmma.cuh: extra (peer / multicast) destinations of the epilogue
 int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int K, double alpha, const double *A,
                 int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int flags,
-                const GemmMirror *mir = nullptr);
+                const GemmMirror *mir = nullptr, const double *scale = nullptr);
 
 
 // ---- per-device bookkeeping (a process may drive several GPUs: stream pools, kernel attributes and events belong to ONE)
