@@ -306,6 +306,28 @@ int lgp_chol_factor_inverse(lgp_stream_t stream, lgp_stream_t inv_stream, const 
                             double epsabs, double *W, int64_t ldw, double *aux, int32_t *info, double *scratch,
                             double *Kinv, int64_t ldkinv);
 
+/* Gram build FUSED with the equilibration pass of the factorisation (north_star: "Gram epilogue -> equilibration / row
+ * sums"): for one set of points and a kernel of the fast family (ExpQuad, Matern nu = p + 1/2 with p <= 3, rational
+ * quadratic, each optionally + White + Constant) the entries K_ij / (s_i s_j), j <= i, are written straight into the
+ * npad x npad factor storage W (identity padding beyond n), s = 2^rint(log2(K_ii)/2) being uniform because the diagonal
+ * of a stationary kernel is constant, and the partial sums of |entry| per tile go to `work` and are reduced in a fixed
+ * order to the Gershgorin bound (aux scalar 0).  K itself is never written: it replaces _makecovblock_points
+ * (_GP/_elements.py:554-579) + diag_scale_pow2 / eigval_bound (_decomp.py:349-361,384-385) for that case, saving the
+ * 8 n^2-byte matrix, its mirror stores and the 12 n^2 bytes of the separate pass.  Returns LGP_ERR_UNSUPPORTED when the
+ * kernel is outside that family (the caller then uses lgp_gram_iso + lgp_chol_factor).  Follow it with
+ * lgp_chol_factor_prepared / lgp_chol_factor_inverse_prepared on the same stream.
+ * work: lgp_gram_prepare_work_doubles(n) doubles (= npad^2 / 64; may alias the `scratch` of the inverse). */
+int64_t lgp_gram_prepare_work_doubles(int64_t n);
+int lgp_gram_iso_prepare(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
+                         int64_t ldx, int64_t n, double *W, int64_t ldw, double *aux, double *work);
+/* lgp_chol_factor / lgp_chol_factor_inverse on a W / aux pair filled by lgp_gram_iso_prepare: jitter, factorisation (and
+ * inverse); same outputs as the plain calls (eps may differ in the last bits: the row sums are added in another order) */
+int lgp_chol_factor_prepared(lgp_stream_t stream, int64_t n, double epsrel, double epsabs, double *W, int64_t ldw,
+                             double *aux, int32_t *info);
+int lgp_chol_factor_inverse_prepared(lgp_stream_t stream, lgp_stream_t inv_stream, int64_t n, double epsrel, double epsabs,
+                                     double *W, int64_t ldw, double *aux, int32_t *info, double *scratch, double *Kinv,
+                                     int64_t ldkinv);
+
 /* out[0] = sum_i log L_ii ; out[1] = sum_i a_i^2 for a (n-vector, may be NULL -> 0).
  * The reductions of Chol.minus_log_normal_density (value), _decomp.py:484-488. */
 int lgp_chol_logdet_quad(lgp_stream_t stream, const double *aux, int64_t n, const double *a, double *out);

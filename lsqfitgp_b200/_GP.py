@@ -214,6 +214,11 @@ def _side_stream_for(main):
         return side
 
 
+def _fusable(kw):
+    """ solver keywords the fused Gram -> factor path understands """
+    return set(kw) <= {'epsrel', 'epsabs'}
+
+
 class _FusedNegLogMLFn(torch.autograd.Function):
     """ Gram -> Chol -> value in one node for the common case (one set of points, kernel-only covariance):
     the backward pass feeds the lower triangle of K^-1 and b = K^-1 r straight into the symmetric Gram-VJP
@@ -222,19 +227,21 @@ class _FusedNegLogMLFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, kern, xd, labels, r, kw, *params):
-        K = kern._gram_device(xd, xd, labels, symmetric=True)
-        _timing.mark('gp&cov')
-        if any(ctx.needs_input_grad[5:]):
-            # the gradient will need K^-1: factorisation and inverse-from-factor in ONE overlapped library call, the
-            # inverse on a persistent side stream: its leading half starts while the panel-chain-bound tail of the
-            # factorisation leaves SMs idle, and the latency-bound triangular solves below overlap its GEMMs
-            main = torch.cuda.current_stream()
-            side = _side_stream_for(main)
-            dec = _linalg.Chol(K, _inverse_stream=side, **kw)
+        # the gradient will need K^-1: factorisation and inverse-from-factor in ONE library call, the inverse on a
+        # persistent side stream (the latency-bound triangular solves below overlap its GEMMs)
+        side = _side_stream_for(torch.cuda.current_stream()) if any(ctx.needs_input_grad[5:]) else None
+        # kernels of the fast family: the Gram build writes the equilibrated lower triangle and the Gershgorin partial
+        # sums straight into the factor's storage (K itself is never materialised)
+        descs, _ = kern._descriptor(labels)
+        dec = _linalg.Chol._from_kernel(descs, xd, _inverse_stream=side, **kw) if _fusable(kw) else None
+        if dec is None:
+            K = kern._gram_device(xd, xd, labels, symmetric=True)
+            _timing.mark('gp&cov')
+            dec = _linalg.Chol(K, _inverse_stream=side, **kw) if side is not None else _linalg.Chol(K, **kw)
+            del K
         else:
-            dec = _linalg.Chol(K, **kw)
+            _timing.mark('gp&cov')
         _timing.mark('decomp')
-        del K
         ldq, a = dec.logdet_quad(r)
         ctx.kern, ctx.xd, ctx.labels, ctx.dec, ctx.a = kern, xd, labels, dec, a
         half = torch.tensor(0.5, dtype=f64, device=xd.device)

@@ -167,6 +167,31 @@ class Chol(Decomposition):
                 raise numpy.linalg.LinAlgError(
                     'cholesky decomposition not finite, probably matrix not pos def numerically')
 
+    @classmethod
+    def _from_kernel(cls, descs, xd, *, epsrel='auto', epsabs=0, _check=True, _inverse_stream=None):
+        """ Decomposition of the Gram matrix of `descs` on the points xd WITHOUT materialising it: Gram build fused with
+        the equilibration pass (lgp_gram_iso_prepare).  Returns None when the kernel is outside the fused family. """
+        out = _ops.gram_chol_factor(descs, xd, side=_inverse_stream, epsrel=epsrel, epsabs=epsabs)
+        if out is None:
+            return None
+        self = object.__new__(cls)
+        self._torch_in = True
+        self._K = self._Kd = None
+        self._addmat = self._adddiag = None
+        self._low = self._low_stream = None
+        if _inverse_stream is not None:
+            self._st, self._low = out
+            self._low_stream = _inverse_stream
+        else:
+            self._st = out
+        self._scal = None
+        if _check:
+            info = int(self._st.info.item())
+            if info != 0:
+                raise numpy.linalg.LinAlgError(
+                    'cholesky decomposition not finite, probably matrix not pos def numerically')
+        return self
+
     # ---- small helpers
     def _scalars(self):
         if self._scal is None:

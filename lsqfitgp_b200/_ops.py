@@ -453,6 +453,59 @@ def chol_factor_inverse(K, side, addmat=None, adddiag=None, epsrel='auto', epsab
     return st, Kinv[:n, :n]
 
 
+
+def gram_chol_factor(descs, x, side=None, epsrel='auto', epsabs=0.0):
+    """ Gram build fused with the equilibration pass of the factorisation (lgp_gram_iso_prepare), then the factorisation
+    (lgp_chol_factor_prepared) or, with a torch stream `side`, factorisation + inverse-from-factor
+    (lgp_chol_factor_inverse_prepared).  x: (ndim, n) float64 device tensor; the matrix K itself is never written.
+    Returns FactorState (side is None) or (FactorState, Kinv view) like chol_factor / chol_factor_inverse, or None when the
+    kernel is outside the fused family (the caller then builds the Gram matrix and factors it). """
+    lib = _lib.load()
+    ndim, n = x.shape
+    if ndim < 1 or n < 1:
+        return None
+    x = x.contiguous() if x.stride(1) != 1 else x
+    st = FactorState()
+    st.n = n
+    st.npad = int(lib.lgp_chol_npad(n))
+    st.device = x.device
+    st.W = torch.empty((st.npad, st.npad), dtype=f64, device=x.device)
+    st.aux = torch.empty(int(lib.lgp_chol_aux_doubles(n)), dtype=f64, device=x.device)
+    st.info = torch.empty(1, dtype=torch.int32, device=x.device)
+    main = torch.cuda.current_stream()
+    nwork = int(lib.lgp_gram_prepare_work_doubles(n))
+    if side is not None:
+        with torch.cuda.stream(side):   # the inverse buffers come from the side stream's allocator pool (kept warm there)
+            scratch = torch.empty((st.npad, st.npad), dtype=f64, device=x.device)
+            Kinv = torch.empty((st.npad, st.npad), dtype=f64, device=x.device)
+        # the partial row sums of the Gram build live in the inverse's scratch (unused until the factor is complete); it
+        # was allocated on the side stream: order the main stream behind whatever used that block there before
+        main.wait_stream(side)
+        work = scratch
+    else:
+        work = torch.empty(nwork, dtype=f64, device=x.device)
+    facs = make_factors(descs)
+    rc = lib.lgp_gram_iso_prepare(ctypes.c_void_p(main.cuda_stream), facs, len(descs), ndim, ptr(x), x.stride(0), n,
+                                  ptr(st.W), st.W.stride(0), ptr(st.aux), ptr(work))
+    if rc == -4:
+        return None
+    check(rc, 'lgp_gram_iso_prepare')
+    er = -1.0 if (isinstance(epsrel, str) and epsrel == 'auto') else float(epsrel)
+    ea = 2.220446049250313e-16 if (isinstance(epsabs, str) and epsabs == 'auto') else float(epsabs)
+    if side is None:
+        check(lib.lgp_chol_factor_prepared(ctypes.c_void_p(main.cuda_stream), n, er, ea, ptr(st.W), st.W.stride(0),
+                                           ptr(st.aux), ptr(st.info)), 'lgp_chol_factor_prepared')
+        return st
+    check(lib.lgp_chol_factor_inverse_prepared(ctypes.c_void_p(main.cuda_stream), ctypes.c_void_p(side.cuda_stream), n, er,
+                                               ea, ptr(st.W), st.W.stride(0), ptr(st.aux), ptr(st.info), ptr(scratch),
+                                               ptr(Kinv), Kinv.stride(0)), 'lgp_chol_factor_inverse_prepared')
+    for t in (st.W, st.aux):
+        t.record_stream(side)
+    scratch.record_stream(main)
+    del scratch
+    return st, Kinv[:n, :n]
+
+
 def chol_solve(st, B, trans, inplace=False):
     """ B: (n, m) device tensor -> L^-1 B (trans=False) or L^-T B (trans=True) """
     lib = _lib.load()

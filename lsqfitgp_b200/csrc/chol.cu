@@ -1162,21 +1162,25 @@ int64_t lgp_chol_aux_doubles(int64_t n) {
     return 3 * npad + 16 + (npad / NB) * (int64_t)NB * NB;
 }
 
-int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const double *addmat, int64_t ldadd,
-                    const double *adddiag, int64_t n64, double epsrel, double epsabs, double *W, int64_t ldw,
-                    double *aux, int32_t *info) {
-    if (n64 < 1 || n64 > (1 << 30) || !K || !W || !aux || !info) return LGP_ERR_BADARG;
+// `prepared`: W already holds the equilibrated lower triangle with identity padding, aux the scales and, in scalar 0, the
+// Gershgorin bound (lgp_gram_iso_prepare): the two passes over K are skipped
+static int chol_factor_impl(lgp_stream_t stream, bool prepared, const double *K, int64_t ldk, const double *addmat,
+                            int64_t ldadd, const double *adddiag, int64_t n64, double epsrel, double epsabs, double *W,
+                            int64_t ldw, double *aux, int32_t *info) {
+    if (n64 < 1 || n64 > (1 << 30) || (!prepared && !K) || !W || !aux || !info) return LGP_ERR_BADARG;
     const int n = (int)n64, npad = (int)lgp_chol_npad(n);
-    if (ldw < npad || ldk < n || (addmat && ldadd < n)) return LGP_ERR_BADARG;
+    if (ldw < npad || (!prepared && (ldk < n || (addmat && ldadd < n)))) return LGP_ERR_BADARG;
     if ((ldw & 1) || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(aux) & 15))
         return LGP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     if (leaf_attr()) return LGP_ERR_CUDA;
     if (epsrel < 0) epsrel = (double)n * 2.220446049250313e-16;
-    chol_diag_scale_kernel<<<(npad + 255) / 256, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, aux);
-    LGP_CUDA_CHECK_LAUNCH();
-    chol_prepare_kernel<<<(npad + 7) / 8, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, W, ldw, aux);
-    LGP_CUDA_CHECK_LAUNCH();
+    if (!prepared) {
+        chol_diag_scale_kernel<<<(npad + 255) / 256, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, aux);
+        LGP_CUDA_CHECK_LAUNCH();
+        chol_prepare_kernel<<<(npad + 7) / 8, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, W, ldw, aux);
+        LGP_CUDA_CHECK_LAUNCH();
+    }
     chol_jitter_kernel<<<1, 1024, 0, st>>>(n, npad, epsrel, epsabs, W, ldw, aux, info);
     LGP_CUDA_CHECK_LAUNCH();
     CholCtx c{st, W, ldw, aux + LGP_AUX_INVDIAG(npad), aux + LGP_AUX_DIAG(npad), info, LGP_OK};
@@ -1190,6 +1194,16 @@ int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const dou
                                            aux + LGP_AUX_SCALARS(npad) + 4);
     LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
+}
+
+int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const double *addmat, int64_t ldadd,
+                    const double *adddiag, int64_t n, double epsrel, double epsabs, double *W, int64_t ldw, double *aux,
+                    int32_t *info) {
+    return chol_factor_impl(stream, false, K, ldk, addmat, ldadd, adddiag, n, epsrel, epsabs, W, ldw, aux, info);
+}
+int lgp_chol_factor_prepared(lgp_stream_t stream, int64_t n, double epsrel, double epsabs, double *W, int64_t ldw,
+                             double *aux, int32_t *info) {
+    return chol_factor_impl(stream, true, nullptr, 0, nullptr, 0, nullptr, n, epsrel, epsabs, W, ldw, aux, info);
 }
 
 // debug/benchmark hook (not in the public header): run the 128x128 leaf `reps` times back to back
@@ -1328,13 +1342,13 @@ static void inverse_early_hook(void *ctx, cudaEvent_t panel_done) {
 }
 }  // namespace lgp
 
-int lgp_chol_factor_inverse(lgp_stream_t stream, lgp_stream_t inv_stream, const double *K, int64_t ldk,
-                            const double *addmat, int64_t ldadd, const double *adddiag, int64_t n64, double epsrel,
-                            double epsabs, double *W, int64_t ldw, double *aux, int32_t *info, double *scratch,
-                            double *Kinv, int64_t ldkinv) {
-    if (n64 < 1 || n64 > (1 << 30) || !K || !W || !aux || !info || !scratch || !Kinv) return LGP_ERR_BADARG;
+static int chol_factor_inverse_impl(lgp_stream_t stream, lgp_stream_t inv_stream, bool prepared, const double *K,
+                                    int64_t ldk, const double *addmat, int64_t ldadd, const double *adddiag, int64_t n64,
+                                    double epsrel, double epsabs, double *W, int64_t ldw, double *aux, int32_t *info,
+                                    double *scratch, double *Kinv, int64_t ldkinv) {
+    if (n64 < 1 || n64 > (1 << 30) || (!prepared && !K) || !W || !aux || !info || !scratch || !Kinv) return LGP_ERR_BADARG;
     const int n = (int)n64, npad = (int)lgp_chol_npad(n);
-    if (ldw < npad || ldk < n || (addmat && ldadd < n) || ldkinv < npad) return LGP_ERR_BADARG;
+    if (ldw < npad || (!prepared && (ldk < n || (addmat && ldadd < n))) || ldkinv < npad) return LGP_ERR_BADARG;
     if ((ldw & 1) || (ldkinv & 1) || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(aux) & 15) ||
         (reinterpret_cast<uintptr_t>(Kinv) & 15) || (reinterpret_cast<uintptr_t>(scratch) & 15))
         return LGP_ERR_ALIGN;
@@ -1346,10 +1360,12 @@ int lgp_chol_factor_inverse(lgp_stream_t stream, lgp_stream_t inv_stream, const 
         cudaEvent_t e0 = ring_event();
         if (!(ev_record(e0, st) && ev_wait(si, e0))) return LGP_ERR_CUDA;
     }
-    chol_diag_scale_kernel<<<(npad + 255) / 256, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, aux);
-    LGP_CUDA_CHECK_LAUNCH();
-    chol_prepare_kernel<<<(npad + 7) / 8, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, W, ldw, aux);
-    LGP_CUDA_CHECK_LAUNCH();
+    if (!prepared) {
+        chol_diag_scale_kernel<<<(npad + 255) / 256, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, aux);
+        LGP_CUDA_CHECK_LAUNCH();
+        chol_prepare_kernel<<<(npad + 7) / 8, 256, 0, st>>>(K, ldk, addmat, ldadd, adddiag, n, npad, W, ldw, aux);
+        LGP_CUDA_CHECK_LAUNCH();
+    }
     chol_jitter_kernel<<<1, 1024, 0, st>>>(n, npad, epsrel, epsabs, W, ldw, aux, info);
     LGP_CUDA_CHECK_LAUNCH();
     CholCtx c{st, W, ldw, aux + LGP_AUX_INVDIAG(npad), aux + LGP_AUX_DIAG(npad), info, LGP_OK};
@@ -1406,6 +1422,20 @@ int lgp_chol_factor_inverse(lgp_stream_t stream, lgp_stream_t inv_stream, const 
                          GEMM_BETA0 | GEMM_LOWER | GEMM_A_UPPER_K, nullptr, aux + LGP_AUX_SINV(npad));
     if (rc) return rc;
     return LGP_OK;
+}
+
+int lgp_chol_factor_inverse(lgp_stream_t stream, lgp_stream_t inv_stream, const double *K, int64_t ldk,
+                            const double *addmat, int64_t ldadd, const double *adddiag, int64_t n, double epsrel,
+                            double epsabs, double *W, int64_t ldw, double *aux, int32_t *info, double *scratch,
+                            double *Kinv, int64_t ldkinv) {
+    return chol_factor_inverse_impl(stream, inv_stream, false, K, ldk, addmat, ldadd, adddiag, n, epsrel, epsabs, W, ldw,
+                                    aux, info, scratch, Kinv, ldkinv);
+}
+int lgp_chol_factor_inverse_prepared(lgp_stream_t stream, lgp_stream_t inv_stream, int64_t n, double epsrel, double epsabs,
+                                     double *W, int64_t ldw, double *aux, int32_t *info, double *scratch, double *Kinv,
+                                     int64_t ldkinv) {
+    return chol_factor_inverse_impl(stream, inv_stream, true, nullptr, 0, nullptr, 0, nullptr, n, epsrel, epsabs, W, ldw,
+                                    aux, info, scratch, Kinv, ldkinv);
 }
 
 // ---- tile-level entry points: building blocks of the block-cyclic multi-GPU factorisation (lsqfitgp_b200/_dist.py)

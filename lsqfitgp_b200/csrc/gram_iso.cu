@@ -955,11 +955,22 @@ __global__ void __launch_bounds__(G_THREADS, 3) gram_fast2_kernel(const __grid_c
 //     128 bulk copies per tile instead of 4096 scattered 16-byte stores, and no thread waits on a global store.
 // Edge tiles (not fully inside the matrix) fall back to bounds-checked stores.
 // ------------------------------------------------------------------------------------------------
-template <int KIND, int P, int MINB>
+// PREP (lgp_gram_iso_prepare): the factorisation's input instead of K.  Same tiles, but (a) every entry is multiplied by
+// 1/s^2 (the power-of-two equilibration scale, uniform because the diagonal of a stationary kernel is constant: read from
+// prep.sinv), (b) only tiles on or below the diagonal are stored (no mirror image), into the npad x npad factor storage
+// whose rows / columns >= n are identity padding, (c) the sums of |entry| over the rows of the tile and, for the mirrored
+// half of the matrix, over its columns go to prep.rowpart[other tile index][row]: every (slot, row) pair is written exactly
+// once, so that the Gershgorin row sums (reference eigval_bound, _decomp.py:349-354) are reduced in a fixed order.
+struct GramPrep {
+    const double *sinv;  // aux + LGP_AUX_SINV: entry 0 = 1/s
+    double *rowpart;     // [npad / 64][npad]
+    int64_t npad;
+};
+template <int KIND, int P, int MINB, bool PREP>
 __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __grid_constant__ FastDesc d,
                                                                   const double *__restrict__ x, int64_t ldx, int64_t n,
                                                                   double *__restrict__ K, int64_t ldk, int vec_ok,
-                                                                  long long ntiles) {
+                                                                  long long ntiles, const GramPrep prep) {
     extern __shared__ __align__(16) double fsm[];
     const int nd = d.nd;
     constexpr int F_TABREP = FTabRep<KIND>::value;
@@ -1010,7 +1021,12 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
     const double rng0 = KIND == LGP_K_CAUCHY ? d.r2max : nu2;
     const bool white = d.has_white != 0;
     const bool mirror = tm != tn;
-    const bool interior = vec_ok && i0 + FT <= n && j0 + FT <= n;
+    const bool interior = PREP || (vec_ok && i0 + FT <= n && j0 + FT <= n);
+    double prep_scale = 1.0;
+    if (PREP) {
+        const double si = prep.sinv[0];
+        prep_scale = si * si;
+    }
 
 #pragma unroll 1
     for (int a0 = 0; a0 < 4; a0 += 2) {
@@ -1054,7 +1070,8 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
             for (int a = 0; a < 2; a++)
 #pragma unroll
                 for (int c = 0; c < 4; c++)
-                    if (fast2_out_of_range<KIND>(r2[a][c], rng0, par0, white))
+                    if (fast2_out_of_range<KIND>(r2[a][c], rng0, par0, white) &&
+                        !(PREP && (i0 + ty + 16 * (a0 + a) >= n || j0 + 2 * tx + 32 * (c >> 1) + (c & 1) >= n)))
                         val[a][c] = RAWSM ? fast2_slow_entry<KIND>(d, r2[a][c], d.white_raw ? ru : su, d.white_raw ? rv : sv,
                                                                    ty + 16 * (a0 + a), 2 * tx + 32 * (c >> 1) + (c & 1))
                                           : fast3_slow_entry<KIND>(d, r2[a][c], su, sv, x, ldx, i0 + ty + 16 * (a0 + a),
@@ -1066,6 +1083,21 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
             for (int a = 0; a < 2; a++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) val[a][c] = __dadd_rn(val[a][c], d.amp_const);
+        }
+        if (PREP) {
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) val[a][c] *= prep_scale;  // exact: power of two
+            if (i0 + FT > n) {  // last tile rows: identity padding beyond n
+#pragma unroll
+                for (int a = 0; a < 2; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int64_t i = i0 + ty + 16 * (a0 + a), j = j0 + 2 * tx + 32 * (c >> 1) + (c & 1);
+                        if (i >= n || j >= n) val[a][c] = (i == j) ? 1.0 : 0.0;
+                    }
+            }
         }
         if (a0 == 0) {
             // D / T of the previous tile may still be read by its bulk stores: the issuing threads wait, then everybody
@@ -1095,7 +1127,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
                 }
             }
         }
-        if (mirror) {
+        if (mirror && !PREP) {
 #pragma unroll
             for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -1106,9 +1138,25 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
     if (interior) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        if (PREP) {
+            // partial Gershgorin sums of the tile: threads 0..63 one row each (rotated start: conflict-free), threads
+            // 64..127 one column each (the rows of the mirror image)
+            const int q = tid & 63;
+            if (tid < FT) {
+                double sum = 0.0;
+#pragma unroll 8
+                for (int c = 0; c < FT; c++) sum += fabs(D[q * F2_TS + ((c + q) & (FT - 1))]);
+                prep.rowpart[(int64_t)tn * prep.npad + i0 + q] = sum;
+            } else if (mirror && tid < 2 * FT) {
+                double sum = 0.0;
+#pragma unroll 8
+                for (int r2_ = 0; r2_ < FT; r2_++) sum += fabs(D[r2_ * F2_TS + q]);
+                prep.rowpart[(int64_t)tm * prep.npad + j0 + q] = sum;
+            }
+        }
         // rows of the tile by threads 0..63, rows of its mirror image by threads 64..127
         const int r = tid & 63;
-        if (tid < FT || (mirror && tid < 2 * FT)) {
+        if (tid < FT || (mirror && !PREP && tid < 2 * FT)) {
             const bool second = tid >= FT;
             const uint32_t src = smem_u32((second ? T : D) + r * F2_TS);
             double *dst = second ? K + (j0 + r) * ldk + i0 : K + (i0 + r) * ldk + j0;
@@ -1117,7 +1165,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB) gram_fast3_kernel(const __gri
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             pending = true;
         }
-    } else if (mirror) {
+    } else if (mirror && !PREP) {
         __syncthreads();
         const int warp = tid >> 5, lane = tid & 31;
         for (int rr = warp; rr < FT; rr += G_THREADS / 32) {
@@ -1513,7 +1561,7 @@ static int launch_fast2(cudaStream_t st, const FastDesc &d, const double *x, int
         const int dev = current_device();
         if (dev < 0) return LGP_ERR_CUDA;
         if (!once.done(dev)) {
-            if (cudaFuncSetAttribute(gram_fast3_kernel<KIND, P, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            if (cudaFuncSetAttribute(gram_fast3_kernel<KIND, P, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      77400) != cudaSuccess ||
                 cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
                 return LGP_ERR_CUDA;
@@ -1530,7 +1578,8 @@ static int launch_fast2(cudaStream_t st, const FastDesc &d, const double *x, int
         }();
         const int64_t wave = waves > 0 ? (int64_t)3 * sm_count[dev] * waves : grid;
         const unsigned g3 = (unsigned)(grid < wave ? grid : wave);
-        gram_fast3_kernel<KIND, P, 3><<<g3, G_THREADS, smem, st>>>(d, x, ldx, n, K, ldk, vec_ok, (long long)grid);
+        gram_fast3_kernel<KIND, P, 3, false><<<g3, G_THREADS, smem, st>>>(d, x, ldx, n, K, ldk, vec_ok, (long long)grid,
+                                                                          GramPrep{nullptr, nullptr, 0});
     } else if (sym) {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(gram_fast2_kernel<KIND, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1545,6 +1594,109 @@ static int launch_fast2(cudaStream_t st, const FastDesc &d, const double *x, int
     LGP_CUDA_CHECK_LAUNCH();
     return LGP_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Gram build fused with the equilibration pass of the factorisation (lgp_gram_iso_prepare)
+// ------------------------------------------------------------------------------------------------
+// Diagonal value of the kernel matrix (the same for every point: stationary core at r2 = 0, plus White and Constant),
+// rounded like the entries the Gram kernel writes there, and s = 2^rint(log2(d)/2) (reference diag_scale_pow2,
+// _decomp.py:356-361): S / SINV of aux filled uniformly (1 for the padding rows), the 16 scalars zeroed.
+template <int KIND>
+__global__ void gram_prep_diag_kernel(const __grid_constant__ FastDesc d, int n, int npad, double *__restrict__ aux) {
+    double v = __dmul_rn(d.amp, fast_core<KIND>(d, 0.0));
+    if (d.has_white) v = __dadd_rn(v, d.amp_white);
+    if (d.has_const) v = __dadd_rn(v, d.amp_const);
+    double s = 1.0;
+    if (v != 0.0) s = exp2(rint(0.5 * log2(v)));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += gridDim.x * blockDim.x) {
+        aux[LGP_AUX_S(npad) + i] = (i < n) ? s : 1.0;
+        aux[LGP_AUX_SINV(npad) + i] = (i < n) ? 1.0 / s : 1.0;
+        if (i < 16) aux[LGP_AUX_SCALARS(npad) + i] = 0.0;
+    }
+}
+
+// max_i sum_slots rowpart[slot][i] over the rows i < n, slots in a fixed order -> scalars[0] (the Gershgorin bound)
+__global__ void __launch_bounds__(256) gram_prep_rowmax_kernel(const double *__restrict__ rowpart, int64_t npad, int slots,
+                                                               int n, double *__restrict__ aux) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double sum = 0.0;
+    if (i < n)
+        for (int s = 0; s < slots; s++) sum += rowpart[(int64_t)s * npad + i];
+    // max over the warp with NaN winning (a NaN row sum must reach eps like in the reference)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double u = __shfl_xor_sync(0xffffffffu, sum, o);
+        sum = (u > sum || u != u) ? u : sum;
+    }
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(reinterpret_cast<unsigned long long *>(aux + LGP_AUX_SCALARS(npad)),
+                  (unsigned long long)__double_as_longlong(sum));
+}
+
+template <int KIND, int P>
+static int launch_prepare(cudaStream_t st, const FastDesc &d, const double *x, int64_t ldx, int64_t n, double *W,
+                          int64_t ldw, double *aux, double *work) {
+    const int64_t npad = lgp_chol_npad(n);
+    // the diagonal must take the library (slow) path of the Gram kernel, which gram_prep_diag_kernel reproduces
+    if (!(d.has_white || KIND == LGP_K_EXPQUAD || KIND == LGP_K_CAUCHY || d.par0 == 0.0)) return LGP_ERR_UNSUPPORTED;
+    const size_t smem = 1024 * FTabRep<KIND>::value + (KIND == LGP_K_CAUCHY ? 2048 : 0) +
+                        (size_t)(2 + ((d.white_raw && FTabRep<KIND>::value == 1) ? 2 : 0)) * d.nd * FT * sizeof(double) +
+                        (size_t)2 * FT * F2_TS * 8;
+    if (smem > 77400) return LGP_ERR_UNSUPPORTED;
+    static DeviceOnce once;
+    const int dev = current_device();
+    if (dev < 0) return LGP_ERR_CUDA;
+    if (!once.done(dev)) {
+        if (cudaFuncSetAttribute(gram_fast3_kernel<KIND, P, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 77400) !=
+            cudaSuccess)
+            return LGP_ERR_CUDA;
+        once.set(dev);
+    }
+    const int64_t t = npad / FT, grid = t * (t + 1) / 2;
+    if (grid > 2147483647LL) return LGP_ERR_UNSUPPORTED;
+    gram_prep_diag_kernel<KIND><<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(d, (int)n, (int)npad, aux);
+    LGP_CUDA_CHECK_LAUNCH();
+    gram_fast3_kernel<KIND, P, 3, true><<<(unsigned)grid, G_THREADS, smem, st>>>(
+        d, x, ldx, n, W, ldw, 1, (long long)grid, GramPrep{aux + LGP_AUX_SINV(npad), work, npad});
+    LGP_CUDA_CHECK_LAUNCH();
+    gram_prep_rowmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(work, npad, (int)t, (int)n, aux);
+    LGP_CUDA_CHECK_LAUNCH();
+    return LGP_OK;
+}
+
+}  // namespace lgp
+
+extern "C" {
+
+int64_t lgp_gram_prepare_work_doubles(int64_t n) {
+    const int64_t npad = lgp_chol_npad(n);
+    return (npad / lgp::FT) * npad;
+}
+
+int lgp_gram_iso_prepare(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
+                         int64_t ldx, int64_t n, double *W, int64_t ldw, double *aux, double *work) {
+    using namespace lgp;
+    if (!factors || !x || !W || !aux || !work || n < 1 || n > (1 << 30)) return LGP_ERR_BADARG;
+    const int64_t npad = lgp_chol_npad(n);
+    if (ldw < npad) return LGP_ERR_BADARG;
+    if ((ldw & 1) || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(aux) & 15)) return LGP_ERR_ALIGN;
+    if (!(nfactors >= 1 && nfactors <= LGP_MAX_FACTORS && ndim >= 1 && ndim <= LGP_MAX_DIMS)) return LGP_ERR_UNSUPPORTED;
+    FastDesc fd;
+    if (!build_fast(factors, nfactors, ndim, fd)) return LGP_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fd.kind == LGP_K_EXPQUAD) return launch_prepare<LGP_K_EXPQUAD, 0>(st, fd, x, ldx, n, W, ldw, aux, work);
+    if (fd.kind == LGP_K_MATERNP && fd.p == 0) return launch_prepare<LGP_K_MATERNP, 0>(st, fd, x, ldx, n, W, ldw, aux, work);
+    if (fd.kind == LGP_K_MATERNP && fd.p == 1) return launch_prepare<LGP_K_MATERNP, 1>(st, fd, x, ldx, n, W, ldw, aux, work);
+    if (fd.kind == LGP_K_MATERNP && fd.p == 2) return launch_prepare<LGP_K_MATERNP, 2>(st, fd, x, ldx, n, W, ldw, aux, work);
+    if (fd.kind == LGP_K_MATERNP && fd.p == 3) return launch_prepare<LGP_K_MATERNP, 3>(st, fd, x, ldx, n, W, ldw, aux, work);
+    if (fd.kind == LGP_K_CAUCHY && fd.cauchy_fast) return launch_prepare<LGP_K_CAUCHY, 0>(st, fd, x, ldx, n, W, ldw, aux, work);
+    return LGP_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"
+
+namespace lgp {
 
 __global__ void zero_kernel(double *p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -238,6 +238,58 @@ def test_vector_solves_on_fresh_streams():
         assert torch.equal(v, ref)  # the sweeps are deterministic
 
 
+@pytest.mark.parametrize('n', [1, 64, 130, 333, 1000, 2111])
+@pytest.mark.parametrize('kind', ['expquad', 'matern12', 'matern52', 'matern72', 'cauchy', 'matern52_nowhite', 'const'])
+def test_gram_fused_with_equilibration_matches_two_pass(n, kind):
+    """ lgp_gram_iso_prepare + lgp_chol_factor[_inverse]_prepared (Gram build writing the equilibrated lower triangle and
+    the Gershgorin partial sums straight into the factor's storage) against lgp_gram_iso + lgp_chol_factor[_inverse]: same
+    scales (bit for bit), same eps up to the order of the row sums, same factor / logdet / inverse """
+    rng = np.random.default_rng(n)
+    x = torch.tensor(rng.uniform(0, 6, (2, n))).to(dev())
+    white = dict(kind=_lib.K_WHITE, term=1, dimmask=3, amp=0.3)
+    main = {'expquad': dict(kind=_lib.K_EXPQUAD, term=0, dimmask=3, scale_x=1.3, scale_y=1.3, amp=37.0),
+            'matern12': dict(kind=_lib.K_MATERNP, term=0, dimmask=3, ipar=0, par0=0.0, scale_x=2.0, scale_y=2.0, amp=1.0),
+            'matern52': dict(kind=_lib.K_MATERNP, term=0, dimmask=3, ipar=2, par0=0.0, scale_x=1.5, scale_y=1.5, amp=0.02),
+            'matern72': dict(kind=_lib.K_MATERNP, term=0, dimmask=3, ipar=3, par0=0.0, scale_x=0.7, scale_y=0.7, loc_x=0.5,
+                             loc_y=0.5, amp=5.0),
+            'cauchy': dict(kind=_lib.K_CAUCHY, term=0, dimmask=3, par0=2.0, par1=3.0, scale_x=1.1, scale_y=1.1, amp=1.0),
+            'matern52_nowhite': dict(kind=_lib.K_MATERNP, term=0, dimmask=3, ipar=2, par0=0.0, scale_x=0.4, scale_y=0.4,
+                                     amp=1.0),
+            'const': dict(kind=_lib.K_EXPQUAD, term=0, dimmask=3, scale_x=1.0, scale_y=1.0, amp=2.0)}[kind]
+    descs = [main] if kind == 'matern52_nowhite' else [main, white]
+    if kind == 'const':
+        descs = descs + [dict(kind=_lib.K_CONSTANT, term=2, dimmask=0, amp=0.7)]
+    K = _ops.gram_iso(descs, x, x, symmetric=True)
+    ref = _ops.chol_factor(K)
+    got = _ops.gram_chol_factor(descs, x)
+    assert got is not None
+    npad = ref.npad
+    assert torch.equal(got.aux[:2 * npad], ref.aux[:2 * npad])                      # s and 1/s
+    sr, sg = ref.scalars().cpu().numpy(), got.scalars().cpu().numpy()
+    assert abs(sg[0] - sr[0]) <= 1e-14 * sr[0] and abs(sg[1] - sr[1]) <= 1e-14 * sr[1]   # Gershgorin bound, eps
+    assert int(got.info.item()) == int(ref.info.item()) == 0
+    assert abs(sg[4] - sr[4]) <= 1e-12 * max(1.0, abs(sr[4]))                       # logdet
+    Lr, Lg = _ops.chol_get_factor(ref), _ops.chol_get_factor(got)
+    assert relerr(Lg, Lr) < 1e-10
+    # factorisation + inverse in one call
+    side = torch.cuda.Stream(dev())
+    st2, Kinv2 = _ops.gram_chol_factor(descs, x, side=side)
+    torch.cuda.current_stream().wait_stream(side)
+    st1, Kinv1 = _ops.chol_factor_inverse(K, side)
+    torch.cuda.current_stream().wait_stream(side)
+    assert relerr(torch.tril(Kinv2), torch.tril(Kinv1)) < 1e-9
+    assert relerr(_ops.chol_get_factor(st2), Lr) < 1e-10
+
+
+def test_gram_fused_unsupported_kernels_fall_back():
+    x = torch.rand(3, 200, dtype=torch.float64, device=dev())
+    # Maternp proper (offset 1e-30) without a White term: its diagonal does not take the library path
+    assert _ops.gram_chol_factor([dict(kind=_lib.K_MATERNP, term=0, dimmask=7, ipar=2, par0=1e-30, amp=1.0)], x) is None
+    # Matern of real order: general kernel
+    assert _ops.gram_chol_factor([dict(kind=_lib.K_MATERN, term=0, dimmask=7, par0=1.3, amp=1.0),
+                                  dict(kind=_lib.K_WHITE, term=1, dimmask=7, amp=0.1)], x) is None
+
+
 def test_chol_failure_reporting():
     K = torch.eye(200, dtype=torch.float64, device=dev())
     K[150, 150] = 1e-30

@@ -22,9 +22,8 @@ descs = [dict(kind=_lib.K_MATERNP, term=0, dimmask=7, ipar=2, par0=0.0, scale_x=
 K = _ops.aligned_empty(n, n, dev)
 side = torch.cuda.Stream(dev)
 for _ in range(reps):
-    _ops.gram_iso(descs, xd, xd, out=K, symmetric=True)
     main = torch.cuda.current_stream()
-    st, Kinv = _ops.chol_factor_inverse(K, side)
+    st, Kinv = _ops.gram_chol_factor(descs, xd, side=side)   # Gram fused with the equilibration pass (no K)
     a = _ops.chol_solve(st, yd[:, None], False)
     ldq = _ops.chol_logdet_quad(st, a[:, 0].contiguous())
     b = _ops.chol_solve(st, a, True, inplace=True)

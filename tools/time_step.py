@@ -7,6 +7,7 @@ sys.path.insert(0, '.')
 from lsqfitgp_b200 import _lib, _ops
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+fused = not (len(sys.argv) > 3 and sys.argv[3] == 'unfused')
 dev = torch.device('cuda:0')
 rng = np.random.default_rng(2002)
 X = rng.uniform(0, 10, (n, 3))
@@ -18,9 +19,12 @@ descs = [dict(kind=_lib.K_MATERNP, term=0, dimmask=7, ipar=2, par0=0.0, scale_x=
 K = _ops.aligned_empty(n, n, dev)
 side = torch.cuda.Stream(dev)
 def step():
-    _ops.gram_iso(descs, xd, xd, out=K, symmetric=True)
     main = torch.cuda.current_stream()
-    st, Kinv = _ops.chol_factor_inverse(K, side)
+    if fused:
+        st, Kinv = _ops.gram_chol_factor(descs, xd, side=side)
+    else:
+        _ops.gram_iso(descs, xd, xd, out=K, symmetric=True)
+        st, Kinv = _ops.chol_factor_inverse(K, side)
     a = _ops.chol_solve(st, yd[:, None], False)
     ldq = _ops.chol_logdet_quad(st, a[:, 0].contiguous())
     b = _ops.chol_solve(st, a, True, inplace=True)
@@ -39,4 +43,4 @@ t, (ldq, vjp) = timeit(step, reps)
 _ops.gram_iso(descs, xd, xd, out=K, symmetric=True)
 tf, st = timeit(lambda: _ops.chol_factor(K), reps)
 ti, _ = timeit(lambda: _ops.chol_inverse(st), reps)
-print(f'n={n}: step {t:.2f} ms ({n**3/t/1e9:.2f} TF) | factor alone {tf:.2f} | inverse alone {ti:.2f} | logdet {float(ldq[0]):.10g} vjp0 {float(vjp.ravel()[0]):.8g}')
+print(f'n={n} fused={fused}: step {t:.2f} ms ({n**3/t/1e9:.2f} TF) | factor alone {tf:.2f} | inverse alone {ti:.2f} | logdet {float(ldq[0]):.10g} vjp0 {float(vjp.ravel()[0]):.8g}')
