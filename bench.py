@@ -47,7 +47,7 @@ UNIT = 'evals/s'
 FP64_DMMA_PEAK_FALLBACK = 37.0   # round-1 measurement (profiles/peaks_fp64_r1.log); the line reports the live probe
 
 # DRAM traffic of one lgp_chol_factor call at n=20000 comes from an ncu capture (it cannot be measured in this process)
-CHOL_TRAFFIC_BYTES_N20000 = 82.90e9   # profiles/traffic_chol20k_r2.txt (68.9 GB read + 14.0 GB written)
+CHOL_TRAFFIC_BYTES_N20000 = 47.37e9   # profiles/traffic_chol20k_r2c.txt (33.5 GB read + 13.8 GB written)
 
 
 def make_data(n, seed=2002):
@@ -848,11 +848,11 @@ def run_gpu(args):
                           frac=chol_tflops / dmma_peak,
                           traffic=CHOL_TRAFFIC_BYTES_N20000 if n == 20000 else None,
                           traffic_source='ncu dram__bytes_read.sum + dram__bytes_write.sum over the kernels of one '
-                                         'lgp_chol_factor call at n=20000 (profiles/traffic_chol20k_r2.txt; ncu cannot run '
-                                         'inside this process): 68.9 GB read + 14.0 GB written, captured before the grouped '
-                                         'rasterisation of the lower-triangular tile enumeration; the right-looking updates '
-                                         're-read the trailing matrix once per panel and stream the panel strips; '
-                                         'tensor-bound (0.97 TB/s average)',
+                                         'lgp_chol_factor call at n=20000 (profiles/traffic_chol20k_r2c.txt; ncu cannot run '
+                                         'inside this process): 33.5 GB read + 13.8 GB written (82.9 GB before the grouped '
+                                         'rasterisation of the lower-triangular tile enumeration, profiles/traffic_chol20k_r2.txt); '
+                                         'the right-looking updates re-read the trailing matrix once per panel; '
+                                         'tensor-bound (0.56 TB/s average)',
                           peak_source='measured in THIS run: register-resident DMMA.8x8x4 loop of the library '
                                       '(lgp_peak_probe), sustained over %.1f s; burst %.2f; MEASURED_PEAKS.json has no '
                                       'FP64 entry' % (peaks['dmma_sustained_seconds'], peaks['dmma_burst_TFLOPs']),
