@@ -270,7 +270,15 @@ __device__ __forceinline__ void l3_store_colblock(const double *__restrict__ S, 
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int idx = base + k * NT;
-            if (idx < NEL2) *reinterpret_cast<double2 *>(invd + (c0 + (idx >> 6)) * 128 + 2 * (idx & 63)) = v[k];
+            if (idx < NEL2) {
+                double *dst = invd + (c0 + (idx >> 6)) * 128 + 2 * (idx & 63);
+                if (VEC) {
+                    *reinterpret_cast<double2 *>(dst) = v[k];
+                } else {
+                    dst[0] = v[k].x;
+                    dst[1] = v[k].y;
+                }
+            }
         }
     }
 }
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) potrf_leaf3_kernel(double *__re
     if (tid < 32) l3_mbar_init(bar0 + 8 * tid, 1);
     // lower triangle in, 16-byte loads with eight in flight per thread: block column 0 by everybody (the panel-0 chain
     // starts on it), the other three block columns by the spare warps while panel 0 runs
-    const bool vec = !((ld & 1) | (int64_t)(reinterpret_cast<uintptr_t>(Wblk) & 15));
+    const bool vec = !((ld & 1) | (int64_t)((reinterpret_cast<uintptr_t>(Wblk) | reinterpret_cast<uintptr_t>(invd)) & 15));
     {
         double2 v[8];
 #pragma unroll
