@@ -702,6 +702,25 @@ class GP:
             _timing.mark('decomp')
             self._decompcache[keys] = decomp
             return decomp
+        if (self._solver_name == 'chol' and len(keys) == 1 and ycov is None and not covtransf
+                and isinstance(self._elements[keys[0]], _Points) and self._covfun is not None and self._covfun._terms
+                and not self._covfun._bart and (keys[0], keys[0]) not in self._covblocks and not self._grad_mode()):
+            # one set of points, kernel-only covariance, matrix not built yet: Gram build fused with the equilibration pass
+            # of the factorisation (lgp_gram_iso_prepare), for the kernels of the fast family.  The finiteness check of the
+            # block moves to the points (a finite kernel of finite points is finite); anything else takes the usual path,
+            # which builds the block, checks it and reports the error
+            elem = self._elements[keys[0]]
+            skw = dict(self._solverkw)
+            skw.update(kw)
+            if _fusable(skw) and (not self._checkfinite or bool(torch.all(torch.isfinite(elem.xd)))):
+                descs, _ = self._covfun._descriptor(elem.labels)
+                if all(math.isfinite(float(v)) for d in descs for v in d.values()):
+                    decomp = _linalg.Chol._from_kernel(descs, elem.xd, **skw)
+                    if decomp is not None:
+                        _timing.mark('gp&cov')
+                        _timing.mark('decomp')
+                        self._decompcache[keys] = decomp
+                        return decomp
         Kxx = self._assemblecovblocks(keys)
         if covtransf:
             if ycov is not None:

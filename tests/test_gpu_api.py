@@ -277,6 +277,35 @@ def test_chol_class_battery(n):
     assert rel(o1[1], o2[1]) < 1e-8 and rel(o1[4], o2[4]) < 1e-8
 
 
+def test_value_path_fused_gram_matches_block_path():
+    """ GP._solver on one set of points with a kernel of the fast family: the Gram build is fused with the equilibration
+    pass (no covariance block); same logML, posterior mean and covariance as when the block has been built first (the
+    two-pass path), and the finiteness check still reports non-finite points """
+    rng = np.random.default_rng(12)
+    n = 700
+    X = rng.uniform(0, 10, (n, 2))
+    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(n)
+    x = lgp.unstructured_to_structured(X, names=['a', 'b'])
+    xp = lgp.unstructured_to_structured(rng.uniform(0, 10, (40, 2)), names=['a', 'b'])
+    kern = 1.3 * lgp.Matern(nu=2.5, scale=1.7) + 0.05 * lgp.White()
+    fused = lgp.GP(kern, checkpos=False).addx(x, 'd').addx(xp, 'p')
+    block = lgp.GP(kern, checkpos=False).addx(x, 'd').addx(xp, 'p')
+    block.prior('d', raw=True)                       # builds and caches the block: _solver takes the two-pass path
+    assert ('d', 'd') in block._covblocks and ('d', 'd') not in fused._covblocks
+    ml_f, ml_b = fused.marginal_likelihood({'d': y}), block.marginal_likelihood({'d': y})
+    assert fused._solver(['d'])._K is None and block._solver(['d'])._K is not None
+    assert abs(ml_f - ml_b) <= 1e-12 * abs(ml_b)
+    m_f, c_f = fused.predfromdata({'d': y}, 'p', raw=True)
+    m_b, c_b = block.predfromdata({'d': y}, 'p', raw=True)
+    np.testing.assert_allclose(m_f, m_b, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(c_f, c_b, rtol=1e-9, atol=1e-12)
+    Xbad = X.copy()
+    Xbad[3, 1] = np.nan
+    bad = lgp.GP(kern, checkpos=False).addx(lgp.unstructured_to_structured(Xbad, names=['a', 'b']), 'd')
+    with pytest.raises(RuntimeError, match='not finite'):
+        bad.marginal_likelihood({'d': y})
+
+
 def test_error_semantics():
     with pytest.raises(np.linalg.LinAlgError):
         lgp._linalg.Chol(-np.eye(5))
