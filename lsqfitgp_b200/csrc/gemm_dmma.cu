@@ -1,6 +1,7 @@
 // Launcher for the FP64 DMMA GEMM (see gemm_dmma.cuh).
 #include "gemm_dmma.cuh"
 #include "internal.h"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -105,3 +106,17 @@ int gemm_launch(cudaStream_t stream, bool a_kmaj, bool b_kmaj, int M, int N, int
 }
 
 }  // namespace lgp
+
+// debug hook (not in the public header; host code, no GPU needed): tile (tm, tn) that CTA `b` of a lower-triangular launch
+// with `tiles_m` tile rows works on: the host-side twin of the index arithmetic at the top of gemm_dmma_kernel
+extern "C" int lgp_debug_lower_tile(long long b, int tiles_m, int *out2) {
+    if (b < 0 || tiles_m < 1 || b >= (long long)tiles_m * (tiles_m + 1) / 2 || !out2) return LGP_ERR_BADARG;
+    int tm = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((long long)(tm + 1) * (tm + 2) / 2 <= b) tm++;
+    while ((long long)tm * (tm + 1) / 2 > b) tm--;
+    int tn = (int)(b - (long long)tm * (tm + 1) / 2);
+    lgp::gemm_lower_grouped_tile(b, tm, tiles_m, tm, tn);
+    out2[0] = tm;
+    out2[1] = tn;
+    return LGP_OK;
+}

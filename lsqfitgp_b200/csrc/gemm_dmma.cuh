@@ -242,6 +242,32 @@ __device__ __forceinline__ void gemm_load_frag_mpair(const unsigned char *tile, 
     v_odd = v.y;
 }
 
+// Grouped rasterisation of the lower-triangular tile enumeration (R == 1): bands of GROUP tile rows, inside a band
+// column by column (rows max(tn, r0)..r1 of column tn), so that a wave of CTAs shares GROUP row strips of A and
+// ~wave/GROUP column strips of B out of L2.  Row by row, a wave spans one or two tile rows and streams EVERY column strip
+// of B: with K = 1024 that is 160 MB per tile row at n = 20 000, more than L2 (the trailing updates of one factorisation read
+// 64 GB from DRAM that way, profiles/traffic_chol20k_r2.txt; 28 GB grouped, traffic_chol20k_r2c.txt).  Rows 0..r0-1 hold
+// r0 (r0+1)/2 tiles, so the band of tile b is the band of its row `row` in the row-by-row order.
+__host__ __device__ __forceinline__ void gemm_lower_grouped_tile(long long b, int row, int tiles_m, int &tm, int &tn) {
+    constexpr int GROUP = 16;
+    const int r0 = (row / GROUP) * GROUP;
+    const int gs = (tiles_m - r0) < GROUP ? (tiles_m - r0) : GROUP;
+    int local = (int)(b - (long long)r0 * (r0 + 1) / 2);
+    if (local < r0 * gs) {
+        tn = local / gs;
+        tm = r0 + local % gs;
+    } else {
+        local -= r0 * gs;
+        int c = 0;
+        while (local >= gs - c) {
+            local -= gs - c;
+            c++;
+        }
+        tn = r0 + c;
+        tm = r0 + c + local;
+    }
+}
+
 template <class Cfg, bool A_KMAJ, bool B_KMAJ>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS) gemm_dmma_kernel(const GemmParams p) {
     static_assert(Cfg::MI % 2 == 0 && Cfg::NJ % 2 == 0, "paired m-major fragments need an even number of MMA tiles");
@@ -262,31 +288,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS) gemm_dmma_kernel
         while ((long long)R * (tm + 1) * (tm + 2) / 2 <= b) tm++;
         while ((long long)R * tm * (tm + 1) / 2 > b) tm--;
         tn = (int)(b - (long long)R * tm * (tm + 1) / 2);
-        if (R == 1) {
-            // Grouped rasterisation of the triangle: bands of GROUP tile rows, inside a band column by column (rows
-            // max(tn, r0)..r1 of column tn), so that a wave of CTAs shares GROUP row strips of A and ~wave/GROUP column
-            // strips of B out of L2.  Row by row, a wave spans one or two tile rows and streams EVERY column strip of B:
-            // with K = 1024 that is 160 MB per tile row at n = 20 000, more than L2 (the trailing updates of one
-            // factorisation read 64 GB from DRAM, profiles/traffic_chol20k_r2.txt).  Rows 0..r0-1 hold r0 (r0+1)/2
-            // tiles, so the band of tile b is the band of its row in the row-by-row order.
-            constexpr int GROUP = 16;
-            const int r0 = (tm / GROUP) * GROUP;
-            const int gs = min(GROUP, p.tiles_m - r0);
-            int local = (int)(b - (long long)r0 * (r0 + 1) / 2);
-            if (local < r0 * gs) {
-                tn = local / gs;
-                tm = r0 + local % gs;
-            } else {
-                local -= r0 * gs;
-                int c = 0;
-                while (local >= gs - c) {
-                    local -= gs - c;
-                    c++;
-                }
-                tn = r0 + c;
-                tm = r0 + c + local;
-            }
-        }
+        if (R == 1) gemm_lower_grouped_tile(b, tm, p.tiles_m, tm, tn);
     } else {
         // Grouped rasterisation: the CTAs in flight at any time (one wave = 3 per SM) cover GROUP row tiles x ~wave/GROUP
         // column tiles, so that both operand streams are re-used out of L2.  (With the plain column-of-tiles-fastest

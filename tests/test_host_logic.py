@@ -129,3 +129,23 @@ def test_peer_buffer_addressing():
         pb.flag_addr(0, 64)
     # without a process group the reservation is a no-op
     assert _dist.peer_reserve(5000, 512, 'cpu') is False
+
+
+@pytest.mark.parametrize('tiles', [1, 2, 15, 16, 17, 31, 32, 33, 100, 314])
+def test_lower_triangular_tile_enumeration_is_a_bijection(tiles):
+    """ the grouped rasterisation of the lower-triangular GEMM launches (csrc/gemm_dmma.cuh: bands of 16 tile rows, column
+    by column): every tile on or below the diagonal exactly once, and consecutive CTAs stay inside one band (the locality
+    the grouping exists for).  Host-side twin of the kernel's index arithmetic, no GPU needed. """
+    import ctypes
+    lib = _lib.load()
+    lib.lgp_debug_lower_tile.restype = ctypes.c_int
+    lib.lgp_debug_lower_tile.argtypes = [ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    out = (ctypes.c_int * 2)()
+    seen = []
+    for b in range(tiles * (tiles + 1) // 2):
+        assert lib.lgp_debug_lower_tile(b, tiles, out) == 0
+        seen.append((out[0], out[1]))
+    assert len(set(seen)) == len(seen) and all(0 <= tn <= tm < tiles for tm, tn in seen)
+    bands = [tm // 16 for tm, _ in seen]
+    assert bands == sorted(bands)
+    assert lib.lgp_debug_lower_tile(tiles * (tiles + 1) // 2, tiles, out) != 0
