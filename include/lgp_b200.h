@@ -298,9 +298,10 @@ int lgp_chol_inverse(lgp_stream_t stream, const double *W, int64_t ldw, const do
  * (Chol.__init__ and the invL / invK of minus_log_normal_density, src/lsqfitgp/_linalg/_decomp.py:380-393,466-472).
  * The factorisation runs on `stream` (on return the factor, aux and info are complete in `stream` order, exactly as after
  * lgp_chol_factor); the inverse runs on `inv_stream` (Kinv is complete in `inv_stream` order: make consumers wait for
- * that stream).  The inverse of the leading half of the factor and its product with L21 are started as soon as the panel
- * that finalises those columns has been enqueued, so that they fill the SMs left idle by the panel-chain-bound tail of the
- * factorisation.  inv_stream == stream gives the plain sequential composition.  Arguments as in the two calls. */
+ * that stream).  The inverse starts behind the complete factor; while it runs on `inv_stream` the caller's latency-bound
+ * triangular solves on `stream` overlap its GEMMs.  (Starting the inverse of the leading half behind the half-way panel
+ * was built and measured twice without gain, DESIGN.md section 3: experiment switch LGP_EARLY_INVERSE=1.)
+ * inv_stream == stream gives the plain sequential composition.  Arguments as in the two calls. */
 int lgp_chol_factor_inverse(lgp_stream_t stream, lgp_stream_t inv_stream, const double *K, int64_t ldk,
                             const double *addmat, int64_t ldadd, const double *adddiag, int64_t n, double epsrel,
                             double epsabs, double *W, int64_t ldw, double *aux, int32_t *info, double *scratch,
