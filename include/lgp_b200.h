@@ -274,7 +274,7 @@ int lgp_chol_factor(lgp_stream_t stream, const double *K, int64_t ldk, const dou
 
 /* B (n x m, ldb even, 16-byte aligned) <- L^-1 B (trans=0) or L^-T B (trans=1), L = diag(s) Lt.
  * Replaces jax.scipy.linalg.solve_triangular in _decomp.py:402-403,407-408,419,426,439,467-469.
- * m = 1: ONE kernel per sweep (block rows chained by device flags in ticket order; up to 32 distinct caller streams per
+ * m = 1: ONE kernel per sweep (block rows chained by device flags in ticket order; up to 128 distinct caller streams per
  * device, LGP_ERR_UNSUPPORTED beyond); m > 1: recursion over DMMA GEMMs with the inverted diagonal blocks. */
 int lgp_chol_solve(lgp_stream_t stream, const double *W, int64_t ldw, const double *aux, int64_t n, double *B,
                    int64_t ldb, int64_t m, int trans);
@@ -319,6 +319,8 @@ int lgp_chol_factor_inverse(lgp_stream_t stream, lgp_stream_t inv_stream, const 
  * lgp_chol_factor_prepared / lgp_chol_factor_inverse_prepared on the same stream.
  * work: lgp_gram_prepare_work_doubles(n) doubles (= npad^2 / 64; may alias the `scratch` of the inverse). */
 int64_t lgp_gram_prepare_work_doubles(int64_t n);
+/* 1 if lgp_gram_iso_prepare accepts this kernel descriptor (host-side query, nothing is launched), else 0 */
+int lgp_gram_iso_prepare_supported(const lgp_factor_t *factors, int nfactors, int ndim);
 int lgp_gram_iso_prepare(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,
                          int64_t ldx, int64_t n, double *W, int64_t ldw, double *aux, double *work);
 /* lgp_chol_factor / lgp_chol_factor_inverse on a W / aux pair filled by lgp_gram_iso_prepare: jitter, factorisation (and

@@ -102,6 +102,7 @@ SIGNATURES = {
     'lgp_chol_factor_inverse': (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, _i64, _vp, _vp, _vp, _vp,
                                        _i64]),
     'lgp_gram_prepare_work_doubles': (_i64, [_i64]),
+    'lgp_gram_iso_prepare_supported': (_int, [ctypes.POINTER(Factor), _int, _int]),
     'lgp_gram_iso_prepare': (_int, [_vp, ctypes.POINTER(Factor), _int, _int, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     'lgp_chol_factor_prepared': (_int, [_vp, _i64, _dbl, _dbl, _vp, _i64, _vp, _vp]),
     'lgp_chol_factor_inverse_prepared': (_int, [_vp, _vp, _i64, _dbl, _dbl, _vp, _i64, _vp, _vp, _vp, _vp, _i64]),

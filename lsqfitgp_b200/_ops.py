@@ -464,6 +464,9 @@ def gram_chol_factor(descs, x, side=None, epsrel='auto', epsabs=0.0):
     ndim, n = x.shape
     if ndim < 1 or n < 1:
         return None
+    facs = make_factors(descs)
+    if not lib.lgp_gram_iso_prepare_supported(facs, len(descs), ndim):
+        return None   # (asked before any buffer is allocated)
     x = x.contiguous() if x.stride(1) != 1 else x
     st = FactorState()
     st.n = n
@@ -484,7 +487,6 @@ def gram_chol_factor(descs, x, side=None, epsrel='auto', epsabs=0.0):
         work = scratch
     else:
         work = torch.empty(nwork, dtype=f64, device=x.device)
-    facs = make_factors(descs)
     rc = lib.lgp_gram_iso_prepare(ctypes.c_void_p(main.cuda_stream), facs, len(descs), ndim, ptr(x), x.stride(0), n,
                                   ptr(st.W), st.W.stride(0), ptr(st.aux), ptr(work))
     if rc == -4:

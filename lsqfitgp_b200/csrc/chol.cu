@@ -1009,7 +1009,7 @@ struct TrsvSlot {
     unsigned long long base;
     unsigned epoch;
 };
-constexpr int TRSV_SLOTS = 32;
+constexpr int TRSV_SLOTS = 128;  // (torch hands out at most 65 stream handles per device: default + 2 pools of 32)
 constexpr int TRSV_MAX_BLOCKS = 1 << 16;  // n up to 8.4 million
 
 static int trsv_inplace(cudaStream_t st, const double *W, int64_t ldw, const double *invd, const double *sinv,
@@ -1041,7 +1041,7 @@ static int trsv_inplace(cudaStream_t st, const double *W, int64_t ldw, const dou
         if (!s.used && !free_slot) free_slot = &s;
     }
     if (!slot) {
-        if (!free_slot) return LGP_ERR_UNSUPPORTED;  // more than 32 distinct caller streams on one device
+        if (!free_slot) return LGP_ERR_UNSUPPORTED;  // more than 128 distinct caller streams on one device
         void *p = nullptr;
         const size_t bytes = 256 + (size_t)TRSV_MAX_BLOCKS * sizeof(unsigned);
         if (cudaMalloc(&p, bytes) != cudaSuccess) return LGP_ERR_CUDA;

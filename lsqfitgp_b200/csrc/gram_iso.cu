@@ -1634,16 +1634,28 @@ __global__ void __launch_bounds__(256) gram_prep_rowmax_kernel(const double *__r
                   (unsigned long long)__double_as_longlong(sum));
 }
 
+// dynamic shared memory of the fused kernel (tables, staged points, tile + mirror staging)
+static size_t prepare_smem(const FastDesc &d) {
+    const int tabrep = d.kind == LGP_K_EXPQUAD ? FTabRep<LGP_K_EXPQUAD>::value : 1;
+    return 1024 * tabrep + (d.kind == LGP_K_CAUCHY ? 2048 : 0) +
+           (size_t)(2 + ((d.white_raw && tabrep == 1) ? 2 : 0)) * d.nd * FT * sizeof(double) + (size_t)2 * FT * F2_TS * 8;
+}
+// Does the fused Gram -> equilibration build apply?  Fast family only; the diagonal must take the library (slow) path of
+// the Gram kernel, which gram_prep_diag_kernel reproduces; three CTAs per SM must fit.
+static bool prepare_supported(const FastDesc &d) {
+    const bool family = d.kind == LGP_K_EXPQUAD || (d.kind == LGP_K_MATERNP && d.p >= 0 && d.p <= 3) ||
+                        (d.kind == LGP_K_CAUCHY && d.cauchy_fast);
+    if (!family) return false;
+    if (!(d.has_white || d.kind == LGP_K_EXPQUAD || d.kind == LGP_K_CAUCHY || d.par0 == 0.0)) return false;
+    return prepare_smem(d) <= 77400;
+}
+
 template <int KIND, int P>
 static int launch_prepare(cudaStream_t st, const FastDesc &d, const double *x, int64_t ldx, int64_t n, double *W,
                           int64_t ldw, double *aux, double *work) {
     const int64_t npad = lgp_chol_npad(n);
-    // the diagonal must take the library (slow) path of the Gram kernel, which gram_prep_diag_kernel reproduces
-    if (!(d.has_white || KIND == LGP_K_EXPQUAD || KIND == LGP_K_CAUCHY || d.par0 == 0.0)) return LGP_ERR_UNSUPPORTED;
-    const size_t smem = 1024 * FTabRep<KIND>::value + (KIND == LGP_K_CAUCHY ? 2048 : 0) +
-                        (size_t)(2 + ((d.white_raw && FTabRep<KIND>::value == 1) ? 2 : 0)) * d.nd * FT * sizeof(double) +
-                        (size_t)2 * FT * F2_TS * 8;
-    if (smem > 77400) return LGP_ERR_UNSUPPORTED;
+    if (!prepare_supported(d)) return LGP_ERR_UNSUPPORTED;
+    const size_t smem = prepare_smem(d);
     static DeviceOnce once;
     const int dev = current_device();
     if (dev < 0) return LGP_ERR_CUDA;
@@ -1672,6 +1684,13 @@ extern "C" {
 int64_t lgp_gram_prepare_work_doubles(int64_t n) {
     const int64_t npad = lgp_chol_npad(n);
     return (npad / lgp::FT) * npad;
+}
+
+int lgp_gram_iso_prepare_supported(const lgp_factor_t *factors, int nfactors, int ndim) {
+    using namespace lgp;
+    if (!factors || !(nfactors >= 1 && nfactors <= LGP_MAX_FACTORS && ndim >= 1 && ndim <= LGP_MAX_DIMS)) return 0;
+    FastDesc fd;
+    return (build_fast(factors, nfactors, ndim, fd) && prepare_supported(fd)) ? 1 : 0;
 }
 
 int lgp_gram_iso_prepare(lgp_stream_t stream, const lgp_factor_t *factors, int nfactors, int ndim, const double *x,

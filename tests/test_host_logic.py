@@ -149,3 +149,26 @@ def test_lower_triangular_tile_enumeration_is_a_bijection(tiles):
     bands = [tm // 16 for tm, _ in seen]
     assert bands == sorted(bands)
     assert lib.lgp_debug_lower_tile(tiles * (tiles + 1) // 2, tiles, out) != 0
+
+
+def test_fused_gram_support_query():
+    """ lgp_gram_iso_prepare_supported (host-side, nothing launched): which kernel descriptors the Gram build fused with the
+    equilibration pass accepts: the fast family whose diagonal takes the library path of the Gram kernel """
+    from lsqfitgp_b200 import _ops
+    lib = _lib.load()
+
+    def sup(descs, nd=3):
+        return bool(lib.lgp_gram_iso_prepare_supported(_ops.make_factors(descs), len(descs), nd))
+    white = dict(kind=_lib.K_WHITE, term=1, dimmask=7, amp=0.1)
+    const = dict(kind=_lib.K_CONSTANT, term=2, dimmask=0, amp=0.3)
+    m52 = dict(kind=_lib.K_MATERNP, term=0, dimmask=7, ipar=2, par0=0.0, amp=1.0)
+    assert sup([m52, white]) and sup([m52]) and sup([m52, white, const])
+    assert sup([dict(kind=_lib.K_EXPQUAD, term=0, dimmask=7, amp=2.0)])
+    assert sup([dict(kind=_lib.K_CAUCHY, term=0, dimmask=7, par0=2.0, par1=3.0, amp=1.0), white])
+    assert not sup([dict(m52, par0=1e-30)])                      # Maternp proper without White: fast-path diagonal
+    assert sup([dict(m52, par0=1e-30), white])
+    assert not sup([dict(kind=_lib.K_MATERN, term=0, dimmask=7, par0=1.3, amp=1.0), white])   # real order: general kernel
+    assert not sup([dict(kind=_lib.K_CAUCHY, term=0, dimmask=7, par0=1.5, par1=3.0, amp=1.0)])
+    assert not sup([dict(m52, ipar=5), white])
+    assert not sup([m52, dict(kind=_lib.K_EXPQUAD, term=0, dimmask=7, amp=1.0)])              # product of two cores
+    assert not sup([dict(m52, scale_y=2.0), white])                                           # asymmetric scales
